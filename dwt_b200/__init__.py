@@ -1,0 +1,272 @@
+"""dwt_b200 -- ctypes binding of libdwt_b200.so (the C ABI in include/dwt_b200.h).
+
+This module is the Python-side mirror used by the tests and by bench.py; the product is the shared
+library and the `encode` / `decode` programs built from dwt_b200/host/.  There is no CPU fallback: if
+the library is missing, or no CUDA device is usable, every call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdwt_b200.so")
+
+# every symbol include/dwt_b200.h declares (tests/test_abi.py checks the library exports all of them)
+ABI_SYMBOLS = [
+    "dwt_ctx_create", "dwt_ctx_destroy", "dwt_last_error", "dwt_encode", "dwt_decode", "dwt_free",
+    "dwt_ctx_upload_image", "dwt_ctx_encode_resident", "dwt_ctx_download_stream", "dwt_ctx_upload_stream",
+    "dwt_ctx_decode_resident", "dwt_ctx_download_image", "dwt_ctx_launch_count", "dwt_ctx_sync",
+    "cdf53", "icdf53", "dwt_forward", "dwt_inverse", "dwt_ycocg_from_rgb", "dwt_rgb_from_ycocg",
+    "compute_lengths", "ilog2", "dwt_debug_front_end",
+    "bytes_reader", "bytes_writer", "bytes_count", "close_bytes_reader", "close_bytes_writer", "put_byte",
+    "write_bytes", "get_byte", "read_bytes", "bytes_writer_mem", "bytes_writer_data", "bytes_reader_mem",
+    "bits_reader", "bits_writer", "bits_count", "close_bits_reader", "close_bits_writer", "put_bit", "write_bits",
+    "get_bit", "read_bits",
+    "vli_reader", "vli_writer", "delete_vli_reader", "delete_vli_writer", "vli_put_bit", "vli_get_bit",
+    "vli_write_bits", "vli_read_bits", "put_vli", "get_vli",
+    "rle_reader", "rle_writer", "rle_flush", "delete_rle_reader", "delete_rle_writer", "put_rle", "get_rle",
+    "rle_put_bit", "rle_get_bit",
+]
+
+
+class Stats(C.Structure):
+    _fields_ = [("meta_bits", C.c_longlong), ("root_bits", C.c_longlong), ("total_bits", C.c_longlong),
+                ("kib", C.c_longlong), ("full_bits", C.c_longlong), ("levels", C.c_int), ("planes", C.c_int * 3),
+                ("ms_h2d", C.c_float), ("ms_lift", C.c_float), ("ms_linearize", C.c_float), ("ms_coder", C.c_float),
+                ("ms_d2h", C.c_float), ("ms_total", C.c_float), ("level_reached", C.c_int)]
+
+
+class DwtError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libdwt_b200.so (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DwtError("libdwt_b200.so is not built: run `make` (or __graft_entry__.build()) first")
+    L = C.CDLL(LIB_PATH)
+    vp, ip = C.c_void_p, C.POINTER(C.c_int)
+    u8p = C.POINTER(C.c_uint8)
+    L.dwt_ctx_create.argtypes = [C.c_int]
+    L.dwt_ctx_create.restype = vp
+    L.dwt_ctx_destroy.argtypes = [vp]
+    L.dwt_last_error.restype = C.c_char_p
+    L.dwt_encode.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(u8p), C.POINTER(C.c_size_t),
+                             C.POINTER(Stats)]
+    L.dwt_decode.argtypes = [vp, u8p, C.c_size_t, C.c_int, C.POINTER(u8p), ip, ip, ip, C.POINTER(Stats)]
+    L.dwt_free.argtypes = [vp]
+    L.dwt_ctx_upload_image.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int]
+    L.dwt_ctx_encode_resident.argtypes = [vp, C.c_int, C.POINTER(Stats)]
+    L.dwt_ctx_download_stream.argtypes = [vp, C.POINTER(u8p), C.POINTER(C.c_size_t)]
+    L.dwt_ctx_upload_stream.argtypes = [vp, u8p, C.c_size_t]
+    L.dwt_ctx_decode_resident.argtypes = [vp, C.c_int, C.POINTER(Stats)]
+    L.dwt_ctx_download_image.argtypes = [vp, C.POINTER(u8p), ip, ip, ip]
+    L.dwt_ctx_launch_count.argtypes = [vp]
+    L.dwt_ctx_launch_count.restype = C.c_longlong
+    L.dwt_ctx_sync.argtypes = [vp]
+    L.cdf53.argtypes = [ip, ip, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.cdf53.restype = None
+    L.icdf53.argtypes = [ip, ip, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.icdf53.restype = None
+    L.dwt_forward.argtypes = [ip, ip, C.c_int, C.c_int, C.c_int]
+    L.dwt_inverse.argtypes = [ip, ip, C.c_int, C.c_int, C.c_int]
+    L.dwt_ycocg_from_rgb.argtypes = [ip, C.c_int]
+    L.dwt_rgb_from_ycocg.argtypes = [ip, C.c_int]
+    L.compute_lengths.argtypes = [ip, ip, ip, ip, C.c_int, C.c_int, C.c_int]
+    L.dwt_debug_front_end.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, ip, ip, ip]
+    _lib = L
+    return L
+
+
+def last_error():
+    return (lib().dwt_last_error() or b"").decode()
+
+
+def _u8p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _shape(img):
+    h, w = img.shape[:2]
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    return w, h, ch
+
+
+class Codec:
+    """One device context (dwt_ctx): a CUDA device, a stream and reusable buffers."""
+
+    def __init__(self, device=-1):
+        self._h = lib().dwt_ctx_create(device)
+        if not self._h:
+            raise DwtError("dwt_ctx_create failed: " + last_error())
+        self.stats = Stats()
+
+    def close(self):
+        if self._h:
+            lib().dwt_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- whole-call API (host buffers in, host buffers out)
+    def encode(self, img, capacity=0):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        w, h, ch = _shape(img)
+        out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+        r = lib().dwt_encode(self._h, _u8p(img), w, h, ch, int(capacity), C.byref(out), C.byref(n), C.byref(self.stats))
+        if r:
+            raise DwtError("dwt_encode failed: " + last_error())
+        data = C.string_at(out, n.value)
+        lib().dwt_free(out)
+        return data
+
+    def decode(self, stream, pixels_max=-1):
+        """returns the decoded uint8 image, or None where the reference program exits 1 without output"""
+        buf = np.frombuffer(bytes(stream), dtype=np.uint8)
+        if buf.size == 0:
+            buf = np.zeros(1, dtype=np.uint8)
+            n = 0
+        else:
+            n = buf.size
+        pix, w, h, ch = C.POINTER(C.c_uint8)(), C.c_int(), C.c_int(), C.c_int()
+        r = lib().dwt_decode(self._h, _u8p(buf), n, int(pixels_max), C.byref(pix), C.byref(w), C.byref(h), C.byref(ch),
+                             C.byref(self.stats))
+        if r == 1:
+            return None
+        if r:
+            raise DwtError("dwt_decode failed: " + last_error())
+        shape = (h.value, w.value, 3) if ch.value == 3 else (h.value, w.value)
+        arr = np.frombuffer(C.string_at(pix, int(np.prod(shape))), dtype=np.uint8).reshape(shape).copy()
+        lib().dwt_free(pix)
+        return arr
+
+    # ---- device-resident API (bench.py: inputs already in HBM)
+    def upload_image(self, img):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        w, h, ch = _shape(img)
+        if lib().dwt_ctx_upload_image(self._h, _u8p(img), w, h, ch) or lib().dwt_ctx_sync(self._h):
+            raise DwtError("upload_image failed: " + last_error())
+
+    def encode_resident(self, capacity=0):
+        if lib().dwt_ctx_encode_resident(self._h, int(capacity), C.byref(self.stats)):
+            raise DwtError("encode_resident failed: " + last_error())
+        return self.stats
+
+    def download_stream(self):
+        out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+        if lib().dwt_ctx_download_stream(self._h, C.byref(out), C.byref(n)):
+            raise DwtError("download_stream failed: " + last_error())
+        data = C.string_at(out, n.value)
+        lib().dwt_free(out)
+        return data
+
+    def upload_stream(self, stream):
+        buf = np.frombuffer(bytes(stream), dtype=np.uint8)
+        if lib().dwt_ctx_upload_stream(self._h, _u8p(buf), buf.size) or lib().dwt_ctx_sync(self._h):
+            raise DwtError("upload_stream failed: " + last_error())
+
+    def decode_resident(self, pixels_max=-1):
+        r = lib().dwt_ctx_decode_resident(self._h, int(pixels_max), C.byref(self.stats))
+        if r < 0:
+            raise DwtError("decode_resident failed: " + last_error())
+        return r
+
+    def download_image(self):
+        pix, w, h, ch = C.POINTER(C.c_uint8)(), C.c_int(), C.c_int(), C.c_int()
+        if lib().dwt_ctx_download_image(self._h, C.byref(pix), C.byref(w), C.byref(h), C.byref(ch)):
+            raise DwtError("download_image failed: " + last_error())
+        shape = (h.value, w.value, 3) if ch.value == 3 else (h.value, w.value)
+        arr = np.frombuffer(C.string_at(pix, int(np.prod(shape))), dtype=np.uint8).reshape(shape).copy()
+        lib().dwt_free(pix)
+        return arr
+
+    def launch_count(self):
+        return int(lib().dwt_ctx_launch_count(self._h))
+
+    # ---- parity taps
+    def front_end(self, img):
+        """(pyramid int32 (h,w,ch) in the reference's interleaved Mallat layout, planar (ch, w*h), planes)"""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        w, h, ch = _shape(img)
+        pyr = np.zeros((h, w, ch), dtype=np.int32)
+        lin = np.zeros((ch, w * h), dtype=np.int32)
+        planes = (C.c_int * 3)()
+        if lib().dwt_debug_front_end(self._h, _u8p(img), w, h, ch, _ip(pyr), _ip(lin), planes):
+            raise DwtError("dwt_debug_front_end failed: " + last_error())
+        return pyr, lin, list(planes)[:ch]
+
+
+# ---- transform entry points with the reference's argument meaning (host buffers)
+
+def cdf53(x, N, SO, SI, CH, out_len=None):
+    """reference cdf53(out, in, N, SO, SI, CH): returns (out, in_after) -- `in` is clobbered like the reference"""
+    x = np.ascontiguousarray(x, dtype=np.int32).copy()
+    out = np.zeros(out_len if out_len else x.size, dtype=np.int32)
+    lib().cdf53(_ip(out), _ip(x), N, SO, SI, CH)
+    return out, x
+
+
+def icdf53(x, N, SO, SI, CH, out_len=None):
+    x = np.ascontiguousarray(x, dtype=np.int32).copy()
+    out = np.zeros(out_len if out_len else x.size, dtype=np.int32)
+    lib().icdf53(_ip(out), _ip(x), N, SO, SI, CH)
+    return out
+
+
+def forward(img_int):
+    """`transformation` of encode.c:16-30 on an interleaved int32 (h,w,ch) buffer -> Mallat pyramid"""
+    a = np.ascontiguousarray(img_int, dtype=np.int32)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    h, w, ch = a.shape
+    out = np.zeros_like(a)
+    if lib().dwt_forward(_ip(out), _ip(a), w, h, ch):
+        raise DwtError("dwt_forward failed: " + last_error())
+    return out
+
+
+def inverse(pyr):
+    a = np.ascontiguousarray(pyr, dtype=np.int32)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    h, w, ch = a.shape
+    out = np.zeros_like(a)
+    if lib().dwt_inverse(_ip(out), _ip(a), w, h, ch):
+        raise DwtError("dwt_inverse failed: " + last_error())
+    return out
+
+
+def ycocg_from_rgb(buf):
+    a = np.ascontiguousarray(buf, dtype=np.int32).copy()
+    if lib().dwt_ycocg_from_rgb(_ip(a), a.size // 3):
+        raise DwtError(last_error())
+    return a
+
+
+def rgb_from_ycocg(buf):
+    a = np.ascontiguousarray(buf, dtype=np.int32).copy()
+    if lib().dwt_rgb_from_ycocg(_ip(a), a.size // 3):
+        raise DwtError(last_error())
+    return a
+
+
+def geometry(w, h):
+    arrs = [(C.c_int * 16)() for _ in range(4)]
+    levels = lib().compute_lengths(arrs[0], arrs[1], arrs[2], arrs[3], w, h, 8)
+    lengths, pixels, widths, heights = [list(a)[:levels + 1] for a in arrs]
+    return dict(levels=levels, lengths=lengths, pixels=pixels, widths=widths, heights=heights)

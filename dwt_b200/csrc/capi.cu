@@ -1,0 +1,250 @@
+// capi.cu -- transform entry points of the C ABI: cdf53 / icdf53 (cdf53.h:9,36), the two `transformation`
+// drivers (encode.c:16-30, decode.c:16-30) and the colour transforms (image.h:67-79) on host buffers.
+#include "pipeline.cuh"
+#include "layout.cuh"
+
+#include "dwt_b200.h"
+
+#include <string.h>
+
+
+static thread_local dwt_ctx *g_default_ctx = nullptr;
+
+static dwt_ctx *default_ctx()
+{
+	if (!g_default_ctx)
+		g_default_ctx = dwt_ctx_create(-1);
+	return g_default_ctx;
+}
+
+// root LL in ll[0] (planar, pitch w[0]) + details in pyr -> image
+int ctx_inverse_transform(dwt_ctx *c, int levels_used, bool to_u8, int *planar_out)
+{
+	const Geom &g = c->geom;
+	cudaStream_t st = c->st;
+	const int top = levels_used > 0 ? levels_used : 0;
+	const long long pyr_stride = g.pix[top];
+	const int pyr_pitch = g.w[top];
+	if (levels_used == 0) {
+		// decode.c:258 with levels == 0 still runs one inverse level on the w0 x h0 root, reading the root
+		// itself as a one-level Mallat pyramid
+		LiftLevel p;
+		p.W = g.w[0];
+		p.H = g.h[0];
+		p.channels = g.channels;
+		p.in = c->ll[0].p;
+		p.in_chan_stride = g.pix[0];
+		p.in_pitch = g.w[0];
+		p.pyr = c->ll[0].as<int>();
+		p.pyr_chan_stride = g.pix[0];
+		p.pyr_pitch = g.w[0];
+		p.maxabs = nullptr;
+		int mode = 2;
+		if (to_u8) {
+			p.out = c->img.p;
+			p.out_chan_stride = 0;
+			p.out_pitch = g.w[0];
+			mode = g.channels == 3 ? 0 : 1;
+		} else {
+			p.out = planar_out;
+			p.out_chan_stride = g.pix[0];
+			p.out_pitch = g.w[0];
+		}
+		return lift_inverse_level(p, mode, st, &c->launches);
+	}
+	for (int lv = 1; lv <= levels_used; ++lv) {
+		LiftLevel p;
+		p.W = g.w[lv];
+		p.H = g.h[lv];
+		p.channels = g.channels;
+		p.in = c->ll[(lv - 1) & 1].p;
+		p.in_chan_stride = g.pix[lv - 1];
+		p.in_pitch = g.w[lv - 1];
+		p.pyr = c->pyr.as<int>();
+		p.pyr_chan_stride = pyr_stride;
+		p.pyr_pitch = pyr_pitch;
+		p.maxabs = nullptr;
+		int mode = 2;
+		if (lv == levels_used && to_u8) {
+			p.out = c->img.p;
+			p.out_chan_stride = 0;
+			p.out_pitch = g.w[lv];
+			mode = g.channels == 3 ? 0 : 1;
+		} else if (lv == levels_used) {
+			p.out = planar_out;
+			p.out_chan_stride = g.pix[lv];
+			p.out_pitch = g.w[lv];
+		} else {
+			p.out = c->ll[lv & 1].p;
+			p.out_chan_stride = g.pix[lv];
+			p.out_pitch = g.w[lv];
+		}
+		if (lift_inverse_level(p, mode, st, &c->launches))
+			return -1;
+	}
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ 1-D entry points
+
+static void run_1d(int *out, int *in, int N, int SO, int SI, int CH, bool inverse)
+{
+	dwt_ctx *c = default_ctx();
+	if (!c || N < 2 || CH < 1) {
+		if (!c)
+			fprintf(stderr, "libdwt_b200: %s\n", dwt_last_error());
+		return; // the reference signature has no error path
+	}
+	cudaSetDevice(c->device);
+	cudaStream_t st = c->st;
+	size_t span_in = (size_t)(N - 1) * SI + CH, span_out = (size_t)(N - 1) * SO + CH;
+	int *d_in = nullptr, *d_out = nullptr;
+	if (cudaMalloc(&d_in, span_in * sizeof(int)) != cudaSuccess || cudaMalloc(&d_out, span_out * sizeof(int)) != cudaSuccess) {
+		fprintf(stderr, "libdwt_b200: out of device memory\n");
+		return;
+	}
+	cudaMemcpyAsync(d_in, in, span_in * sizeof(int), cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(d_out, out, span_out * sizeof(int), cudaMemcpyHostToDevice, st); // untouched gaps survive
+	lift_cdf53_1d(d_out, d_in, N, SO, SI, CH, inverse, st);
+	c->launches += 1;
+	cudaMemcpyAsync(out, d_out, span_out * sizeof(int), cudaMemcpyDeviceToHost, st);
+	if (!inverse) // cdf53.h:12-23 lifts in place: the caller sees the lifted samples in `in`
+		cudaMemcpyAsync(in, d_in, span_in * sizeof(int), cudaMemcpyDeviceToHost, st);
+	cudaStreamSynchronize(st);
+	cudaFree(d_in);
+	cudaFree(d_out);
+}
+
+extern "C" void cdf53(int *out, int *in, int N, int SO, int SI, int CH)
+{
+	run_1d(out, in, N, SO, SI, CH, false);
+}
+
+extern "C" void icdf53(int *out, int *in, int N, int SO, int SI, int CH)
+{
+	run_1d(out, in, N, SO, SI, CH, true);
+}
+
+// ------------------------------------------------------------------------------------------------ 2-D drivers
+
+extern "C" int dwt_forward(int *out, const int *in, int W, int H, int CH)
+{
+	dwt_ctx *c = default_ctx();
+	if (!c)
+		return -1;
+	if (W < 2 || H < 2 || CH < 1 || CH > 3) {
+		dwt_set_error("dwt_forward: unsupported shape %dx%dx%d", W, H, CH);
+		return -1;
+	}
+	CUDA_OK(cudaSetDevice(c->device));
+	if (ctx_set_geometry(c, W, H, CH))
+		return -1;
+	const Geom &g = c->geom;
+	const int L = g.levels;
+	cudaStream_t st = c->st;
+	const long long npix = (long long)W * H;
+	const size_t n = (size_t)npix * CH;
+	int *d_a = nullptr, *d_b = nullptr;
+	CUDA_OK(cudaMalloc(&d_a, n * sizeof(int)));
+	CUDA_OK(cudaMalloc(&d_b, n * sizeof(int)));
+	CUDA_OK(cudaMemcpyAsync(d_a, in, n * sizeof(int), cudaMemcpyHostToDevice, st));
+	deinterleave_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_a, d_b, npix, CH);
+	int r = ctx_forward_transform(c, d_b);
+	if (!r) {
+		export_pyramid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->pyr.as<int>(), ctx_root_ll(c), d_a, W, H, CH,
+		                                                                   g.w[0], g.h[0]);
+		c->launches += 2;
+		cudaMemcpyAsync(out, d_a, n * sizeof(int), cudaMemcpyDeviceToHost, st);
+	}
+	cudaError_t e = cudaStreamSynchronize(st);
+	cudaFree(d_a);
+	cudaFree(d_b);
+	(void)L;
+	if (r || e != cudaSuccess) {
+		if (!r)
+			dwt_set_error("dwt_forward: %s", cudaGetErrorString(e));
+		return -1;
+	}
+	return 0;
+}
+
+extern "C" int dwt_inverse(int *out, const int *in, int W, int H, int CH)
+{
+	dwt_ctx *c = default_ctx();
+	if (!c)
+		return -1;
+	if (W < 2 || H < 2 || CH < 1 || CH > 3) {
+		dwt_set_error("dwt_inverse: unsupported shape %dx%dx%d", W, H, CH);
+		return -1;
+	}
+	CUDA_OK(cudaSetDevice(c->device));
+	if (ctx_set_geometry(c, W, H, CH))
+		return -1;
+	const Geom &g = c->geom;
+	const int L = g.levels;
+	cudaStream_t st = c->st;
+	if (ensure_transform_buffers(c))
+		return -1;
+	const long long npix = (long long)W * H;
+	const size_t n = (size_t)npix * CH;
+	int *d_a = nullptr, *d_b = nullptr;
+	CUDA_OK(cudaMalloc(&d_a, n * sizeof(int)));
+	CUDA_OK(cudaMalloc(&d_b, n * sizeof(int)));
+	CUDA_OK(cudaMemcpyAsync(d_a, in, n * sizeof(int), cudaMemcpyHostToDevice, st));
+	// planar pyramid; the root rectangle is copied to ll[0] with its own pitch
+	deinterleave_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_a, c->pyr.as<int>(), npix, CH);
+	for (int ch = 0; ch < CH; ++ch)
+		CUDA_OK(cudaMemcpy2DAsync(c->ll[0].as<int>() + (size_t)ch * g.pix[0], sizeof(int) * g.w[0],
+		                          c->pyr.as<int>() + (size_t)ch * npix, sizeof(int) * W, sizeof(int) * g.w[0], g.h[0],
+		                          cudaMemcpyDeviceToDevice, st));
+	int r = ctx_inverse_transform(c, L, false, d_b);
+	if (!r) {
+		interleave_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_b, d_a, npix, CH);
+		c->launches += 2;
+		cudaMemcpyAsync(out, d_a, n * sizeof(int), cudaMemcpyDeviceToHost, st);
+	}
+	cudaError_t e = cudaStreamSynchronize(st);
+	cudaFree(d_a);
+	cudaFree(d_b);
+	if (r || e != cudaSuccess) {
+		if (!r)
+			dwt_set_error("dwt_inverse: %s", cudaGetErrorString(e));
+		return -1;
+	}
+	return 0;
+}
+
+static int colour_host(int *buffer, int total, bool inverse)
+{
+	dwt_ctx *c = default_ctx();
+	if (!c)
+		return -1;
+	if (total <= 0)
+		return 0;
+	CUDA_OK(cudaSetDevice(c->device));
+	int *d = nullptr;
+	size_t bytes = (size_t)total * 3 * sizeof(int);
+	CUDA_OK(cudaMalloc(&d, bytes));
+	cudaMemcpyAsync(d, buffer, bytes, cudaMemcpyHostToDevice, c->st);
+	int r = lift_colour(d, total, inverse, c->st);
+	c->launches += 1;
+	cudaMemcpyAsync(buffer, d, bytes, cudaMemcpyDeviceToHost, c->st);
+	cudaError_t e = cudaStreamSynchronize(c->st);
+	cudaFree(d);
+	if (r || e != cudaSuccess) {
+		if (!r)
+			dwt_set_error("colour transform: %s", cudaGetErrorString(e));
+		return -1;
+	}
+	return 0;
+}
+
+extern "C" int dwt_ycocg_from_rgb(int *buffer, int total)
+{
+	return colour_host(buffer, total, false);
+}
+
+extern "C" int dwt_rgb_from_ycocg(int *buffer, int total)
+{
+	return colour_host(buffer, total, true);
+}

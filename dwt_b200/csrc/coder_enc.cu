@@ -1,0 +1,570 @@
+// coder_enc.cu -- the bit-plane coder of encode.c:60-95,183-221 + rle.h + vli.h + bits.h as a parallel pipeline.
+//
+// The reference emits one bit at a time through put_rle -> put_vli -> put_bit -> put_byte.  The stream it
+// produces is: for every chunk (channel, level, plane) in schedule order, a
+// significance pass (zero runs, adaptive-Rice coded, each closed by a 1 and followed by a raw sign bit)
+// and a refinement pass (raw bits, preceded by a "phantom one" that closes a pending run).  Runs and the
+// Rice order cross chunk boundaries.  Parallel formulation:
+//
+//   count    per (chunk, tile of 256 groups): #zero symbols, #ones, #refinement bits, from popc on the
+//            bit-sliced store ("already significant" <=> a higher plane has a 1)            [enc_count_kernel]
+//   scan     exclusive prefixes in schedule order; per-chunk token index / run bookkeeping   [enc_scan_kernel,
+//            (flush candidates = phantom ones, final rle_flush token)                         enc_chunk_setup_kernel]
+//   emit     every 1 becomes a token: Z[t] = number of zero symbols before it, so its run is Z[t]-Z[t-1];
+//            sign bits and the dense refinement bit vector are packed with a software pext    [enc_emit_kernel]
+//   orders   the Rice order is a serial recurrence k' = max(ilog2(v + 2^k) - 2, 0).  The maps are monotone
+//            in k, so a tile whose end order agrees for entry orders 0 and 31 is a constant map; tiles are
+//            solved by a block-local fixed-point iteration, the (rare) non-constant tiles are chained
+//            exactly                                                              [enc_vli_tile/resolve/len_kernel]
+//   offsets  exclusive scan of token bit lengths                                           [enc_bitscan_kernel]
+//   scatter  tokens and refinement bits are OR-ed into the zero-initialised stream          [enc_scatter_kernel,
+//                                                                                            enc_refcopy_kernel]
+#include "coder.cuh"
+
+namespace {
+
+constexpr int TG = DWT_TILE_GROUPS;
+constexpr int TT = DWT_TOK_TILE;
+constexpr int TPT = DWT_TOK_PER_THREAD;
+
+__device__ __forceinline__ void tile_coords(const Geom &G, int b, int &c, int &l, int &i)
+{
+	int tpc = G.tbase[G.levels];
+	c = b / tpc;
+	int r = b - c * tpc;
+	l = 0;
+	while (l + 1 < G.levels && r >= G.tbase[l + 1])
+		++l;
+	i = r - G.tbase[l];
+}
+
+__device__ __forceinline__ u32 group_valid_mask(const Geom &G, int l, int g)
+{
+	if (g >= G.G[l])
+		return 0u;
+	long long rem = G.num[l] - (long long)g * 32;
+	return rem >= 32 ? 0xffffffffu : ((1u << (int)rem) - 1u);
+}
+
+// ------------------------------------------------------------------------------------------------ count
+
+__global__ void __launch_bounds__(TG) enc_count_kernel(const __grid_constant__ Geom G, const Sched *__restrict__ S,
+                                                        const u32 *__restrict__ bs, u32 *ent_z, u32 *ent_1, u32 *ent_r)
+{
+	__shared__ u32 acc[DWT_MAX_PLANES][3];
+	int c, l, i;
+	tile_coords(G, blockIdx.x, c, l, i);
+	const int P = S->planes[c];
+	for (int k = threadIdx.x; k < P * 3; k += TG)
+		(&acc[0][0])[k] = 0;
+	__syncthreads();
+	const int g = i * TG + threadIdx.x;
+	const u32 vm = group_valid_mask(G, l, g);
+	const u32 *base = bs + S->bsbase[c] + G.gbase[l] + g;
+	u32 sig = 0;
+	for (int p = P - 1; p >= 0; --p) {
+		u32 B = vm ? __ldg(base + (long long)p * G.GT) : 0u;
+		u32 member = vm & ~sig;
+		u32 n1 = __popc(B & member), nz = __popc(member) - n1, nr = __popc(sig);
+		nz = __reduce_add_sync(0xffffffffu, nz);
+		n1 = __reduce_add_sync(0xffffffffu, n1);
+		nr = __reduce_add_sync(0xffffffffu, nr);
+		if ((threadIdx.x & 31) == 0) {
+			if (nz)
+				atomicAdd(&acc[p][0], nz);
+			if (n1)
+				atomicAdd(&acc[p][1], n1);
+			if (nr)
+				atomicAdd(&acc[p][2], nr);
+		}
+		sig |= B;
+	}
+	__syncthreads();
+	if (threadIdx.x < P) {
+		int j = S->chunk_of[c][l][threadIdx.x];
+		int e = S->ebase[j] + i;
+		ent_z[e] = acc[threadIdx.x][0];
+		ent_1[e] = acc[threadIdx.x][1];
+		ent_r[e] = acc[threadIdx.x][2];
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ scans
+
+__global__ void __launch_bounds__(1024) enc_scan_kernel(u32 *ez, u32 *e1, u32 *er, int n, EncInfo *info)
+{
+	__shared__ u64 ws[32];
+	const int per = (n + 1023) / 1024;
+	const int b = threadIdx.x * per, e = min(b + per, n);
+	u32 *arr[3] = {ez, e1, er};
+	u64 tots[3];
+	for (int a = 0; a < 3; ++a) {
+		u64 s = 0;
+		for (int k = b; k < e; ++k)
+			s += arr[a][k];
+		u64 tot;
+		u64 base = block_exscan_u64(s, ws, &tot);
+		u32 run = (u32)base; // prefixes are used modulo 2^32 (runs are differences)
+		for (int k = b; k < e; ++k) {
+			u32 v = arr[a][k];
+			arr[a][k] = run;
+			run += v;
+		}
+		tots[a] = tot;
+	}
+	if (threadIdx.x == 0) {
+		info->tot_zero = tots[0];
+		info->tot_one = tots[1];
+		info->tot_ref = tots[2];
+		info->error = 0;
+		info->opaque_tiles = 0;
+		if (tots[1] >= 0xfffff000ull || tots[2] >= 0xfffff000ull)
+			info->error = 2; // more than 2^32 tokens / refinement bits: outside the supported range
+	}
+}
+
+__global__ void __launch_bounds__(1024) enc_chunk_setup_kernel(const Sched *__restrict__ S, const u32 *ez, const u32 *e1,
+                                                                const u32 *er, EncChunks *C, EncInfo *info, u32 *Z,
+                                                                u32 *specbuf, u32 max_tokens)
+{
+	__shared__ u64 ws[32];
+	const int J = S->nchunks;
+	const int per = (J + 1 + 1023) / 1024;
+	const int b = threadIdx.x * per, e = min(b + per, J);
+	const u32 tz = (u32)info->tot_zero, t1 = (u32)info->tot_one, tr = (u32)info->tot_ref;
+	u64 nf = 0;
+	for (int j = b; j < e; ++j) {
+		u32 r0 = er[S->ebase[j]], r1 = j + 1 < J ? er[S->ebase[j + 1]] : tr;
+		nf += (r1 != r0);
+	}
+	u64 tot;
+	u64 F = block_exscan_u64(nf, ws, &tot);
+	for (int j = b; j < e; ++j) {
+		const int e0 = S->ebase[j];
+		u32 r0 = er[e0], r1 = j + 1 < J ? er[S->ebase[j + 1]] : tr;
+		u32 o0 = e1[e0], o1 = j + 1 < J ? e1[S->ebase[j + 1]] : t1;
+		u32 z1 = j + 1 < J ? ez[S->ebase[j + 1]] : tz;
+		C->tok_start[j] = o0 + (u32)F;
+		C->tok_adj[j] = (u32)F;
+		C->ref_start[j] = r0;
+		C->nref[j] = r1 - r0;
+		C->ref_pos[j] = 0;
+		if (r1 != r0) { // flush candidate right after the chunk's last 1 (rle.h:79-89)
+			u32 t = o1 + (u32)F;
+			if (t < max_tokens) {
+				Z[t + 1] = z1;
+				atomicOr(specbuf + (t >> 5), 1u << (t & 31));
+			}
+			++F;
+		}
+	}
+	if (threadIdx.x == 0) {
+		u32 tf = t1 + (u32)tot; // final rle_flush token (rle.h:37-40)
+		C->tok_start[J] = tf;
+		C->tok_adj[J] = (u32)tot;
+		C->ref_start[J] = tr;
+		Z[0] = 0;
+		if (tf < max_tokens) {
+			Z[tf + 1] = tz;
+			atomicOr(specbuf + (tf >> 5), 1u << (tf & 31));
+		} else {
+			info->error = 3;
+		}
+		info->ntok = tf + 1;
+		info->ntiles = (tf + 1 + TT - 1) / TT;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ emit
+
+__global__ void __launch_bounds__(TG) enc_emit_kernel(const __grid_constant__ Geom G, const Sched *__restrict__ S,
+                                                       const u32 *__restrict__ bs, const u32 *__restrict__ ez,
+                                                       const u32 *__restrict__ e1, const u32 *__restrict__ er,
+                                                       const EncChunks *__restrict__ C, u32 *Z, u32 *signbuf, u32 *refbuf)
+{
+	__shared__ u64 ws[32];
+	int c, l, i;
+	tile_coords(G, blockIdx.x, c, l, i);
+	const int P = S->planes[c];
+	const int g = i * TG + threadIdx.x;
+	const u32 vm = group_valid_mask(G, l, g);
+	const u32 *base = bs + S->bsbase[c] + G.gbase[l] + g;
+	const u32 sgn = vm ? __ldg(base + (long long)P * G.GT) : 0u;
+	u32 sig = 0;
+	for (int p = P - 1; p >= 0; --p) {
+		u32 B = vm ? __ldg(base + (long long)p * G.GT) : 0u;
+		u32 member = vm & ~sig;
+		u32 ones = B & member, zeros = member & ~B;
+		u32 n1 = __popc(ones), nz = __popc(zeros), nr = __popc(sig);
+		u64 packed = (u64)nz | ((u64)n1 << 21) | ((u64)nr << 42), tot;
+		u64 ex = block_exscan_u64(packed, ws, &tot);
+		const int j = S->chunk_of[c][l][p];
+		const int e = S->ebase[j] + i;
+		if (n1) {
+			u32 zb = ez[e] + (u32)(ex & 0x1fffffu);
+			u32 tb = e1[e] + C->tok_adj[j] + (u32)((ex >> 21) & 0x1fffffu);
+			bits_or(signbuf, tb, bit_compress(sgn, ones), (int)n1);
+			u32 o = ones, t = tb;
+			while (o) {
+				int b = __ffs(o) - 1;
+				Z[t + 1] = zb + __popc(zeros & ((1u << b) - 1u));
+				++t;
+				o &= o - 1;
+			}
+		}
+		if (nr) {
+			u32 rb = er[e] + (u32)(ex >> 42);
+			bits_or(refbuf, rb, bit_compress(B, sig), (int)nr);
+		}
+		sig |= B;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ VLI orders
+
+struct Tok {
+	u32 v[TPT];
+	u32 kinds; // 2 bits per token: 0 = one (+sign), 1 = flush candidate, 2 = final, 3 = inactive
+	u32 signs;
+};
+
+__device__ __forceinline__ void load_tokens(const u32 *__restrict__ Z, const u32 *__restrict__ specbuf,
+                                            const u32 *__restrict__ signbuf, u32 ntok, u32 t0, Tok &T)
+{
+	T.kinds = 0;
+	T.signs = 0;
+	if (t0 >= ntok) {
+		T.kinds = 0xffffu;
+#pragma unroll
+		for (int k = 0; k < TPT; ++k)
+			T.v[k] = 0;
+		return;
+	}
+	const uint4 a = *reinterpret_cast<const uint4 *>(Z + t0), b = *reinterpret_cast<const uint4 *>(Z + t0 + 4);
+	const u32 last = Z[t0 + 8];
+	u32 z[9] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, last};
+	const u32 spec = (specbuf[t0 >> 5] >> (t0 & 31)) & 0xffu;
+	if (signbuf)
+		T.signs = (signbuf[t0 >> 5] >> (t0 & 31)) & 0xffu;
+#pragma unroll
+	for (int k = 0; k < TPT; ++k) {
+		u32 t = t0 + k;
+		T.v[k] = z[k + 1] - z[k];
+		u32 kind = t >= ntok ? 3u : (t == ntok - 1 ? 2u : ((spec >> k) & 1u));
+		if (kind == 3u)
+			T.v[k] = 0;
+		T.kinds |= kind << (2 * k);
+	}
+}
+
+// run the tokens of one thread from order k; returns the order after them and adds their bit lengths
+__device__ __forceinline__ int run_tokens(const Tok &T, int k, u32 *bits)
+{
+	u32 sum = 0;
+#pragma unroll
+	for (int i = 0; i < TPT; ++i) {
+		u32 kind = (T.kinds >> (2 * i)) & 3u;
+		u32 v = T.v[i];
+		if (kind == 3u || (kind == 1u && v == 0))
+			continue; // an empty phantom run emits nothing and leaves the order alone (rle.h:83)
+		int e = vli_e(v, k);
+		sum += 2 * e - k + 1 + (kind == 0u);
+		k = vli_next(e);
+	}
+	if (bits)
+		*bits = sum;
+	return k;
+}
+
+// block-local fixed point: thread t starts from the order thread t-1 ended with; `first` is the tile's entry order
+__device__ __forceinline__ int solve_tile(const Tok &T, int first, unsigned char *ends, int *start_out)
+{
+	int s = threadIdx.x == 0 ? first : 0, e = 0;
+	bool dirty = true;
+	for (;;) {
+		if (dirty)
+			e = run_tokens(T, s, nullptr);
+		ends[threadIdx.x] = (unsigned char)e;
+		__syncthreads();
+		int ns = threadIdx.x == 0 ? first : ends[threadIdx.x - 1];
+		dirty = ns != s;
+		s = ns;
+		if (!__syncthreads_or(dirty))
+			break;
+	}
+	*start_out = s;
+	return e;
+}
+
+__global__ void __launch_bounds__(256) enc_vli_tile_kernel(const u32 *__restrict__ Z, const u32 *__restrict__ specbuf,
+                                                            const EncInfo *__restrict__ info, u32 *tile_lo, u32 *tile_hi)
+{
+	__shared__ unsigned char ends[256];
+	const u32 ntok = info->ntok;
+	const u32 tile = blockIdx.x;
+	if ((u64)tile * TT >= ntok)
+		return;
+	Tok T;
+	load_tokens(Z, specbuf, nullptr, ntok, tile * TT + threadIdx.x * TPT, T);
+	int s;
+	int lo = solve_tile(T, 0, ends, &s);
+	__syncthreads();
+	int hi = solve_tile(T, 31, ends, &s);
+	if (threadIdx.x == 255) {
+		tile_lo[tile] = lo;
+		tile_hi[tile] = hi;
+	}
+}
+
+__global__ void __launch_bounds__(256) enc_vli_resolve_kernel(const u32 *__restrict__ Z, const u32 *__restrict__ specbuf,
+                                                               EncInfo *info, const u32 *tile_lo, const u32 *tile_hi,
+                                                               u32 *tile_start, int k0)
+{
+	__shared__ unsigned char ends[256];
+	__shared__ unsigned char flags[256];
+	const u32 ntok = info->ntok;
+	const int nt = (int)info->ntiles;
+	for (int i = threadIdx.x; i < nt; i += 256) {
+		if (i == 0)
+			tile_start[0] = (u32)k0;
+		if (i + 1 < nt && tile_lo[i] == tile_hi[i])
+			tile_start[i + 1] = tile_lo[i]; // constant map: the entry order does not matter
+	}
+	__syncthreads();
+	u32 nopaque = 0;
+	for (int base = 0; base < nt; base += 256) {
+		int i = base + threadIdx.x;
+		bool op = i + 1 < nt && tile_lo[i] != tile_hi[i];
+		if (!__syncthreads_or(op))
+			continue;
+		flags[threadIdx.x] = op;
+		__syncthreads();
+		for (int w = 0; w < 256; ++w) {
+			if (!flags[w])
+				continue;
+			int tile = base + w;
+			Tok T;
+			load_tokens(Z, specbuf, nullptr, ntok, (u32)tile * TT + threadIdx.x * TPT, T);
+			int first = (int)tile_start[tile], s;
+			int end = solve_tile(T, first, ends, &s);
+			if (threadIdx.x == 255)
+				tile_start[tile + 1] = (u32)end;
+			++nopaque;
+			__syncthreads();
+		}
+	}
+	if (threadIdx.x == 0)
+		info->opaque_tiles = nopaque;
+}
+
+__global__ void __launch_bounds__(256) enc_vli_len_kernel(const u32 *__restrict__ Z, const u32 *__restrict__ specbuf,
+                                                           EncInfo *info, const u32 *__restrict__ tile_start,
+                                                           unsigned char *thr_state, u32 *tile_bits)
+{
+	__shared__ unsigned char ends[256];
+	__shared__ u32 total;
+	const u32 ntok = info->ntok;
+	const u32 tile = blockIdx.x;
+	if ((u64)tile * TT >= ntok)
+		return;
+	if (threadIdx.x == 0)
+		total = 0;
+	Tok T;
+	load_tokens(Z, specbuf, nullptr, ntok, tile * TT + threadIdx.x * TPT, T);
+	bool big = false;
+#pragma unroll
+	for (int k = 0; k < TPT; ++k)
+		big |= T.v[k] >= (1u << 30);
+	if (big)
+		info->error = 4; // run length beyond the reference's int range
+	int s;
+	solve_tile(T, (int)tile_start[tile], ends, &s);
+	thr_state[(size_t)tile * 256 + threadIdx.x] = (unsigned char)s;
+	u32 bits;
+	run_tokens(T, s, &bits);
+	bits = __reduce_add_sync(0xffffffffu, bits);
+	if ((threadIdx.x & 31) == 0)
+		atomicAdd(&total, bits);
+	__syncthreads();
+	if (threadIdx.x == 0)
+		tile_bits[tile] = total;
+}
+
+__global__ void __launch_bounds__(1024) enc_bitscan_kernel(const u32 *tile_bits, u64 *tile_bitbase, EncInfo *info)
+{
+	__shared__ u64 ws[32];
+	const int n = (int)info->ntiles;
+	const int per = (n + 1023) / 1024;
+	const int b = threadIdx.x * per, e = min(b + per, n);
+	u64 s = 0;
+	for (int k = b; k < e; ++k)
+		s += tile_bits[k];
+	u64 tot;
+	u64 run = block_exscan_u64(s, ws, &tot);
+	for (int k = b; k < e; ++k) {
+		tile_bitbase[k] = run;
+		run += tile_bits[k];
+	}
+	if (threadIdx.x == 0)
+		info->tok_bits = tot;
+}
+
+// ------------------------------------------------------------------------------------------------ scatter
+
+__device__ __forceinline__ int chunk_of_index(const u32 *starts, int J, u32 t) // max j in [0,J] with starts[j] <= t
+{
+	int lo = 0, hi = J;
+	while (lo < hi) {
+		int mid = (lo + hi + 1) >> 1;
+		if (starts[mid] <= t)
+			lo = mid;
+		else
+			hi = mid - 1;
+	}
+	return lo;
+}
+
+__global__ void __launch_bounds__(256) enc_scatter_kernel(const u32 *__restrict__ Z, const u32 *__restrict__ specbuf,
+                                                           const u32 *__restrict__ signbuf, EncInfo *info,
+                                                           const unsigned char *__restrict__ thr_state,
+                                                           const u64 *__restrict__ tile_bitbase, EncChunks *C, int J,
+                                                           u32 *out, u64 prefix_bits, u64 limit_bits)
+{
+	__shared__ u64 ws[32];
+	const u32 ntok = info->ntok;
+	const u32 tile = blockIdx.x;
+	if ((u64)tile * TT >= ntok)
+		return;
+	const u32 t0 = tile * TT + threadIdx.x * TPT;
+	Tok T;
+	load_tokens(Z, specbuf, signbuf, ntok, t0, T);
+	int k = thr_state[(size_t)tile * 256 + threadIdx.x];
+	u32 mybits;
+	run_tokens(T, k, &mybits);
+	u64 tot;
+	u64 off = prefix_bits + tile_bitbase[tile] + block_exscan_u64(mybits, ws, &tot);
+	if (t0 >= ntok)
+		return;
+	int j = chunk_of_index(C->tok_start, J, t0);
+#pragma unroll
+	for (int i = 0; i < TPT; ++i) {
+		const u32 t = t0 + i;
+		const u32 kind = (T.kinds >> (2 * i)) & 3u;
+		if (kind == 3u)
+			break;
+		while (j < J && t >= C->tok_start[j + 1])
+			++j;
+		const u32 v = T.v[i];
+		int len = 0;
+		if (!(kind == 1u && v == 0)) {
+			const int e = vli_e(v, k);
+			const int nz = e - k;
+			const u32 payload = v - ((1u << e) - (1u << k));
+			u64 code = (1ull << nz) | ((u64)payload << (nz + 1));
+			len = nz + 1 + e;
+			if (kind == 0u) {
+				code |= (u64)((T.signs >> i) & 1u) << len;
+				++len;
+			}
+			const u64 pos = off + C->ref_start[j];
+			if (pos < limit_bits) {
+				bits_or(out, pos, (u32)code, len < 32 ? len : 32);
+				if (len > 32)
+					bits_or(out, pos + 32, (u32)(code >> 32), len - 32);
+			}
+			k = vli_next(e);
+		}
+		off += len;
+		if (kind == 1u)
+			C->ref_pos[j] = off + C->ref_start[j]; // the chunk's refinement block starts right after the phantom one
+		if (kind == 2u)
+			info->total_bits = off + C->ref_start[j];
+	}
+}
+
+__global__ void __launch_bounds__(256) enc_refcopy_kernel(const u32 *__restrict__ refbuf, const EncChunks *__restrict__ C,
+                                                           int J, u64 tot_ref, u32 *out, u64 limit_bits)
+{
+	const u64 sw = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	u64 pos = sw * 32;
+	if (pos >= tot_ref)
+		return;
+	const u64 end = min(pos + 32, tot_ref);
+	const u32 word = refbuf[sw];
+	int j = chunk_of_index(C->ref_start, J, (u32)pos);
+	while (pos < end) {
+		while (j < J && (u64)C->ref_start[j + 1] <= pos)
+			++j;
+		u64 seg_end = min(end, (u64)C->ref_start[j + 1]);
+		int n = (int)(seg_end - pos);
+		u32 bits = word >> (int)(pos - sw * 32);
+		u64 dst = C->ref_pos[j] + (pos - C->ref_start[j]);
+		if (dst < limit_bits)
+			bits_or(out, dst, bits, n);
+		pos = seg_end;
+	}
+}
+
+} // namespace
+
+int enc_count(const Geom &g, const Sched &hs, const EncBuffers &b, cudaStream_t st, long long *launches)
+{
+	(void)hs;
+	int blocks = g.channels * g.tbase[g.levels];
+	enc_count_kernel<<<blocks, TG, 0, st>>>(g, b.sched, b.bs, b.ent_z, b.ent_1, b.ent_r);
+	++*launches;
+	CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
+int enc_scan_and_setup(const Geom &g, const Sched &hs, const EncBuffers &b, cudaStream_t st, long long *launches)
+{
+	(void)g;
+	(void)hs;
+	enc_scan_kernel<<<1, 1024, 0, st>>>(b.ent_z, b.ent_1, b.ent_r, b.nent, b.info);
+	enc_chunk_setup_kernel<<<1, 1024, 0, st>>>(b.sched, b.ent_z, b.ent_1, b.ent_r, b.chunks, b.info, b.Z, b.specbuf,
+	                                           b.max_tokens);
+	*launches += 2;
+	CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
+int enc_emit(const Geom &g, const Sched &hs, const EncBuffers &b, cudaStream_t st, long long *launches)
+{
+	(void)hs;
+	int blocks = g.channels * g.tbase[g.levels];
+	enc_emit_kernel<<<blocks, TG, 0, st>>>(g, b.sched, b.bs, b.ent_z, b.ent_1, b.ent_r, b.chunks, b.Z, b.signbuf,
+	                                       b.refbuf);
+	++*launches;
+	CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
+int enc_vli_orders(const EncBuffers &b, int k0, cudaStream_t st, long long *launches)
+{
+	// the token count lives on the device: launch for the upper bound, surplus tiles exit at once
+	unsigned tiles = (b.max_tokens + TT - 1) / TT;
+	enc_vli_tile_kernel<<<tiles, 256, 0, st>>>(b.Z, b.specbuf, b.info, b.tile_lo, b.tile_hi);
+	enc_vli_resolve_kernel<<<1, 256, 0, st>>>(b.Z, b.specbuf, b.info, b.tile_lo, b.tile_hi, b.tile_start, k0);
+	enc_vli_len_kernel<<<tiles, 256, 0, st>>>(b.Z, b.specbuf, b.info, b.tile_start, b.thr_state, b.tile_bits);
+	enc_bitscan_kernel<<<1, 1024, 0, st>>>(b.tile_bits, b.tile_bitbase, b.info);
+	*launches += 4;
+	CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
+int enc_scatter(const Sched &hs, const EncBuffers &b, u64 prefix_bits, u64 tot_ref, cudaStream_t st, long long *launches)
+{
+	unsigned tiles = (b.max_tokens + TT - 1) / TT;
+	enc_scatter_kernel<<<tiles, 256, 0, st>>>(b.Z, b.specbuf, b.signbuf, b.info, b.thr_state, b.tile_bitbase, b.chunks,
+	                                          hs.nchunks, b.out, prefix_bits, b.out_limit_bits);
+	++*launches;
+	if (tot_ref) {
+		u64 words = (tot_ref + 31) / 32;
+		enc_refcopy_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(b.refbuf, b.chunks, hs.nchunks, tot_ref, b.out,
+		                                                                      b.out_limit_bits);
+		++*launches;
+	}
+	CUDA_OK(cudaGetLastError());
+	return 0;
+}

@@ -1,0 +1,33 @@
+// hilbert.cuh -- Hilbert-order linearisation of the Mallat pyramid into the bit-sliced coefficient store
+// (encode.c:32-58 + encode.c:112-131) and its inverse (decode.c:32-65 + decode.c:102-117).
+#pragma once
+#include "common.cuh"
+
+// Geometry-only plan: for every detail level the curve is cut into aligned cells of cs x cs positions
+// (cs = min(32, side)); cell_base[cell_off[l] + q] = number of valid positions (inside the level's
+// w x h domain, outside its LL rectangle) that precede cell q on the curve -- the closed-form rank of
+// SURVEY.md App. C.3 evaluated per cell.
+struct HilbertPlan {
+	int cell_off[DWT_MAX_LEVELS + 1];
+	int ncell[DWT_MAX_LEVELS];
+	int cs[DWT_MAX_LEVELS];
+	u32 *cell_base; // device
+};
+
+int hilbert_plan_build(const Geom &g, HilbertPlan *plan, cudaStream_t st, long long *launches);
+void hilbert_plan_free(HilbertPlan *plan);
+
+// pyramid (planar int32 [c][H][W], Mallat layout) -> bit-sliced store.
+// store word (c, p, gAll) = bs[bsbase[c] + p * GT + gAll]; plane index planes[c] holds the sign bits.
+int hilbert_linearize(const Geom &g, const HilbertPlan &plan, const Sched &s, const int *pyr,
+                      long long pyr_chan_stride, int pyr_pitch, u32 *bs, int levels_used, cudaStream_t st,
+                      long long *launches);
+
+// bit-sliced store -> pyramid, adding the dequantisation bias of decode.c:51-58 (missing[c*16+l]).
+// Only detail levels < levels_used are written; the root is written by the caller.
+int hilbert_reconstruct(const Geom &g, const HilbertPlan &plan, const Sched &s, const u32 *bs,
+                        const int *missing_dev /* 48 ints */, int *pyr, long long pyr_chan_stride, int pyr_pitch,
+                        int levels_used, cudaStream_t st, long long *launches);
+
+// bit-sliced store -> planar two's-complement coefficients (tests / debugging): out[c * total + pix[0] + k]
+int hilbert_unslice(const Geom &g, const Sched &s, const u32 *bs, int *planar, long long total, cudaStream_t st);

@@ -1,0 +1,67 @@
+// pipeline.cuh -- the per-device codec context (host orchestration of the kernels)
+#pragma once
+#include "coder.cuh"
+#include "hilbert.cuh"
+#include "lift.cuh"
+
+#include <stddef.h>
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes); // grows (never shrinks); contents are lost on growth
+	void release();
+	template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct PinBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes);
+	void release();
+	template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct dwt_stats;
+
+struct dwt_ctx {
+	int device = 0;
+	cudaStream_t st = nullptr;
+	long long launches = 0;
+	cudaEvent_t ev[8] = {};
+
+	// geometry cache
+	bool have_geom = false;
+	Geom geom;
+	HilbertPlan plan;
+	Sched sched;
+
+	// image / transform buffers
+	DevBuf img;        // u8 interleaved
+	DevBuf pyr;        // planar int32 Mallat pyramid
+	DevBuf ll[2];      // ping-pong LL
+	DevBuf small;      // maxabs[4] | missing[48] | misc
+	int img_w = 0, img_h = 0, img_ch = 0;
+	bool img_resident = false;
+
+	// coder buffers
+	DevBuf bs, sig, ent, Z, signbuf, specbuf, refbuf, tiles, thr_state, chunks, info, dsched, out, stream;
+	DevBuf mem_pref, ref_pref, ones_rank, sign_rank, dstate;
+	PinBuf pin_small, pin_io;
+
+	// last encode result (device resident)
+	size_t out_bytes = 0;      // valid bytes in `out` (already truncated to the capacity)
+	// last decode result
+	int dec_w = 0, dec_h = 0, dec_ch = 0;
+	size_t stream_len = 0;
+	bool stream_resident = false;
+};
+
+int ctx_set_geometry(dwt_ctx *c, int w, int h, int ch);
+void build_schedule(const Geom &g, const int *planes, Sched *s);
+// img (or a planar int32 image when planar_in != NULL) -> pyr (+ root LL in an ll buffer), maxabs in small
+int ctx_forward_transform(dwt_ctx *c, const int *planar_in);
+// root LL in ll[0] + details in pyr (pitch w[levels_used]) -> u8 image in img (to_u8) or planar int32
+int ctx_inverse_transform(dwt_ctx *c, int levels_used, bool to_u8, int *planar_out);
+int ensure_transform_buffers(dwt_ctx *c);
+const int *ctx_root_ll(dwt_ctx *c);      // device pointer to the planar root LL after ctx_forward_transform
