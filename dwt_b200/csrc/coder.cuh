@@ -55,12 +55,16 @@ int enc_scatter(const Sched &hs, const EncBuffers &b, u64 prefix_bits, u64 tot_r
 struct DecState {                 // device-resident cursor of the serial parse (decode.c:187-243)
 	u64 bitpos;                   // next stream bit
 	u64 end_bits;                 // 8 * stream length
+	u64 ref_bitpos;               // where the current chunk's refinement bits start
 	int order;                    // VLI order
 	u32 pending;                  // rle.h:66-77 counter `cnt`
 	int stopped;                  // EOF / corrupt stream reached: later chunks are skipped
 	int level;                    // highest level started
 	int missing[48];
 	u32 n_member, n_ref;          // per-chunk totals (scratch)
+	int ref_valid;                // the refinement pass of the current chunk was reached
+	int chunk_done;               // number of chunks whose parse ran
+	u32 dbg_windows, dbg_iters;   // parse statistics: windows walked, fix-up iterations
 };
 
 struct DecBuffers {

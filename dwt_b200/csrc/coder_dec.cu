@@ -3,12 +3,16 @@
 // Chunks (channel, level, plane) are decoded in schedule order; within a chunk:
 //   prep     per tile of 256 groups: how many coefficients are still insignificant (members of the
 //            significance pass) and how many are already significant (refinement bits)   [dec_prep_kernel]
-//   parse    the significance pass is a chain of [adaptive-Rice run][sign] tokens.  One CTA walks the stream
-//            in windows of 1024 x 64 bits: every thread parses speculatively from the start of its 64-bit
-//            slice, then entries are corrected to the predecessor's exit until nothing changes (the parses
-//            re-synchronise after a few tokens), a scan of the run lengths turns tokens into member ranks,
-//            and ones / signs are set in rank space.  EOF, the run carried across chunks (rle.h:66-77) and the
-//            phantom one before refinement bits (rle.h:91-103) follow the reference exactly [dec_parse_kernel]
+//   parse    the significance pass is a serial chain of [adaptive-Rice run][sign] tokens.  One CTA walks the
+//            stream in windows of 1024 slices of 64 bits.  Every slice is parsed speculatively from its first
+//            two bit offsets at order 0 (at order 0 all tokens have even length, so a chain keeps its parity)
+//            and remembers WHERE its chains had token starts (a 64-bit "visited" mask).  A slice then
+//            classifies each possible exit of its predecessor by looking it up in its masks (exact merge
+//            detection; an exit that joins no chain is parsed on the spot as an extra hypothesis), which
+//            turns the serial chain into a scan over 5-state maps.  Token run lengths are scanned into member
+//            ranks and ones / signs are set in rank space.  EOF, the run carried across chunks
+//            (rle.h:66-77) and the phantom one before refinement bits (rle.h:91-103) follow the reference
+//            exactly.                                                                      [dec_parse_kernel]
 //   deposit  rank-space bits are expanded into the insignificant positions of each group (software pdep),
 //            refinement bits are taken straight from the stream, significance is updated [dec_deposit_kernel]
 #include "coder.cuh"
@@ -16,9 +20,11 @@
 namespace {
 
 constexpr int TG = DWT_TILE_GROUPS;
-constexpr int PT = 1024;        // parse threads
-constexpr int SLICE = 64;       // stream bits per thread and window
-constexpr int DEAD = 255;
+constexpr int PT = 1024;   // parse threads = slices per window
+constexpr int SLICE = 64;  // stream bits per slice; >= the longest token (31 zeros + 1 + 31 payload + sign)
+constexpr int DEAD = 255;  // a chain that cannot continue (EOF inside a token, impossible order)
+constexpr int ABSENT = 254;
+constexpr u32 ST_U = 4;    // "undetermined" chain state (absorbing)
 
 __device__ __forceinline__ u32 group_valid_mask(const Geom &G, int l, int g)
 {
@@ -82,11 +88,18 @@ __device__ __forceinline__ bool read_vli(const u32 *__restrict__ s, u64 end_bits
 	return true;
 }
 
-// speculative run over one slice: parse [VLI][sign] tokens that start before `lim`
-__device__ __forceinline__ void spec_run(const u32 *__restrict__ s, u64 end_bits, u64 lim, u64 &pos, int &k, u64 &csum)
+// Parse the [VLI][sign] tokens that start inside the slice [lo, lo+SLICE), beginning at (pos, k).
+// Returns the exit (first token start at or behind the slice end), the members consumed, and the mask of
+// slice offsets at which this chain had a token start while at order 0.
+__device__ __forceinline__ void run_slice(const u32 *__restrict__ s, u64 end_bits, u64 lo, u64 &pos, int &k, u64 &csum,
+                                          u64 &visited)
 {
+	const u64 lim = lo + SLICE;
 	csum = 0;
+	visited = 0;
 	while (k != DEAD && pos < lim) {
+		if (k == 0)
+			visited |= 1ull << (int)(pos - lo);
 		u64 n, w;
 		int len, kn;
 		if (!read_vli(s, end_bits, pos, k, &n, &len, &kn, &w)) {
@@ -101,18 +114,36 @@ __device__ __forceinline__ void spec_run(const u32 *__restrict__ s, u64 end_bits
 
 enum { EV_NONE = 0, EV_COVERED = 1, EV_PENDING = 2, EV_STOP = 3 };
 
+// chain-state maps: input = hypothesis (0..3) the predecessor slice's chain follows, output = hypothesis this
+// slice's chain follows (0..3) or ST_U.  3 bits per input.
+__device__ __forceinline__ u32 map_apply(u32 m, u32 s)
+{
+	return s >= ST_U ? ST_U : (m >> (3 * s)) & 7u;
+}
+__device__ __forceinline__ u32 map_compose(u32 first, u32 then)
+{
+	u32 r = 0;
+#pragma unroll
+	for (u32 s = 0; s < 4; ++s)
+		r |= map_apply(then, map_apply(first, s)) << (3 * s);
+	return r;
+}
+constexpr u32 MAP_ID = 0u | (1u << 3) | (2u << 6) | (3u << 9);
+
 __global__ void __launch_bounds__(PT) dec_parse_kernel(DecState *st, const u32 *__restrict__ stream,
                                                         const u32 *__restrict__ tile_sums, u32 *tile_base, int ntile,
                                                         u32 *ones_rank, u32 *sign_rank, int chan, int level)
 {
 	__shared__ u64 ws[32];
-	__shared__ u64 x_pos[PT];
-	__shared__ unsigned char x_k[PT];
-	__shared__ int winner;
-	__shared__ u64 f_pos;     // final state written by the winning thread
+	__shared__ u32 wmap[32];
+	__shared__ u32 x_off[4][PT];          // exits of the (up to) four hypotheses of every slice, relative to the window
+	__shared__ unsigned char x_k[4][PT];
+	__shared__ unsigned char sigma[PT];   // hypothesis the true chain follows in every slice
+	__shared__ int first_u, winner;
+	__shared__ u64 f_pos; // final state written by the winning thread
 	__shared__ int f_k, f_event;
 	__shared__ u32 f_pending;
-	const int tid = threadIdx.x;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	if (st->stopped)
 		return;
 
@@ -141,7 +172,6 @@ __global__ void __launch_bounds__(PT) dec_parse_kernel(DecState *st, const u32 *
 			st->n_ref = (u32)tr;
 			if (st->level < level)
 				st->level = level; // decode.c:203,219-220,236-237: the chunk is started
-			winner = PT;
 			f_event = EV_NONE;
 		}
 	}
@@ -154,6 +184,7 @@ __global__ void __launch_bounds__(PT) dec_parse_kernel(DecState *st, const u32 *
 	u32 pending = st->pending;
 	u64 r0 = 0; // members already accounted for
 	bool stop = false;
+	u32 n_windows = 0, n_short = 0;
 	__syncthreads();
 
 	// ---- a run carried in from earlier chunks (rle.h:66-77): (pending-1) zeros, then a one
@@ -166,7 +197,7 @@ __global__ void __launch_bounds__(PT) dec_parse_kernel(DecState *st, const u32 *
 			if (tid == 0)
 				atomicOr(ones_rank + (rk >> 5), 1u << (rk & 31));
 			if (bitpos < end_bits) {
-				if (tid == 0 && ((peek64(stream, bitpos)) & 1ull))
+				if (tid == 0 && (peek64(stream, bitpos) & 1ull))
 					atomicOr(sign_rank + (rk >> 5), 1u << (rk & 31));
 				bitpos += 1;
 			} else {
@@ -179,48 +210,140 @@ __global__ void __launch_bounds__(PT) dec_parse_kernel(DecState *st, const u32 *
 
 	// ---- significance pass: windows of PT slices
 	while (!stop && pending == 0 && r0 < R) {
+		++n_windows;
 		const u64 Rrem = R - r0;
-		const u64 sub_lo = bitpos + (u64)tid * SLICE, sub_hi = sub_lo + SLICE;
-		u64 e_pos = tid == 0 ? bitpos : sub_lo; // entry
-		int e_k = tid == 0 ? order : 0;
-		u64 xp = e_pos, csum = 0;
-		int xk = e_k;
-		bool dirty = true;
-		for (;;) {
-			if (dirty) {
-				xp = e_pos;
-				xk = e_k;
-				spec_run(stream, end_bits, sub_hi, xp, xk, csum);
-			}
-			x_pos[tid] = xp;
-			x_k[tid] = (unsigned char)xk;
-			__syncthreads();
-			if (tid > 0) {
-				u64 np = x_pos[tid - 1];
-				int nk = x_k[tid - 1];
-				dirty = np != e_pos || nk != e_k;
-				e_pos = np;
-				e_k = nk;
+		const u64 wb = bitpos;
+		const u64 sub_lo = wb + (u64)tid * SLICE;
+		u64 hv[4] = {0, 0, 0, 0};      // visited masks of my hypotheses
+		u64 he_pos[4] = {0, 0, 0, 0};  // their entries
+		int he_k[4] = {ABSENT, ABSENT, ABSENT, ABSENT};
+		u64 dummy;
+
+		// (1) two hypotheses per slice: a token starts at slice offset 0 / 1 at order 0 (slice 0 knows the truth)
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			u64 p = tid == 0 ? wb : sub_lo + h;
+			int k = tid == 0 ? order : 0;
+			he_pos[h] = p;
+			he_k[h] = k;
+			if (tid == 0 && h == 1) {
+				x_off[1][0] = x_off[0][0];
+				x_k[1][0] = x_k[0][0];
+				hv[1] = hv[0];
 			} else {
-				dirty = false;
+				run_slice(stream, end_bits, sub_lo, p, k, dummy, hv[h]);
+				x_off[h][tid] = (u32)(p - wb);
+				x_k[h][tid] = (unsigned char)k;
 			}
-			if (!__syncthreads_or(dirty))
-				break;
 		}
-		// member ranks: exclusive scan of the members consumed per slice
+		x_k[2][tid] = ABSENT;
+		x_k[3][tid] = ABSENT;
+		if (tid == 0)
+			first_u = PT;
+		__syncthreads();
+
+		// which of my chains does an entry (p, k) join?  exact: it must coincide with one of their token starts
+		auto classify = [&](u64 p, int k) -> u32 {
+			if (k == DEAD || k == ABSENT || p < sub_lo || p >= sub_lo + SLICE)
+				return ST_U;
+#pragma unroll
+			for (int h = 0; h < 4; ++h) {
+				if (he_k[h] == ABSENT)
+					continue;
+				if (k == 0 && ((hv[h] >> (int)(p - sub_lo)) & 1ull))
+					return (u32)h;
+				if (p == he_pos[h] && k == he_k[h])
+					return (u32)h;
+			}
+			return ST_U;
+		};
+
+		// (2) classify the predecessor's two exits; an exit that joins none of my chains becomes a new hypothesis
+		u32 cls[4] = {ST_U, ST_U, ST_U, ST_U};
+		if (tid > 0) {
+#pragma unroll
+			for (int s = 0; s < 2; ++s) {
+				u64 p = wb + x_off[s][tid - 1];
+				int k = x_k[s][tid - 1];
+				if (k == DEAD)
+					continue;
+				u32 c = classify(p, k);
+				if (c == ST_U && p >= sub_lo && p < sub_lo + SLICE) {
+					const int h = 2 + s;
+					he_pos[h] = p;
+					he_k[h] = k;
+					run_slice(stream, end_bits, sub_lo, p, k, dummy, hv[h]);
+					x_off[h][tid] = (u32)(p - wb);
+					x_k[h][tid] = (unsigned char)k;
+					c = (u32)h;
+				}
+				cls[s] = c;
+			}
+		}
+		__syncthreads();
+		// (3) classify the predecessor's extra hypotheses (no further parsing: an unknown ends the window early)
+		u32 mymap;
+		if (tid > 0) {
+#pragma unroll
+			for (int s = 2; s < 4; ++s) {
+				int k = x_k[s][tid - 1];
+				if (k != ABSENT)
+					cls[s] = classify(wb + x_off[s][tid - 1], k);
+			}
+			mymap = cls[0] | (cls[1] << 3) | (cls[2] << 6) | (cls[3] << 9);
+		} else {
+			mymap = 0; // slice 0 follows its hypothesis 0 (the true entry) whatever comes in
+		}
+		// inclusive scan of the maps: sigma_i = (M_i o ... o M_0)(0)
+		u32 inc = mymap;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			u32 t = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= d)
+				inc = map_compose(t, inc);
+		}
+		if (lane == 31)
+			wmap[wid] = inc;
+		__syncthreads();
+		u32 pre = MAP_ID;
+		for (int i = 0; i < wid; ++i)
+			pre = map_compose(pre, wmap[i]);
+		const u32 sg = map_apply(map_compose(pre, inc), 0);
+		sigma[tid] = (unsigned char)sg;
+		if (sg == ST_U)
+			atomicMin(&first_u, tid);
+		if (tid == 0)
+			winner = PT;
+		__syncthreads();
+		const int J = first_u; // slices [0, J) have an exact entry
+		if (J < PT)
+			++n_short;
+
+		// (4) count pass from the exact entry, scan into member ranks, then the walk that writes ones and signs
+		u64 e_pos = wb;
+		int e_k = order;
+		if (tid > 0 && tid < J) {
+			const int sp = sigma[tid - 1];
+			e_pos = wb + x_off[sp][tid - 1];
+			e_k = x_k[sp][tid - 1];
+		}
+		u64 csum = 0;
+		if (tid < J) {
+			u64 p = e_pos, v;
+			int k = e_k;
+			run_slice(stream, end_bits, sub_lo, p, k, csum, v);
+		}
 		u64 total;
-		u64 cum = block_exscan_u64(csum, ws, &total);
-		// final walk with output
+		u64 cum = block_exscan_u64(csum, ws, &total); // members consumed before this slice (syncs inside)
 		{
 			u64 pos = e_pos;
-			int k = e_k;
+			int k = tid < J ? e_k : DEAD;
 			int ev = EV_NONE;
 			u64 ev_pos = 0;
 			int ev_k = 0;
 			u32 ev_pending = 0;
-			if (k == DEAD && (tid == 0 || x_k[tid - 1] == DEAD) && tid == 0)
-				ev = EV_STOP;
-			while (k != DEAD && pos < sub_hi) {
+			const u64 lim = sub_lo + SLICE;
+			while (k != DEAD && pos < lim) {
 				if (cum >= Rrem) {
 					ev = EV_COVERED;
 					ev_pos = pos;
@@ -238,7 +361,7 @@ __global__ void __launch_bounds__(PT) dec_parse_kernel(DecState *st, const u32 *
 					const u64 rk = r0 + one;
 					atomicOr(ones_rank + (rk >> 5), 1u << (rk & 31));
 					if (pos + len + 1 > end_bits) {
-						ev = EV_STOP; // sign bit beyond EOF
+						ev = EV_STOP; // sign bit beyond EOF: the magnitude bit stays
 						break;
 					}
 					if ((w >> len) & 1ull)
@@ -276,9 +399,12 @@ __global__ void __launch_bounds__(PT) dec_parse_kernel(DecState *st, const u32 *
 			}
 			break;
 		}
-		// no end inside this window: continue behind the last slice
-		bitpos = x_pos[PT - 1];
-		order = x_k[PT - 1];
+		// no end inside this window: continue behind the last exact slice
+		{
+			const int sl = sigma[J - 1];
+			bitpos = wb + x_off[sl][J - 1];
+			order = x_k[sl][J - 1];
+		}
 		r0 += total;
 		__syncthreads();
 		if (order == DEAD) {
@@ -289,16 +415,19 @@ __global__ void __launch_bounds__(PT) dec_parse_kernel(DecState *st, const u32 *
 
 	// ---- refinement pass (raw bits) and bookkeeping, decode.c:89-98,206,223,240
 	if (tid == 0) {
-		bool complete = !stop;
+		const bool sig_done = !stop; // every member has its symbol (or is covered by the carried run)
+		bool complete = sig_done;
+		int ref_valid = 0;
 		u64 ref_pos = bitpos;
-		if (!stop && nref > 0) {
+		if (sig_done && nref > 0) {
 			if (pending > 1) {
-				stop = true; // rle.h:98-99: a pending run must end exactly here
+				stop = true; // rle.h:98-99: a pending run must end exactly at the phantom one
 				complete = false;
 			} else {
-				pending = 0; // the phantom one
+				pending = 0;
+				ref_valid = 1;
 				if (bitpos + nref > end_bits) {
-					stop = true;
+					stop = true; // partial refinement: the deposit keeps the bits before EOF
 					complete = false;
 				} else {
 					bitpos += nref;
@@ -306,16 +435,14 @@ __global__ void __launch_bounds__(PT) dec_parse_kernel(DecState *st, const u32 *
 			}
 		}
 		st->ref_bitpos = ref_pos;
-		st->ref_valid = (!stop || ref_pos < end_bits) && nref > 0 && (complete || bitpos == ref_pos) ? 1 : 0;
-		if (!complete && nref > 0 && pending <= 1 && ref_pos <= end_bits)
-			st->ref_valid = 1; // partial refinement: bits before EOF are kept, the deposit clips at end_bits
-		if (stop && (r0 < R || pending > 1))
-			st->ref_valid = 0; // the refinement pass was never reached
+		st->ref_valid = ref_valid;
 		st->bitpos = bitpos;
 		st->order = order == DEAD ? 0 : order;
 		st->pending = pending;
 		st->stopped = stop ? 1 : 0;
 		st->chunk_done += 1;
+		st->dbg_windows += n_windows;
+		st->dbg_iters += n_short;
 		if (complete)
 			st->missing[chan * 16 + level] -= 1;
 	}

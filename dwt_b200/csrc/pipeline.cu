@@ -123,6 +123,7 @@ extern "C" void dwt_ctx_destroy(dwt_ctx *c)
 		b->release();
 	c->pin_small.release();
 	c->pin_io.release();
+	c->pin_stream.release();
 	hilbert_plan_free(&c->plan);
 	for (auto &e : c->ev)
 		cudaEventDestroy(e);

@@ -47,7 +47,7 @@ struct dwt_ctx {
 	// coder buffers
 	DevBuf bs, sig, ent, Z, signbuf, specbuf, refbuf, tiles, thr_state, chunks, info, dsched, out, stream;
 	DevBuf mem_pref, ref_pref, ones_rank, sign_rank, dstate;
-	PinBuf pin_small, pin_io;
+	PinBuf pin_small, pin_io, pin_stream;
 
 	// last encode result (device resident)
 	size_t out_bytes = 0;      // valid bytes in `out` (already truncated to the capacity)

@@ -1,7 +1,311 @@
-// pipeline_dec.cu -- placeholder until the decoder lands
+// pipeline_dec.cu -- decode side of the C ABI (include/dwt_b200.h).
+//
+// Host orchestration mirrors main() of decode.c:136-268: magic + size (decode.c:145-159), geometry, the
+// optional PIXELS limit (decode.c:165-171), root image and plane counts (decode.c:119-134,180-186; host,
+// through the reference-shaped stream entry points), then the chunk schedule of decode.c:187-243 on the GPU
+// with a device-resident cursor (bit position, Rice order, pending run, missing[], level), and finally
+// reconstruction + inverse lifting + inverse colour for the resolution the stream reached (decode.c:249-263).
 #include "pipeline.cuh"
+
+#include "../host/streamio_internal.h"
 #include "dwt_b200.h"
-extern "C" int dwt_ctx_upload_stream(dwt_ctx *, const uint8_t *, size_t) { dwt_set_error("decoder not built yet"); return -1; }
-extern "C" int dwt_ctx_decode_resident(dwt_ctx *, int, struct dwt_stats *) { dwt_set_error("decoder not built yet"); return -1; }
-extern "C" int dwt_ctx_download_image(dwt_ctx *, uint8_t **, int *, int *, int *) { dwt_set_error("decoder not built yet"); return -1; }
-extern "C" int dwt_decode(dwt_ctx *, const uint8_t *, size_t, int, uint8_t **, int *, int *, int *, struct dwt_stats *) { dwt_set_error("decoder not built yet"); return -1; }
+
+#include <stdlib.h>
+#include <string.h>
+
+static inline size_t round_up(size_t v, size_t a)
+{
+	return (v + a - 1) / a * a;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b)
+{
+	float ms = 0.f;
+	if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) {
+		cudaGetLastError();
+		return 0.f;
+	}
+	return ms;
+}
+
+extern "C" int dwt_ctx_upload_stream(dwt_ctx *c, const uint8_t *stream, size_t len)
+{
+	if (!c) {
+		dwt_set_error("null context");
+		return -1;
+	}
+	CUDA_OK(cudaSetDevice(c->device));
+	const size_t room = round_up(len, 4) + 64;
+	if (c->stream.ensure(room) || c->pin_stream.ensure(len + 16))
+		return -1;
+	// the parse peeks up to 12 bytes past its position: keep the tail zeroed
+	CUDA_OK(cudaMemsetAsync((char *)c->stream.p + (len / 4) * 4, 0, room - (len / 4) * 4, c->st));
+	if (len) {
+		memcpy(c->pin_stream.p, stream, len);
+		CUDA_OK(cudaMemcpyAsync(c->stream.p, c->pin_stream.p, len, cudaMemcpyHostToDevice, c->st));
+	}
+	c->stream_len = len;
+	c->stream_resident = true;
+	return 0;
+}
+
+// chunk list of decode.c:199-243: the encoder's order, cut where a level loop reaches l >= levels_max
+static int decode_schedule_length(const Geom &g, const Sched &S, int levels_max)
+{
+	if (levels_max >= g.levels)
+		return S.nchunks;
+	if (levels_max <= 0)
+		return 0;
+	// walk the same loops and count the chunks emitted before the first l >= levels_max
+	int planes_max = 0;
+	for (int c = 0; c < g.channels; ++c)
+		if (S.planes[c] > planes_max)
+			planes_max = S.planes[c];
+	if (planes_max == 0)
+		return 0;
+	const int levels = g.levels;
+	const int maximum = levels > planes_max ? levels : planes_max;
+	const int layers_max = 2 * maximum - 1;
+	int n = 0;
+	if (planes_max == S.planes[0])
+		++n;
+	for (int layers = 0; layers < layers_max; ++layers) {
+		for (int l = 0; l < levels && l <= layers + 1; ++l) {
+			if (l >= levels_max)
+				return n;
+			int p = planes_max - 1 - (layers + 1 - l);
+			if (p >= 0 && p < S.planes[0])
+				++n;
+		}
+		for (int l = 0; l < levels && l <= layers; ++l) {
+			if (l >= levels_max)
+				return n;
+			int p = planes_max - 1 - (layers - l);
+			for (int c = 1; c < g.channels; ++c)
+				if (p >= 0 && p < S.planes[c])
+					++n;
+		}
+	}
+	return n;
+}
+
+extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_stats *stt)
+{
+	if (!c || !c->stream_resident) {
+		dwt_set_error("no stream uploaded");
+		return -1;
+	}
+	CUDA_OK(cudaSetDevice(c->device));
+	cudaStream_t st = c->st;
+	// ---- header + root image + plane counts on the host (the bytes are still in the pinned staging buffer)
+	const uint8_t *bytes = c->pin_stream.as<uint8_t>();
+	const size_t len = c->stream_len;
+	struct bytes_reader *br = bytes_reader_mem(bytes, len);
+	int width = 0, height = 0;
+	int letter = get_byte(br);
+	int number = letter == 'W' ? get_byte(br) : -1;
+	if (letter != 'W' || (number != '5' && number != '6') || read_bytes(br, &width, 2) || read_bytes(br, &height, 2)) {
+		close_bytes_reader(br);
+		return 1; // decode.c:145-156
+	}
+	++width;
+	++height;
+	if (width < 8 || height < 8) {
+		close_bytes_reader(br);
+		return 1; // decode.c:157-159
+	}
+	const int C = number == '6' ? 3 : 1;
+	if (ctx_set_geometry(c, width, height, C)) {
+		close_bytes_reader(br);
+		return -1;
+	}
+	const Geom &g = c->geom;
+	const int L = g.levels;
+	int levels_max = L;
+	if (pixels_max >= 0)
+		while (levels_max > 0 && g.pix[levels_max] > pixels_max)
+			--levels_max; // decode.c:165-171
+	struct bits_reader *bits = bits_reader(br);
+	struct vli_reader *vli = vli_reader(bits);
+	const int nroot = (int)g.pix[0];
+	if (c->pin_small.ensure(sizeof(int) * (size_t)(nroot * C + 64) + sizeof(DecState) + 64)) {
+		return -1;
+	}
+	int *h_root = c->pin_small.as<int>();
+	memset(h_root, 0, sizeof(int) * (size_t)nroot * C);
+	int planes[3] = {0, 0, 0};
+	bool bad = false;
+	for (int ch = 0; ch < C && !bad; ++ch) { // decode_root decode.c:119-134
+		int cnt = get_vli(vli);
+		if (cnt < 0) {
+			bad = true;
+			break;
+		}
+		for (int i = 0; cnt && i < nroot; ++i) {
+			int v = 0, r = 0;
+			if (vli_read_bits(vli, &v, cnt)) {
+				bad = true;
+				break;
+			}
+			if (v && (r = vli_get_bit(vli)) > 0)
+				v = -v;
+			if (r < 0) {
+				bad = true;
+				break;
+			}
+			h_root[ch * nroot + i] = v;
+		}
+	}
+	for (int ch = 0; ch < C && !bad; ++ch)
+		if ((planes[ch] = get_vli(vli)) < 0)
+			bad = true; // decode.c:183-186
+	const int k0 = dwt_vli_reader_order(vli);
+	const long long b0 = dwt_bits_reader_position(bits);
+	delete_vli_reader(vli);
+	close_bits_reader(bits);
+	close_bytes_reader(br);
+	if (bad)
+		return 1;
+	int planes_max = 0;
+	for (int ch = 0; ch < C; ++ch) {
+		if (planes[ch] > planes_max)
+			planes_max = planes[ch];
+		if (planes[ch] > DWT_MAX_PLANES - 1) {
+			dwt_set_error("stream declares %d bit planes: outside the reference's range", planes[ch]);
+			return -1;
+		}
+	}
+	CUDA_OK(cudaEventRecord(c->ev[0], st));
+	build_schedule(g, planes, &c->sched);
+	const Sched &S = c->sched;
+	const int nchunks = decode_schedule_length(g, S, levels_max);
+
+	// ---- device state
+	DecState *h_state = (DecState *)(((uintptr_t)(h_root + nroot * C + 8) + 15) & ~(uintptr_t)15);
+	memset(h_state, 0, sizeof(DecState));
+	h_state->bitpos = (u64)b0;
+	h_state->end_bits = (u64)len * 8;
+	h_state->order = k0;
+	h_state->level = -1;
+	for (int ch = 0; ch < C; ++ch)
+		for (int l = 0; l < L; ++l)
+			h_state->missing[ch * 16 + l] = planes[ch];
+	int level = -1;
+	if (planes_max == 0) {
+		// all-zero detail: the reference decodes one pseudo plane of the coarsest luma
+		// level; whatever the stream holds there, every coefficient stays zero and `level` becomes 0
+		if (levels_max > 0)
+			level = 0;
+	} else if (nchunks > 0) {
+		const size_t bs_words = (size_t)S.bsbase[C];
+		const size_t sig_words = (size_t)g.GT * C;
+		int gmax = 0, tmax = 0;
+		for (int l = 0; l < L; ++l) {
+			if (g.G[l] > gmax)
+				gmax = g.G[l];
+			if (g.ntile[l] > tmax)
+				tmax = g.ntile[l];
+		}
+		if (c->bs.ensure(bs_words * 4 + 64) || c->sig.ensure(sig_words * 4 + 64) || c->dstate.ensure(sizeof(DecState)) ||
+		    c->mem_pref.ensure((size_t)tmax * 8 + 64) || c->ref_pref.ensure((size_t)tmax * 8 + 64) ||
+		    c->ones_rank.ensure((size_t)gmax * 4 + 64) || c->sign_rank.ensure((size_t)gmax * 4 + 64))
+			return -1;
+		CUDA_OK(cudaMemsetAsync(c->bs.p, 0, bs_words * 4, st));
+		CUDA_OK(cudaMemsetAsync(c->sig.p, 0, sig_words * 4, st));
+		CUDA_OK(cudaMemcpyAsync(c->dstate.p, h_state, sizeof(DecState), cudaMemcpyHostToDevice, st));
+		DecBuffers b;
+		b.bs = c->bs.as<u32>();
+		b.sig = c->sig.as<u32>();
+		b.stream = c->stream.as<u32>();
+		b.mem_pref = c->mem_pref.as<u32>();
+		b.ref_pref = c->ref_pref.as<u32>();
+		b.ones_rank = c->ones_rank.as<u32>();
+		b.sign_rank = c->sign_rank.as<u32>();
+		b.state = c->dstate.as<DecState>();
+		for (int j = 0; j < nchunks; ++j)
+			if (dec_chunk(g, S, b, j, st, &c->launches))
+				return -1;
+		CUDA_OK(cudaMemcpyAsync(h_state, c->dstate.p, sizeof(DecState), cudaMemcpyDeviceToHost, st));
+		CUDA_OK(cudaEventRecord(c->ev[1], st));
+		CUDA_OK(cudaStreamSynchronize(st));
+		level = h_state->level;
+	}
+	if (planes_max == 0 || nchunks == 0)
+		CUDA_OK(cudaEventRecord(c->ev[1], st));
+
+	// ---- reconstruction for the resolution reached (decode.c:249-263)
+	const int levels_used = level + 1;
+	const int ow = g.w[levels_used], oh = g.h[levels_used];
+	if (ensure_transform_buffers(c))
+		return -1;
+	if (c->img.ensure((size_t)ow * oh * C + 16))
+		return -1;
+	CUDA_OK(cudaMemcpyAsync(c->ll[0].p, h_root, sizeof(int) * (size_t)nroot * C, cudaMemcpyHostToDevice, st));
+	if (levels_used > 0) {
+		int *d_missing = c->small.as<int>() + 16;
+		CUDA_OK(cudaMemcpyAsync(d_missing, h_state->missing, sizeof(int) * 48, cudaMemcpyHostToDevice, st));
+		if (planes_max == 0) {
+			// no coefficient was coded: the detail bands of the levels used are all zero
+			CUDA_OK(cudaMemsetAsync(c->pyr.p, 0, sizeof(int) * (size_t)g.pix[levels_used] * C, st));
+		} else if (hilbert_reconstruct(g, c->plan, S, c->bs.as<u32>(), d_missing, c->pyr.as<int>(), g.pix[levels_used], ow,
+		                               levels_used, st, &c->launches)) {
+			return -1;
+		}
+	}
+	CUDA_OK(cudaEventRecord(c->ev[2], st));
+	if (ctx_inverse_transform(c, levels_used, true, nullptr))
+		return -1;
+	CUDA_OK(cudaEventRecord(c->ev[3], st));
+	CUDA_OK(cudaStreamSynchronize(st));
+	c->dec_w = ow;
+	c->dec_h = oh;
+	c->dec_ch = C;
+	if (stt) {
+		memset(stt, 0, sizeof(*stt));
+		stt->levels = L;
+		for (int ch = 0; ch < 3; ++ch)
+			stt->planes[ch] = planes[ch];
+		stt->level_reached = level;
+		stt->ms_coder = ev_ms(c->ev[0], c->ev[1]);
+		stt->ms_linearize = ev_ms(c->ev[1], c->ev[2]);
+		stt->ms_lift = ev_ms(c->ev[2], c->ev[3]);
+		stt->ms_total = ev_ms(c->ev[0], c->ev[3]);
+		stt->full_bits = (long long)h_state->bitpos;
+		stt->meta_bits = h_state->dbg_windows;
+		stt->root_bits = h_state->dbg_iters;
+	}
+	return 0;
+}
+
+extern "C" int dwt_ctx_download_image(dwt_ctx *c, uint8_t **pixels, int *width, int *height, int *channels)
+{
+	CUDA_OK(cudaSetDevice(c->device));
+	const size_t n = (size_t)c->dec_w * c->dec_h * c->dec_ch;
+	uint8_t *buf = (uint8_t *)malloc(n ? n : 1);
+	if (!buf) {
+		dwt_set_error("out of host memory");
+		return -1;
+	}
+	CUDA_OK(cudaMemcpyAsync(buf, c->img.p, n, cudaMemcpyDeviceToHost, c->st));
+	CUDA_OK(cudaStreamSynchronize(c->st));
+	*pixels = buf;
+	*width = c->dec_w;
+	*height = c->dec_h;
+	*channels = c->dec_ch;
+	return 0;
+}
+
+extern "C" int dwt_decode(dwt_ctx *c, const uint8_t *stream, size_t len, int pixels_max, uint8_t **pixels, int *width,
+                          int *height, int *channels, struct dwt_stats *stats)
+{
+	if (!c) {
+		dwt_set_error("null context (no CUDA device?)");
+		return -1;
+	}
+	if (dwt_ctx_upload_stream(c, stream, len))
+		return -1;
+	int r = dwt_ctx_decode_resident(c, pixels_max, stats);
+	if (r)
+		return r;
+	return dwt_ctx_download_image(c, pixels, width, height, channels);
+}
