@@ -64,16 +64,25 @@ struct DecState {                 // device-resident cursor of the serial parse 
 	u32 n_member, n_ref;          // per-chunk totals (scratch)
 	int ref_valid;                // the refinement pass of the current chunk was reached
 	int chunk_done;               // number of chunks whose parse ran
-	u32 dbg_windows, dbg_iters;   // parse statistics: windows walked, fix-up iterations
+	u64 c_bitpos;                 // snapshot of (bitpos, order, pending) at the start of the current chunk
+	int c_order;
+	u32 c_pending;
+	u32 ticket;                   // parse windows handed out so far (reset per chunk)
+	int done;                     // the chunk's significance pass has found its end
+	u32 dbg_windows, dbg_iters, dbg_walk; // parse statistics: windows up to the end, fix-up iterations, walk steps
 };
 
 struct DecBuffers {
 	u32 *bs;              // bit-sliced store being filled
 	u32 *sig;             // significance words [c][GT]
-	const u32 *stream;    // stream words (zero padded by >= 16 bytes)
-	u32 *mem_pref, *ref_pref; // per group exclusive prefixes of member / refinement counts (one level)
-	u32 *ones_rank, *sign_rank; // rank-space bit vectors of the current chunk
+	const u32 *stream;    // stream words (zero padded by >= 64 bytes)
+	u32 *tile_sums, *tile_base; // per tile (member, refinement) counts and their exclusive prefixes (one level)
+	u32 *ones_rank, *sign_rank; // rank-space bit vectors of the current chunk (adjacent: one memset)
+	u64 *win_state, *win_rank;  // per parse window: published exit state / inclusive member count
+	int nwin_cap;
+	int parse_ctas;       // persistent parse CTAs (one per SM)
 	DecState *state;
 };
 
+int dec_setup(void);  // one-time kernel attribute setup
 int dec_chunk(const Geom &g, const Sched &hs, const DecBuffers &b, int j, cudaStream_t st, long long *launches);

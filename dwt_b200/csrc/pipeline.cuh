@@ -46,7 +46,9 @@ struct dwt_ctx {
 
 	// coder buffers
 	DevBuf bs, sig, ent, Z, signbuf, specbuf, refbuf, tiles, thr_state, chunks, info, dsched, out, stream;
-	DevBuf mem_pref, ref_pref, ones_rank, sign_rank, dstate;
+	DevBuf mem_pref, ref_pref, ones_rank, sign_rank, dstate, win;
+	bool dec_ready = false;
+	int sm_count = 1;
 	PinBuf pin_small, pin_io, pin_stream;
 
 	// last encode result (device resident)

@@ -206,10 +206,20 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 			if (g.ntile[l] > tmax)
 				tmax = g.ntile[l];
 		}
+		const int nwin_cap = (int)(len * 8 / 65536 + 4);
 		if (c->bs.ensure(bs_words * 4 + 64) || c->sig.ensure(sig_words * 4 + 64) || c->dstate.ensure(sizeof(DecState)) ||
 		    c->mem_pref.ensure((size_t)tmax * 8 + 64) || c->ref_pref.ensure((size_t)tmax * 8 + 64) ||
-		    c->ones_rank.ensure((size_t)gmax * 4 + 64) || c->sign_rank.ensure((size_t)gmax * 4 + 64))
+		    c->ones_rank.ensure((size_t)gmax * 4 + 64) || c->sign_rank.ensure((size_t)gmax * 4 + 64) ||
+		    c->win.ensure((size_t)nwin_cap * 16 + 64))
 			return -1;
+		if (!c->dec_ready) {
+			if (dec_setup())
+				return -1;
+			int sms = 0;
+			CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+			c->sm_count = sms > 0 ? sms : 1;
+			c->dec_ready = true;
+		}
 		CUDA_OK(cudaMemsetAsync(c->bs.p, 0, bs_words * 4, st));
 		CUDA_OK(cudaMemsetAsync(c->sig.p, 0, sig_words * 4, st));
 		CUDA_OK(cudaMemcpyAsync(c->dstate.p, h_state, sizeof(DecState), cudaMemcpyHostToDevice, st));
@@ -217,10 +227,14 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		b.bs = c->bs.as<u32>();
 		b.sig = c->sig.as<u32>();
 		b.stream = c->stream.as<u32>();
-		b.mem_pref = c->mem_pref.as<u32>();
-		b.ref_pref = c->ref_pref.as<u32>();
+		b.tile_sums = c->mem_pref.as<u32>();
+		b.tile_base = c->ref_pref.as<u32>();
 		b.ones_rank = c->ones_rank.as<u32>();
 		b.sign_rank = c->sign_rank.as<u32>();
+		b.win_state = c->win.as<u64>();
+		b.win_rank = b.win_state + nwin_cap;
+		b.nwin_cap = nwin_cap;
+		b.parse_ctas = c->sm_count;
 		b.state = c->dstate.as<DecState>();
 		for (int j = 0; j < nchunks; ++j)
 			if (dec_chunk(g, S, b, j, st, &c->launches))
@@ -273,6 +287,7 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		stt->full_bits = (long long)h_state->bitpos;
 		stt->meta_bits = h_state->dbg_windows;
 		stt->root_bits = h_state->dbg_iters;
+		stt->total_bits = h_state->dbg_walk;
 	}
 	return 0;
 }

@@ -1,0 +1,13 @@
+"""decode one synthetic 1080p stream a few times (profiling aid)"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, dwt_b200 as D
+from oracle import pyoracle as O
+w, h = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1920, 1080)
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+cod = D.Codec()
+img = O.synth(w, h, 'photo', 1)
+s = cod.encode(img)
+for _ in range(reps):
+    d = cod.decode(s)
+print('ok' if (d == img).all() else 'MISMATCH', cod.stats.ms_total, cod.stats.ms_coder)
