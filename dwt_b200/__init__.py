@@ -34,7 +34,8 @@ class Stats(C.Structure):
     _fields_ = [("meta_bits", C.c_longlong), ("root_bits", C.c_longlong), ("total_bits", C.c_longlong),
                 ("kib", C.c_longlong), ("full_bits", C.c_longlong), ("levels", C.c_int), ("planes", C.c_int * 3),
                 ("ms_h2d", C.c_float), ("ms_lift", C.c_float), ("ms_linearize", C.c_float), ("ms_coder", C.c_float),
-                ("ms_d2h", C.c_float), ("ms_total", C.c_float), ("level_reached", C.c_int)]
+                ("ms_d2h", C.c_float), ("ms_total", C.c_float), ("level_reached", C.c_int),
+                ("parse_windows", C.c_longlong), ("parse_jumps", C.c_longlong), ("parse_exact", C.c_longlong)]
 
 
 class DwtError(RuntimeError):

@@ -285,9 +285,9 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		stt->ms_lift = ev_ms(c->ev[2], c->ev[3]);
 		stt->ms_total = ev_ms(c->ev[0], c->ev[3]);
 		stt->full_bits = (long long)h_state->bitpos;
-		stt->meta_bits = h_state->dbg_windows;
-		stt->root_bits = h_state->dbg_iters;
-		stt->total_bits = h_state->dbg_walk;
+		stt->parse_windows = h_state->dbg_windows;
+		stt->parse_jumps = h_state->dbg_iters;
+		stt->parse_exact = h_state->dbg_walk;
 	}
 	return 0;
 }

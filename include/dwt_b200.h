@@ -37,6 +37,8 @@ struct dwt_stats {
 	float ms_h2d, ms_lift, ms_linearize, ms_coder, ms_d2h, ms_total;
 	/* decoder only */
 	int level_reached;    /* `level` of decode.c:197: highest detail level started (-1: root only) */
+	/* decoder parse statistics: windows up to the end of each pass, chain jumps, exact slice steps */
+	long long parse_windows, parse_jumps, parse_exact;
 };
 
 typedef struct dwt_ctx dwt_ctx;

@@ -114,7 +114,7 @@ def main():
                     if not ok:
                         extra = "got None" if got is None else ("want None" if want is None else first_diff(got, want))
                     report("decode cap=%d pix=%d %s" % (cap, pm, name), ok, extra)
-                print("   stats: total %.3f ms coder %.3f ms windows %d short %d" % (cod.stats.ms_total, cod.stats.ms_coder, cod.stats.meta_bits, cod.stats.root_bits), flush=True)
+                print("   stats: total %.3f ms coder %.3f ms windows %d short %d" % (cod.stats.ms_total, cod.stats.ms_coder, cod.stats.parse_windows, cod.stats.parse_exact), flush=True)
         except Exception:
             fails_local = traceback.format_exc()
             report("exception " + name, False, fails_local.splitlines()[-1])

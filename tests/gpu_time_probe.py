@@ -19,4 +19,4 @@ for (w, h, kind) in cases:
     st = cod.stats
     print('   dec', 'ok' if (d == img).all() else 'MISMATCH', 'wall %.1f ms' % (dt * 1e3),
           'dev total %.2f coder %.2f recon %.2f lift %.2f' % (st.ms_total, st.ms_coder, st.ms_linearize, st.ms_lift),
-          'windows', st.meta_bits, 'jumps', st.root_bits, 'exact', st.total_bits, flush=True)
+          'windows', st.parse_windows, 'jumps', st.parse_jumps, 'exact', st.parse_exact, flush=True)
