@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- encode/decode Mpixel/s on 8K RGB (BASELINE.json's metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one pass of the hot path over one synthetic 7680x4320 RGB frame: lossless encode to a .dwt stream
+and decode of that stream back to pixels.  Mpixel/s = W*H*steps*ranks / seconds.
+  value : device-resident round trip (image and stream already in HBM), CUDA events on the codec's stream
+  e2e   : the same through the public C ABI with page-locked HOST buffers (dwt_encode_into/dwt_decode_into),
+          host->device and device->host copies inside the timed region
+Images are independent, so ranks shard frames with no collective on the data path ("weak" scaling: one frame
+stream per GPU); torch.distributed is only the barrier and the max-over-ranks of the timing.
+--impl reference times the UNMODIFIED reference programs (oracle/_ref, built by oracle/Makefile) on the host
+cores, on bands of the same frame (one process per band).
+"""
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, CH = 7680, 4320, 3
+WORKLOAD = "synthetic 7680x4320 RGB 'photo' frame (SURVEY App. E.2, seed = rank+1), lossless encode + decode round trip"
+LIFT_BYTES_PER_PIXEL = 23.0   # u8 in (colour fused), int32 between levels, RGB
+L2_NOTE = "L2 flushed (256 MB write) between timed steps; per-step working set ~1.5 GB >> 126 MB L2"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = [s for s in sm if s >= 0.5 * max(sm)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+
+TILE_W, TILE_H = 1920, 1080   # 16 tiles of the 8K frame; 16:9 like the frame, so the reference's Hilbert walk over the
+                              # enclosing power-of-two square (encode.c:46-49) has the frame's own overhead ratio (2.02x)
+
+
+def make_tile_files(tmp, seed):
+    from oracle import pyoracle as O
+    img = O.synth(W, H, "photo", seed)
+    paths = []
+    for ty in range(H // TILE_H):
+        for tx in range(W // TILE_W):
+            tile = np.ascontiguousarray(img[ty * TILE_H:(ty + 1) * TILE_H, tx * TILE_W:(tx + 1) * TILE_W])
+            p = os.path.join(tmp, "tile%d_%d.pnm" % (ty, tx))
+            with open(p, "wb") as f:
+                f.write(O.pnm_bytes(tile))
+            paths.append(p)
+    return paths
+
+
+def reference_step(paths, workers):
+    """every tile through the reference encode then decode program, `workers` processes at a time; wall seconds"""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as O
+    enc, dec = os.path.join(O.REF_DIR, "encode"), os.path.join(O.REF_DIR, "decode")
+
+    def one(p):
+        return subprocess.call("%s %s %s.dwt && %s %s.dwt %s.out" % (enc, p, p, dec, p, p), shell=True,
+                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        rc = list(ex.map(one, paths))
+    dt = time.perf_counter() - t0
+    if any(rc):
+        raise RuntimeError("reference program failed: %s" % rc)
+    return dt
+
+
+def reference_bench(steps, warmup, quick=False):
+    """Mpixel/s of the unmodified reference programs on the host cores: the 8K frame cut into 16 tiles of 1920x1080,
+    one reference process per tile, as many at a time as there are cores (the reference is single-threaded)."""
+    from oracle import pyoracle as O
+    if not O.have_ref():
+        raise RuntimeError("oracle/_ref is not built (oracle/Makefile needs /root/reference at build time)")
+    cores = os.cpu_count() or 1
+    tmp = tempfile.mkdtemp(prefix="dwtref", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        paths = make_tile_files(tmp, 1)
+        workers = max(1, min(cores, len(paths)))
+        if quick:                         # bounded sample for the cpu_baseline leg of the default run: one wave of tiles
+            paths = paths[:workers]
+        pixels = TILE_W * TILE_H * len(paths)
+        for _ in range(warmup):
+            reference_step(paths, workers)
+        times = [reference_step(paths, workers) for _ in range(steps)]
+        # parity of the sample: the reference round trip is lossless
+        assert open(paths[0], "rb").read() == open(paths[0] + ".out", "rb").read(), "reference round trip is not lossless?"
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    sec = sum(times) / len(times)
+    return dict(value=pixels / sec / 1e6, unit="Mpixel/s", cores=workers, kind="reference", ms_per_step=sec * 1e3,
+                sample="%d tiles of %dx%d cut from the 8K frame (%.1f Mpixel), reference encode + decode program per tile, %d "
+                       "processes at a time, files in /dev/shm, CLI wall time incl. PNM I/O" %
+                       (len(paths), TILE_W, TILE_H, pixels / 1e6, workers))
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+
+def frame_seed(rank):
+    """images are independent: rank r codes its own frame stream (seed r+1), no exchange step"""
+    return rank + 1
+
+
+def job_mpixels_per_s(pixels_per_step, steps, world, max_ms_over_ranks):
+    """whole-job throughput: every rank processed `steps` frames in the slowest rank's time"""
+    return pixels_per_step * steps * world / (max_ms_over_ranks / 1e3) / 1e6
+
+
+def reduce_over_ranks(total_ms, e2e_ms, launches, device):
+    """max over ranks of the two timings, sum of the launch counts (the only collectives in the benchmark)"""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    l = torch.tensor([launches], dtype=torch.int64, device=device)
+    dist.all_reduce(l, op=dist.ReduceOp.SUM)
+    return float(t[0]), float(t[1]), int(l[0])
+
+
+def our_bench(args, rank, world, local):
+    import torch
+    import dwt_b200 as D
+    from oracle import pyoracle as O  # synthetic generator only (inputs); the codec never touches it
+
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cod = D.Codec(local)
+    img = O.synth(W, H, "photo", frame_seed(rank))
+    npx = W * H
+
+    # ---- page-locked host buffers for the end-to-end path
+    pin_flat, own1 = D.pinned_array(img.size)
+    pin_flat[:] = img.reshape(-1)
+    pin_img = pin_flat.reshape(H, W, CH)
+    pin_out, own2 = D.pinned_array(img.size * 2 + 4096)
+    pin_dec, own3 = D.pinned_array(img.size)
+
+    # ---- parity gate: no number without bit-exactness (lossless round trip + pin for rank 0's frame)
+    n = cod.encode_into(pin_img, pin_out)
+    import hashlib
+    if rank == 0:
+        digest = hashlib.sha256(pin_out[:n].tobytes()).hexdigest()[:32]
+        assert (n, digest) == (48863617, "f14ef79d0680a4ace7daa2b9e8063651"), "8K stream differs from the reference pin"
+    shp = cod.decode_into(pin_out, n, pin_dec)
+    assert shp == (H, W, CH) and np.array_equal(pin_dec, pin_flat), "round trip is not lossless"
+    stream_bytes = n
+
+    def barrier():
+        cod_sync()
+        if use_dist:
+            dist.barrier()
+
+    def cod_sync():
+        D.lib().dwt_ctx_sync(cod._h)
+
+    # ---- device-resident steps: image and stream already in HBM
+    cod.upload_image(pin_img)
+    cod.upload_stream(pin_out[:n])
+    stage = dict(lift_fwd=[], linearize=[], enc_coder=[], dec_coder=[], reconstruct=[], lift_inv=[], enc=[], dec=[])
+
+    def resident_step(timed):
+        cod.flush_l2()
+        cod.event_record(0)
+        se = cod.encode_resident(0)
+        e = (se.ms_lift, se.ms_linearize, se.ms_coder, se.ms_total)
+        sd_ = cod.decode_resident(-1)
+        sd = cod.stats
+        cod.event_record(1)
+        ms = cod.event_elapsed_ms(0, 1)
+        if timed:
+            stage["lift_fwd"].append(e[0]); stage["linearize"].append(e[1]); stage["enc_coder"].append(e[2]); stage["enc"].append(e[3])
+            stage["dec_coder"].append(sd.ms_coder); stage["reconstruct"].append(sd.ms_linearize)
+            stage["lift_inv"].append(sd.ms_lift); stage["dec"].append(sd.ms_total)
+        return ms
+
+    for _ in range(args.warmup):
+        resident_step(False)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = cod.launch_count()
+    t_wall0 = time.perf_counter()
+    dev_ms = [resident_step(True) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = cod.launch_count() - l0
+    total_ms = sum(dev_ms)
+
+    # ---- end-to-end steps: host buffers in, host buffers out, copies inside the timed region
+    def e2e_step():
+        cod.flush_l2()
+        t0 = time.perf_counter()
+        m = cod.encode_into(pin_img, pin_out)
+        cod.decode_into(pin_out, m, pin_dec)
+        return (time.perf_counter() - t0) * 1e3
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    e2e_ms = [e2e_step() for _ in range(args.steps)]
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    e2e_total = sum(e2e_ms)
+
+    # ---- max over ranks
+    if use_dist:
+        total_ms, e2e_total, launches = reduce_over_ranks(total_ms, e2e_total, launches, torch.device("cuda", local))
+    if rank != 0:
+        if use_dist:
+            dist.destroy_process_group()
+        return None
+
+    value = job_mpixels_per_s(npx, args.steps, world, total_ms)
+    e2e_value = job_mpixels_per_s(npx, args.steps, world, e2e_total)
+    peak, peak_kind = peaks()
+    med = {k: statistics.median(v) for k, v in stage.items()}
+
+    def roof(ms, nbytes):
+        gbs = nbytes / (ms / 1e3) / 1e9
+        return dict(bound="hbm", achieved=round(gbs, 1), peak=peak, unit="GB/s", frac=round(gbs / peak, 4),
+                    ms=round(ms, 4), bytes=int(nbytes))
+
+    nsamples = npx * CH
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        traffic = {}
+    roofline = roof(med["lift_fwd"], LIFT_BYTES_PER_PIXEL * npx)
+    roofline.update(kernel="lift_fwd_kernel, all %d levels (colour fused into the first)" % 10, peak_source=peak_kind,
+                    traffic=traffic.get("lift_fwd"))
+    stages = dict(
+        lift_fwd=roofline,
+        lift_inv=dict(roof(med["lift_inv"], LIFT_BYTES_PER_PIXEL * npx), kernel="lift_inv_kernel, all levels (colour + clamp fused into the last)",
+                      traffic=traffic.get("lift_inv")),
+        linearize=dict(roof(med["linearize"], 4 * nsamples + nsamples * 10 / 8), kernel="linearize_kernel (Hilbert gather + bit-slicing)"),
+        enc_coder=dict(roof(med["enc_coder"], 4 * nsamples + stream_bytes), kernel="enc_* (count, scan, emit, VLI orders, scatter)"),
+        dec_coder=dict(roof(med["dec_coder"], 4 * nsamples + stream_bytes), kernel="dec_* (prep, tilescan, parse, deposit) x chunks"),
+        reconstruct=dict(roof(med["reconstruct"], 4 * nsamples + nsamples * 10 / 8), kernel="reconstruct_kernel (Hilbert scatter + bias)"),
+    )
+    out = dict(metric="encode/decode Mpixel/s, 8K RGB", value=round(value, 2), unit="Mpixel/s", n_gpus=world, steps=args.steps,
+               warmup=args.warmup, ms_per_step=round(total_ms / args.steps, 3), higher_is_better=True, scaling="weak",
+               vs_baseline=None, dtype="int32", data="synthetic",
+               config=dict(workload=WORKLOAD, frames_per_step_per_gpu=1, width=W, height=H, channels=CH, l2=L2_NOTE,
+                           stream_bytes=stream_bytes, parallelism="one frame stream per GPU, no collective"),
+               e2e=dict(value=round(e2e_value, 2), unit="Mpixel/s", ms_per_step=round(e2e_total / args.steps, 3),
+                        h2d_bytes_per_step=int(img.size + stream_bytes), d2h_bytes_per_step=int(stream_bytes + img.size),
+                        api="dwt_encode_into + dwt_decode_into on page-locked host buffers"),
+               gpu_launches=int(launches), clocks=clocks, roofline=roofline, stages=stages,
+               encode_mpx_s=round(npx / (med["enc"] / 1e3) / 1e6, 1), decode_mpx_s=round(npx / (med["dec"] / 1e3) / 1e6, 1),
+               wall_ms_per_step=round(t_wall * 1e3 / args.steps, 3))
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = reference_bench(1, 0, quick=True)
+        except Exception as ex:  # the oracle always exists; _ref may be missing on a box that never built it
+            out["cpu_baseline"] = dict(value=None, unit="Mpixel/s", cores=0, kind="reference", sample="unavailable: %s" % ex)
+    if use_dist:
+        dist.destroy_process_group()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = reference_bench(max(1, args.steps), max(0, args.warmup))
+        line = dict(impl="reference", metric="encode/decode Mpixel/s, 8K RGB", value=round(r["value"], 3), unit="Mpixel/s",
+                    n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=round(r["ms_per_step"], 1),
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32", data="synthetic",
+                    config=dict(workload=WORKLOAD, sample=r["sample"]),
+                    cpu_baseline=dict(value=round(r["value"], 3), unit="Mpixel/s", cores=r["cores"], kind="reference", sample=r["sample"]),
+                    e2e=dict(value=round(r["value"], 3), unit="Mpixel/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return 0
+    if args.warmup < 3:
+        args.warmup = 3
+    out = our_bench(args, rank, world, local)
+    if out is not None:
+        print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -17,6 +17,8 @@ ABI_SYMBOLS = [
     "dwt_ctx_create", "dwt_ctx_destroy", "dwt_last_error", "dwt_encode", "dwt_decode", "dwt_free",
     "dwt_ctx_upload_image", "dwt_ctx_encode_resident", "dwt_ctx_download_stream", "dwt_ctx_upload_stream",
     "dwt_ctx_decode_resident", "dwt_ctx_download_image", "dwt_ctx_launch_count", "dwt_ctx_sync",
+    "dwt_host_alloc", "dwt_host_free", "dwt_encode_into", "dwt_decode_into", "dwt_ctx_flush_l2",
+    "dwt_ctx_event_record", "dwt_ctx_event_elapsed_ms",
     "cdf53", "icdf53", "dwt_forward", "dwt_inverse", "dwt_ycocg_from_rgb", "dwt_rgb_from_ycocg",
     "compute_lengths", "ilog2", "dwt_debug_front_end",
     "bytes_reader", "bytes_writer", "bytes_count", "close_bytes_reader", "close_bytes_writer", "put_byte",
@@ -72,6 +74,17 @@ def lib():
     L.dwt_ctx_launch_count.argtypes = [vp]
     L.dwt_ctx_launch_count.restype = C.c_longlong
     L.dwt_ctx_sync.argtypes = [vp]
+    L.dwt_host_alloc.argtypes = [C.c_size_t]
+    L.dwt_host_alloc.restype = vp
+    L.dwt_host_free.argtypes = [vp]
+    L.dwt_host_free.restype = None
+    L.dwt_encode_into.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_size_t, C.POINTER(C.c_size_t),
+                                  C.POINTER(Stats)]
+    L.dwt_decode_into.argtypes = [vp, u8p, C.c_size_t, C.c_int, u8p, C.c_size_t, ip, ip, ip, C.POINTER(Stats)]
+    L.dwt_ctx_flush_l2.argtypes = [vp]
+    L.dwt_ctx_event_record.argtypes = [vp, C.c_int]
+    L.dwt_ctx_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int]
+    L.dwt_ctx_event_elapsed_ms.restype = C.c_float
     L.cdf53.argtypes = [ip, ip, C.c_int, C.c_int, C.c_int, C.c_int]
     L.cdf53.restype = None
     L.icdf53.argtypes = [ip, ip, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -198,6 +211,55 @@ class Codec:
 
     def launch_count(self):
         return int(lib().dwt_ctx_launch_count(self._h))
+
+    # ---- caller-owned (page-locked) buffers: the end-to-end path of bench.py
+    def encode_into(self, img, out, capacity=0):
+        """img, out: uint8 numpy arrays (ideally views of pinned_array()); returns the stream length"""
+        w, h, ch = _shape(img)
+        n = C.c_size_t()
+        if lib().dwt_encode_into(self._h, _u8p(img), w, h, ch, int(capacity), _u8p(out), out.size, C.byref(n),
+                                 C.byref(self.stats)):
+            raise DwtError("dwt_encode_into failed: " + last_error())
+        return n.value
+
+    def decode_into(self, stream, nbytes, out, pixels_max=-1):
+        """stream: uint8 array holding nbytes stream bytes; out: uint8 array for the pixels; returns (h, w, ch)"""
+        w, h, ch = C.c_int(), C.c_int(), C.c_int()
+        r = lib().dwt_decode_into(self._h, _u8p(stream), nbytes, int(pixels_max), _u8p(out), out.size, C.byref(w),
+                                  C.byref(h), C.byref(ch), C.byref(self.stats))
+        if r:
+            raise DwtError("dwt_decode_into failed (%d): %s" % (r, last_error()))
+        return h.value, w.value, ch.value
+
+    def flush_l2(self):
+        if lib().dwt_ctx_flush_l2(self._h):
+            raise DwtError("flush_l2 failed: " + last_error())
+
+    def event_record(self, slot):
+        if lib().dwt_ctx_event_record(self._h, slot):
+            raise DwtError("event_record failed: " + last_error())
+
+    def event_elapsed_ms(self, a, b):
+        return float(lib().dwt_ctx_event_elapsed_ms(self._h, a, b))
+
+
+def pinned_array(nbytes):
+    """uint8 numpy view of page-locked host memory (dwt_host_alloc); keep the returned owner alive"""
+    p = lib().dwt_host_alloc(nbytes)
+    if not p:
+        raise DwtError("dwt_host_alloc failed: " + last_error())
+    arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,))
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib().dwt_host_free(self.ptr)
+            except Exception:
+                pass
+    return arr, _Owner(p)
 
     # ---- parity taps
     def front_end(self, img):

@@ -118,7 +118,7 @@ extern "C" void dwt_ctx_destroy(dwt_ctx *c)
 	DevBuf *bufs[] = {&c->img, &c->pyr, &c->ll[0], &c->ll[1], &c->small, &c->bs, &c->sig, &c->ent, &c->Z,
 	                  &c->signbuf, &c->specbuf, &c->refbuf, &c->tiles, &c->thr_state, &c->chunks, &c->info,
 	                  &c->dsched, &c->out, &c->stream, &c->mem_pref, &c->ref_pref, &c->ones_rank, &c->sign_rank,
-	                  &c->dstate, &c->win};
+	                  &c->dstate, &c->win, &c->flush};
 	for (DevBuf *b : bufs)
 		b->release();
 	c->pin_small.release();
@@ -364,9 +364,9 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 	if (c->pin_small.ensure(sizeof(int) * (4 + nroot) + sizeof(EncInfo) + 64))
 		return -1;
 	int *h_small = c->pin_small.as<int>();
+	CUDA_OK(cudaEventRecord(c->ev[1], st)); // ev0..ev1 = the lifting kernels only
 	CUDA_OK(cudaMemcpyAsync(h_small, c->small.p, 16, cudaMemcpyDeviceToHost, st));
 	CUDA_OK(cudaMemcpyAsync(h_small + 4, ctx_root_ll(c), sizeof(int) * nroot, cudaMemcpyDeviceToHost, st));
-	CUDA_OK(cudaEventRecord(c->ev[1], st));
 	CUDA_OK(cudaStreamSynchronize(st));
 	int planes[3] = {0, 0, 0}, planes_max = 0;
 	for (int ch = 0; ch < C; ++ch) {

@@ -46,7 +46,7 @@ struct dwt_ctx {
 
 	// coder buffers
 	DevBuf bs, sig, ent, Z, signbuf, specbuf, refbuf, tiles, thr_state, chunks, info, dsched, out, stream;
-	DevBuf mem_pref, ref_pref, ones_rank, sign_rank, dstate, win;
+	DevBuf mem_pref, ref_pref, ones_rank, sign_rank, dstate, win, flush;
 	bool dec_ready = false;
 	int sm_count = 1;
 	PinBuf pin_small, pin_io, pin_stream;
@@ -55,7 +55,7 @@ struct dwt_ctx {
 	size_t out_bytes = 0;      // valid bytes in `out` (already truncated to the capacity)
 	// last decode result
 	int dec_w = 0, dec_h = 0, dec_ch = 0;
-	size_t stream_len = 0;
+	size_t stream_len = 0, stream_head = 0;
 	bool stream_resident = false;
 };
 

@@ -36,14 +36,18 @@ extern "C" int dwt_ctx_upload_stream(dwt_ctx *c, const uint8_t *stream, size_t l
 	}
 	CUDA_OK(cudaSetDevice(c->device));
 	const size_t room = round_up(len, 4) + 64;
-	if (c->stream.ensure(room) || c->pin_stream.ensure(len + 16))
+	// the host only parses the stream prefix (header, root image < 16x16, plane counts: a few KB)
+	const size_t head = len < (1u << 20) ? len : (1u << 20);
+	if (c->stream.ensure(room) || c->pin_stream.ensure(head + 16))
 		return -1;
 	// the parse peeks up to 12 bytes past its position: keep the tail zeroed
 	CUDA_OK(cudaMemsetAsync((char *)c->stream.p + (len / 4) * 4, 0, room - (len / 4) * 4, c->st));
 	if (len) {
-		memcpy(c->pin_stream.p, stream, len);
-		CUDA_OK(cudaMemcpyAsync(c->stream.p, c->pin_stream.p, len, cudaMemcpyHostToDevice, c->st));
+		memcpy(c->pin_stream.p, stream, head);
+		CUDA_OK(cudaMemcpyAsync(c->stream.p, stream, len, cudaMemcpyHostToDevice, c->st));
+		CUDA_OK(cudaStreamSynchronize(c->st)); // the caller's buffer is free again when this returns
 	}
+	c->stream_head = head;
 	c->stream_len = len;
 	c->stream_resident = true;
 	return 0;
@@ -100,7 +104,7 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 	// ---- header + root image + plane counts on the host (the bytes are still in the pinned staging buffer)
 	const uint8_t *bytes = c->pin_stream.as<uint8_t>();
 	const size_t len = c->stream_len;
-	struct bytes_reader *br = bytes_reader_mem(bytes, len);
+	struct bytes_reader *br = bytes_reader_mem(bytes, c->stream_head); // prefix only (see dwt_ctx_upload_stream)
 	int width = 0, height = 0;
 	int letter = get_byte(br);
 	int number = letter == 'W' ? get_byte(br) : -1;

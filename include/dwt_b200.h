@@ -77,6 +77,20 @@ int dwt_ctx_download_image(dwt_ctx *ctx, uint8_t **pixels, int *width, int *heig
 long long dwt_ctx_launch_count(const dwt_ctx *ctx);
 int dwt_ctx_sync(dwt_ctx *ctx);
 
+/* Caller-owned buffer variants of dwt_encode / dwt_decode (same semantics and return values; -1 with
+ * *out_len = needed size when the buffer is too small).  With buffers from dwt_host_alloc() (page-locked
+ * memory) the host<->device copies run at PCIe rate; this is what the CLIs' file buffers use. */
+void *dwt_host_alloc(size_t bytes);
+void dwt_host_free(void *p);
+int dwt_encode_into(dwt_ctx *ctx, const uint8_t *pixels, int width, int height, int channels, int capacity,
+                    uint8_t *out, size_t out_room, size_t *out_len, struct dwt_stats *stats);
+int dwt_decode_into(dwt_ctx *ctx, const uint8_t *stream, size_t len, int pixels_max, uint8_t *pixels,
+                    size_t pixels_room, int *width, int *height, int *channels, struct dwt_stats *stats);
+/* benchmark helpers: evict L2 (writes 256 MB), CUDA events on the context's stream (slots 0..3) */
+int dwt_ctx_flush_l2(dwt_ctx *ctx);
+int dwt_ctx_event_record(dwt_ctx *ctx, int slot);
+float dwt_ctx_event_elapsed_ms(dwt_ctx *ctx, int slot_a, int slot_b);
+
 /* ------------------------------------------------------------------ transform entry points */
 
 /* cdf53.h:9 and cdf53.h:36 -- exact reference signatures and semantics: host buffers, strides in ints,
