@@ -68,8 +68,10 @@ struct DecState {                 // device-resident cursor of the serial parse 
 	int c_order;
 	u32 c_pending;
 	u32 ticket;                   // parse windows handed out so far (reset per chunk)
+	u32 published;                // parse windows whose exit state is known
 	int done;                     // the chunk's significance pass has found its end
 	u32 dbg_windows, dbg_iters, dbg_walk; // parse statistics: windows up to the end, fix-up iterations, walk steps
+	u64 dbg_cyc[4];               // SM cycles of thread 0: window set-up, wait for the predecessor, walk
 };
 
 struct DecBuffers {

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(1024) dec_tilescan_kernel(DecState *st, const 
 		if (st->level < level)
 			st->level = level; // decode.c:203,219-220,236-237: the chunk is started
 		st->ticket = 0;
+		st->published = 0;
 		st->done = 0;
 		st->c_bitpos = st->bitpos;
 		st->c_order = st->order;
@@ -176,20 +177,25 @@ __device__ __forceinline__ bool read_vli(const u32 *__restrict__ s, u64 end_bits
 // slice-local token step on the two 64-bit words of a slice (w0 = the slice, w1 = the 64 bits behind it):
 // token at offset d (< 64) with order k; avail = stream bits left from the slice start.
 // Returns the offset behind [VLI][sign] (may be >= 64) or -1 when the chain dies.
-__device__ __forceinline__ int slice_step(u64 w0, u64 w1, long long avail, int d, int &k)
+// Only the unary prefix decides a token's length, and it is at most 31 zeros, so a 32-bit window suffices.
+__device__ __forceinline__ int slice_step(u64 w0, u64 w1, int avail, int d, int &k)
 {
-	if (d >= avail)
-		return -1;
-	const u64 w = d ? (w0 >> d) | (w1 << (64 - d)) : w0;
-	const int u = w ? __ffsll((long long)w) - 1 : 64;
+	const u32 lo = d < 32 ? (u32)w0 : (u32)(w0 >> 32);
+	const u32 hi = d < 32 ? (u32)(w0 >> 32) : (u32)w1;
+	const u32 bits = __funnelshift_r(lo, hi, d & 31);
+	const int u = bits ? __ffs((int)bits) - 1 : 32;
 	const int e = k + u;
-	if (e > 31)
-		return -1;
 	const int L = u + 1 + e;
-	if (d + L > avail)
+	if (e > 31 || d >= avail || d + L > avail)
 		return -1;
 	k = e >= 2 ? e - 2 : 0;
 	return d + L + 1;
+}
+
+__device__ __forceinline__ int clamp_avail(u64 end_bits, u64 lo_bit)
+{
+	const long long av = (long long)end_bits - (long long)lo_bit;
+	return av > (1 << 30) ? (1 << 30) : (av < -(1 << 30) ? -(1 << 30) : (int)av);
 }
 
 // the two 64-bit words a slice's token steps can touch (zero behind the padded end of the stream)
@@ -201,7 +207,7 @@ __device__ __forceinline__ void load_slice(const u32 *__restrict__ stream, u64 e
 }
 
 // exit state of a slice for the entry (off, k), using the slice's order-0 table for the order-0 part
-__device__ __forceinline__ unsigned short slice_exit(const unsigned short *row, u64 w0, u64 w1, long long avail,
+__device__ __forceinline__ unsigned short slice_exit(const unsigned short *row, u64 w0, u64 w1, int avail,
                                                      unsigned short entry)
 {
 	if (entry == PDEAD)
@@ -282,7 +288,8 @@ __global__ void __launch_bounds__(PT, 1) dec_parse_kernel(DecState *st, const u3
 	__shared__ unsigned short ecan[2][PT];       // entries of the two canonical chains
 	__shared__ unsigned short xcan[2][PT];       // their exits
 	__shared__ unsigned short etrue[PT];         // entries of the true chain where it was stepped exactly
-	__shared__ unsigned short nbad[2][PT];       // next wrong link of the predicted chains
+	__shared__ u64 winfo[PT];                    // per slice: predicted entries of both chains + their next wrong link
+	__shared__ u32 xpair[PT];                    // per slice: exact exits of both chains for those entries
 	__shared__ unsigned char mark[PT];           // walker marks: 1/2 = follows predicted chain 0/1 from here, 3 = exact, 4 = dead
 	__shared__ u64 sw[PT + 1];                   // the window's stream words
 	__shared__ u32 s_w;
@@ -345,8 +352,16 @@ __global__ void __launch_bounds__(PT, 1) dec_parse_kernel(DecState *st, const u3
 	for (;;) {
 		__syncthreads();
 		if (tid == 0) {
-			s_w = atomicAdd(&st->ticket, 1u);
-			s_done = *(volatile int *)&st->done;
+			const u32 tk = atomicAdd(&st->ticket, 1u);
+			// speculation is throttled: at most as many unconfirmed windows as confirmed ones (+2), so a chunk
+			// that ends in its first window does not pay for 148 table builds behind it
+			volatile u32 *pub = &st->published;
+			volatile int *dn = &st->done;
+			int d = *dn;
+			while (!d && tk < nwin && tk >= 2u * *pub + 2u)
+				d = *dn;
+			s_w = tk;
+			s_done = d;
 			winner = PT;
 		}
 		__syncthreads();
@@ -360,11 +375,12 @@ __global__ void __launch_bounds__(PT, 1) dec_parse_kernel(DecState *st, const u3
 			}
 			break;
 		}
+		const long long t_win0 = clock64();
 		const int sz = win_size(w);                 // active slices (threads) of this window
 		const u64 wslice0 = S0 + win_start(w);      // its first slice
 		const u64 slice = wslice0 + tid;
 		const u64 sub_lo = slice << 6;
-		const long long avail = (long long)end_bits - (long long)sub_lo;
+		const int avail = clamp_avail(end_bits, sub_lo);
 		u64 w0, w1;
 		load_slice(stream, end_bits, slice, w0, w1);
 		unsigned short *row = T + tid * ROW;
@@ -456,7 +472,9 @@ __global__ void __launch_bounds__(PT, 1) dec_parse_kernel(DecState *st, const u3
 			xcan[c][tid] = x_c[c];
 		}
 		__syncthreads();
-		// nbad[c][i] = first slice j >= i whose exit does not match the predicted entry of slice j+1
+		// nbad[c] = first slice j >= i whose exit does not match the predicted entry of slice j+1;
+		// everything the walker needs about slice i goes into one 64-bit record
+		u32 nb[2];
 #pragma unroll
 		for (int c = 0; c < 2; ++c) {
 			const bool ok = tid < sz - 1 && x_c[c] == ecan[c][tid + 1];
@@ -472,13 +490,17 @@ __global__ void __launch_bounds__(PT, 1) dec_parse_kernel(DecState *st, const u3
 			__syncthreads();
 			for (int i = wid + 1; i < PT / 32; ++i)
 				v = min(v, wmap[i]);
-			nbad[c][tid] = (unsigned short)v;
+			nb[c] = v;
 			__syncthreads();
 		}
+		winfo[tid] = (u64)e_c[0] | ((u64)e_c[1] << 16) | ((u64)nb[0] << 32) | ((u64)nb[1] << 48);
+		xpair[tid] = (u32)x_c[0] | ((u32)x_c[1] << 16);
+		__syncthreads();
 
 		// (3) the serial step: previous window's exit -> walk the true chain.  Where it coincides with a predicted
 		// chain it jumps to that chain's next wrong link; elsewhere it steps exactly, one slice at a time.
 		if (tid == 0) {
+			const long long t_wait0 = clock64();
 			unsigned short state = PDEAD;
 			bool over = false;
 			if (w == 0) {
@@ -487,8 +509,9 @@ __global__ void __launch_bounds__(PT, 1) dec_parse_kernel(DecState *st, const u3
 				volatile u64 *src = win_state + (w - 1);
 				volatile int *dn = &st->done;
 				u64 v;
+				u32 spins = 0;
 				while (!((v = *src) & FLAG))
-					if (*dn) {
+					if ((++spins & 31u) == 0 && *dn) {
 						over = true;
 						break;
 					}
@@ -496,40 +519,77 @@ __global__ void __launch_bounds__(PT, 1) dec_parse_kernel(DecState *st, const u3
 			}
 			int i = 0;
 			u32 nexact = 0, njump = 0;
+			const long long t_walk0 = clock64();
 			if (over) {
 				i = -1; // the pass ended in an earlier window: nothing to do here
 			} else if (state == PDEAD) {
 				i = -2; // dead on arrival
 			} else {
-				const long long avail0 = (long long)end_bits - (long long)(wslice0 << 6);
+				long long av = (long long)end_bits - (long long)(wslice0 << 6);
+				const int availw = av > (1 << 30) ? (1 << 30) : (av < -(1 << 30) ? -(1 << 30) : (int)av);
+				u32 st32 = state;
 				while (i < sz) {
-					if (state == PDEAD) { // the chain died inside this window: later slices have no tokens
+					if (st32 == PDEAD) { // the chain died inside this window: later slices have no tokens
 						mark[i] = 4;
 						break;
 					}
-					const int c = state == ecan[0][i] ? 0 : (state == ecan[1][i] ? 1 : -1);
+					const u64 rec = winfo[i];
+					const int c = st32 == (u32)(rec & 0xffffu) ? 0 : (st32 == (u32)((rec >> 16) & 0xffffu) ? 1 : -1);
 					if (c >= 0) {
-						const int j = nbad[c][i];
+						const int j = (int)((rec >> (32 + 16 * c)) & 0xffffu);
 						mark[i] = (unsigned char)(1 + c);
-						state = xcan[c][j];
+						st32 = (xpair[j] >> (16 * c)) & 0xffffu;
 						i = j + 1;
 						++njump;
-					} else {
-						mark[i] = 3;
-						etrue[i] = state;
-						state = slice_exit(T + i * ROW, sw[i], sw[i + 1], avail0 - 64ll * i, state);
-						++i;
-						++nexact;
+						continue;
 					}
+					mark[i] = 3;
+					etrue[i] = (unsigned short)st32;
+					++nexact;
+					// exact step through slice i: table look-up at order 0, plain token steps otherwise
+					int off = st32 & 63, k = (st32 >> 6) & 63;
+					const unsigned short *trow = T + i * ROW;
+					if (k != 0) {
+						const u64 a = sw[i], b = sw[i + 1];
+						const int avail_i = availw - 64 * i;
+						for (;;) {
+							const u32 lo = off < 32 ? (u32)a : (u32)(a >> 32);
+							const u32 hi = off < 32 ? (u32)(a >> 32) : (u32)b;
+							const u32 bits = __funnelshift_r(lo, hi, off & 31);
+							const int u = bits ? __ffs((int)bits) - 1 : 32;
+							const int e = k + u;
+							const int L = u + 1 + e;
+							if (e > 31 || off >= avail_i || off + L > avail_i) {
+								off = -1;
+								break;
+							}
+							k = e >= 2 ? e - 2 : 0;
+							off += L + 1;
+							if (off >= 64 || k == 0)
+								break;
+						}
+					}
+					if (off < 0)
+						st32 = PDEAD;
+					else if (off >= 64)
+						st32 = (u32)pack_state(off - 64, k);
+					else
+						st32 = trow[off];
+					++i;
 				}
+				state = (unsigned short)st32;
 				i = 0;
 			}
-			win_state[w] = FLAG | state;
+			win_state[w] = FLAG | state; // flag and value travel in one 64-bit word: no fence needed
+			*(volatile u32 *)&st->published = w + 1;
 			if (over)
 				win_rank[w] = FLAG | (FLAG - 1);
-			__threadfence();
+			const long long t_walk1 = clock64();
 			atomicAdd(&st->dbg_walk, nexact);
 			atomicAdd(&st->dbg_iters, njump);
+			atomicAdd(&st->dbg_cyc[0], (u64)(t_wait0 - t_win0));
+			atomicAdd(&st->dbg_cyc[1], (u64)(t_walk0 - t_wait0));
+			atomicAdd(&st->dbg_cyc[2], (u64)(t_walk1 - t_walk0));
 			s_merge_at = i;
 		}
 		__syncthreads();
@@ -581,7 +641,6 @@ __global__ void __launch_bounds__(PT, 1) dec_parse_kernel(DecState *st, const u3
 			if (incl >= FLAG)
 				incl = FLAG - 1;
 			win_rank[w] = FLAG | incl;
-			__threadfence();
 			s_rank_excl = base;
 			f_event = EV_NONE;
 		}

@@ -292,6 +292,8 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		stt->parse_windows = h_state->dbg_windows;
 		stt->parse_jumps = h_state->dbg_iters;
 		stt->parse_exact = h_state->dbg_walk;
+		if (getenv("DWT_DEBUG"))
+			fprintf(stderr, "parse cycles: setup %llu wait %llu walk %llu\n", h_state->dbg_cyc[0], h_state->dbg_cyc[1], h_state->dbg_cyc[2]);
 	}
 	return 0;
 }
