@@ -52,39 +52,75 @@ int enc_scatter(const Sched &hs, const EncBuffers &b, u64 prefix_bits, u64 tot_r
 
 // ---------------------------------------------------------------------------------------------- decoder
 
-struct DecState {                 // device-resident cursor of the serial parse (decode.c:187-243)
+#define DWT_DEC_WS 512            // stream slices (64 bits each) per scan window
+
+struct DecState {                 // device-resident cursor of the serial parse (decode.c:187-243); read back by the host
 	u64 bitpos;                   // next stream bit
 	u64 end_bits;                 // 8 * stream length
-	u64 ref_bitpos;               // where the current chunk's refinement bits start
 	int order;                    // VLI order
 	u32 pending;                  // rle.h:66-77 counter `cnt`
 	int stopped;                  // EOF / corrupt stream reached: later chunks are skipped
 	int level;                    // highest level started
 	int missing[48];
-	u32 n_member, n_ref;          // per-chunk totals (scratch)
-	int ref_valid;                // the refinement pass of the current chunk was reached
-	int chunk_done;               // number of chunks whose parse ran
-	u64 c_bitpos;                 // snapshot of (bitpos, order, pending) at the start of the current chunk
-	int c_order;
-	u32 c_pending;
-	u32 ticket;                   // parse windows handed out so far (reset per chunk)
-	u32 published;                // parse windows whose exit state is known
-	int done;                     // the chunk's significance pass has found its end
-	u32 dbg_windows, dbg_iters, dbg_walk; // parse statistics: windows up to the end, fix-up iterations, walk steps
-	u64 dbg_cyc[4];               // SM cycles of thread 0: window set-up, wait for the predecessor, walk
+	u32 nseg;                     // (chunk, window) segments handed to the emit kernel
+	u32 dbg_slow, dbg_stray;      // resolver statistics: slow-path entries, stray slices walked
+	u64 dbg_cyc[4];               // resolver cycles: exact steps, linked windows, end search, total
+	unsigned short dbg_cs[DWT_MAX_CHUNKS]; // stray slices per chunk
+};
+
+struct DecChunk {                 // per chunk, written by the resolver, read by emit + deposit
+	u64 rank_base;                // bit offset of the chunk's member ranks in ones_rank / sign_rank
+	u64 ref_bitpos;               // where the refinement bits start
+	u32 r0;                       // members covered by the run carried in from earlier chunks
+	u32 T;                        // members left for this chunk's own tokens
+	int parsed;                   // the significance pass of this chunk ran
+	int ref_valid;                // the refinement pass was reached
+};
+
+struct DecLink {                  // window w entered with the exit state of class q of window w-1
+	u64 mem;                      // members consumed inside the window
+	u32 tok;                      // tokens started inside the window
+	u32 stray_mem, stray_tok;     // ... of which before the chain joins a canonical chain (saturating)
+	unsigned short exit_state;    // state behind the window when the chain never joined (qn == 2)
+	unsigned short m;             // slice where it joins (DWT_DEC_WS: never)
+	unsigned char qn;             // class behind the window: 0 / 1 canonical, 2 stray, 3 dead
+	unsigned char qm;             // canonical class joined at slice m
+	unsigned char pad[6];
+};
+
+struct DecSeg {                   // one (chunk, window) visit of the true chain
+	u32 w;                        // window
+	unsigned short j;             // chunk
+	unsigned short state;         // entry state (offset | order << 6) at slice i0
+	unsigned short i0;            // first slice of the visit
+	unsigned short m;             // slice from which the chain is canonical class qm (DWT_DEC_WS: nowhere)
+	u32 qm;
+	u32 cum0;                     // members of the chunk consumed before the visit (after r0)
+	u32 cum_m;                    // ... before slice m
 };
 
 struct DecBuffers {
 	u32 *bs;              // bit-sliced store being filled
 	u32 *sig;             // significance words [c][GT]
 	const u32 *stream;    // stream words (zero padded by >= 64 bytes)
-	u32 *tile_sums, *tile_base; // per tile (member, refinement) counts and their exclusive prefixes (one level)
-	u32 *ones_rank, *sign_rank; // rank-space bit vectors of the current chunk (adjacent: one memset)
-	u64 *win_state, *win_rank;  // per parse window: published exit state / inclusive member count
-	int nwin_cap;
-	int parse_ctas;       // persistent parse CTAs (one per SM)
+	u64 end_bits;
+	u32 nwin;             // scan windows covering the stream
+	u32 *E;               // per slice: canonical entry states of the two classes (e0 | e1 << 16)
+	ulonglong2 *P;        // per slice: members consumed by each class since the window start
+	u32 *TK;              // per slice: tokens started by each class since the window start (t0 | t1 << 16)
+	u32 *winX;            // per window: exit states of the two classes
+	ulonglong2 *winPT;    // per window: member totals
+	u32 *winTT;           // per window: token totals
+	DecLink *link;        // [window][class]
+	DecSeg *seg;
+	DecChunk *chunks;
+	u32 *tile_sums, *tile_base; // per (channel, tile): (member, refinement) counts and their exclusive prefixes
+	u32 *ones_rank, *sign_rank; // rank-space bit vectors, all chunks back to back
 	DecState *state;
+	const Sched *sched;   // device copy
 };
 
-int dec_setup(void);  // one-time kernel attribute setup
-int dec_chunk(const Geom &g, const Sched &hs, const DecBuffers &b, int j, cudaStream_t st, long long *launches);
+// whole significance/refinement decode of `nchunks` chunks of the schedule into b.bs (zero-initialised by the caller)
+int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b, int nchunks, cudaStream_t st, long long *launches);
+// bits of rank space needed for the first nchunks chunks
+u64 dec_rank_bits(const Geom &g, const Sched &hs, int nchunks);

@@ -1,67 +1,851 @@
 // coder_dec.cu -- the bit-plane decoder of decode.c:67-100,187-243 + rle.h + vli.h + bits.h on the GPU.
 //
-// Chunks (channel, level, plane) are decoded in schedule order; within a chunk:
-//   prep      per tile of 256 groups: how many coefficients are still insignificant (members of the
-//             significance pass) and how many are already significant (refinement bits)   [dec_prep_kernel]
-//   tilescan  exclusive prefixes of those counts, chunk totals, parse control reset     [dec_tilescan_kernel]
-//   parse     the significance pass is a serial chain of [adaptive-Rice run][sign] tokens.  The stream is cut
-//             into windows of 1024 slices of 64 bits; persistent CTAs (one per SM) take windows in order.
-//             A CTA first builds, for each of its slices, the exact transfer table "a token starts at offset
-//             d with order 0 -> where (and with which order) does the chain leave the slice" by dynamic
-//             programming from the slice end.  With the tables the two canonical chains of the window (even
-//             / odd start) are resolved by a parity-predicted fixed-point iteration of table look-ups.  The
-//             only serial step is then: wait for the previous window's exit state, follow the tables until
-//             the true chain joins a canonical chain (a few look-ups), publish the exit.  Token run
-//             lengths are scanned into member ranks (a second look-back chain across windows) and ones /
-//             signs are set in rank space.  EOF, the run carried across chunks (rle.h:66-77) and the phantom
-//             one before refinement bits (rle.h:91-103) follow the reference exactly.      [dec_parse_kernel]
-//   deposit   rank-space bits are expanded into the insignificant positions of each group (software pdep),
-//             refinement bits are taken straight from the stream, significance is updated [dec_deposit_kernel]
+// The significance pass of a chunk is a serial chain of [adaptive-Rice run][sign] tokens whose end is only known
+// once the runs cover the chunk's members, and the chunks follow each other in the stream.  The work is split so
+// that everything expensive is independent of the chunks and runs once over the whole stream:
+//
+//   scan     (dec_scan_kernel, one CTA per window of 512 slices of 64 bits)  two canonical token chains per
+//            window, seeded at bit 0 / bit 1 of the window with order 0, are resolved exactly by a parity-class
+//            prediction and a neighbour fixed-point iteration.  Per slice: entry state of both chains, prefix of
+//            members (run + 1) and of tokens along each chain.  Chains that start anywhere else join one of the
+//            two within a few slices (the code is self-synchronising), so these tables describe the true chain.
+//   link     (dec_link_kernel, one thread per window and class)  where does the exit state of class q of window
+//            w-1 join the canonical chains of window w, and what does the whole window consume on that path.
+//   resolve  (dec_resolve_kernel, ONE warp)  the only serial step: walks the chunk schedule.  A chunk start is
+//            followed token by token until it joins a canonical chain; whole windows are then consumed 32 at a
+//            time through the link records (a warp scan over 2-state class maps); the window where the members
+//            run out is searched on the per-slice prefixes and the last slice is stepped exactly.  EOF, the run
+//            carried across chunks (rle.h:66-77) and the phantom one before refinement bits (rle.h:91-103)
+//            follow the reference exactly.  Output: per chunk its rank offset / refinement position, per
+//            (chunk, window) visit a segment record.
+//   emit     (dec_emit_kernel, one CTA per segment)  every slice knows its entry state and member rank: ones and
+//            signs are set in rank space.
+//   deposit  (per plane depth, all channels and levels at once)  rank-space bits are expanded into the
+//            insignificant positions of each group (software pdep), refinement bits come straight from the
+//            stream, significance is updated.
 #include "coder.cuh"
 
 namespace {
 
 constexpr int TG = DWT_TILE_GROUPS;
-constexpr int PT = 1024;          // parse threads = slices per window
-constexpr int SLICE = 64;         // stream bits per slice; >= the longest token (31 zeros + 1 + 31 payload + sign)
-constexpr int WIN_BITS = PT * SLICE;
-constexpr int ROW = 66;           // u16 entries per table row (64 + padding against bank conflicts)
-constexpr int KDEAD = 255;        // a chain that cannot continue (EOF inside a token, impossible order)
-constexpr unsigned short PDEAD = 0xffffu;
-constexpr u64 FLAG = 1ull << 63;
-constexpr int REFINE_ROUNDS = 6;
+constexpr int WS = DWT_DEC_WS;
+constexpr u32 PDEAD = 0xffffu;    // a chain that cannot continue (EOF inside a token, impossible order)
+constexpr u64 DEATH = 1ull << 48; // member count charged to a slice in which a canonical chain dies: more than any chunk holds
 
-// Parse windows grow 64, 128, 256, 512, 1024, 1024, ... slices, so that the many small chunks of the coarse
-// levels do not pay for a full window.
-__host__ __device__ __forceinline__ int win_size(u32 w)
+enum { EV_NONE = 0, EV_COVERED = 1, EV_PENDING = 2, EV_STOP = 3 };
+
+__device__ __forceinline__ int clamp_avail(u64 end_bits, u64 lo_bit)
 {
-	return w < 4 ? 64 << w : PT;
-}
-__host__ __device__ __forceinline__ u64 win_start(u32 w) // first slice of window w, relative to the chunk's first slice
-{
-	return w <= 4 ? 64ull * ((1u << w) - 1u) : 960ull + (u64)(w - 4) * PT;
-}
-__host__ __device__ __forceinline__ u64 windows_for(u64 slices) // windows needed to cover `slices` slices
-{
-	if (slices <= 960)
-		for (u32 w = 0; w <= 4; ++w)
-			if (win_start(w) >= slices)
-				return w;
-	return 4 + (slices - 960 + PT - 1) / PT;
+	const long long av = (long long)end_bits - (long long)lo_bit;
+	return av > (1 << 30) ? (1 << 30) : (av < -(1 << 30) ? -(1 << 30) : (int)av);
 }
 
-__device__ __forceinline__ unsigned short pack_state(int off, int k)
+// the two 64-bit words a slice's tokens can touch (zero behind the padded end of the stream)
+__device__ __forceinline__ void load_slice(const u32 *__restrict__ stream, u64 end_bits, u64 slice, u64 &w0, u64 &w1)
 {
-	return (unsigned short)(off | (k << 6));
+	const u64 lo = slice << 6;
+	w0 = lo < end_bits + 128 ? __ldg((const u64 *)stream + slice) : 0ull;
+	w1 = lo < end_bits + 64 ? __ldg((const u64 *)stream + slice + 1) : 0ull;
 }
-__device__ __forceinline__ int st_off(unsigned short s)
+
+__device__ __forceinline__ u64 bits_from(u64 a, u64 b, int d) // 64 stream bits from offset d (0..63) of the pair
 {
-	return s & 63;
+	return d ? (a >> d) | (b << (64 - d)) : a;
 }
-__device__ __forceinline__ int st_k(unsigned short s)
+
+// exit state of a slice entered with `entry` (first token at offset entry & 63 with order entry >> 6):
+// the state the next slice is entered with.  Only the unary prefix decides a token's length, and a valid
+// one has at most 31 zeros, so a 32-bit window is enough.  avail = stream bits left from the slice start.
+__device__ __forceinline__ u32 slice_exit(u64 a, u64 b, int avail, u32 entry)
 {
-	return s == PDEAD ? KDEAD : (s >> 6) & 63;
+	if (entry == PDEAD)
+		return PDEAD;
+	int d = (int)(entry & 63u), k = (int)(entry >> 6);
+	do {
+		const u32 lo = d < 32 ? (u32)a : (u32)(a >> 32);
+		const u32 hi = d < 32 ? (u32)(a >> 32) : (u32)b;
+		const u32 bits = __funnelshift_r(lo, hi, d & 31);
+		const int u = bits ? __ffs((int)bits) - 1 : 32;
+		const int e = k + u;
+		const int L = u + 1 + e;
+		if (e > 31 || d + L > avail)
+			return PDEAD;
+		k = e >= 2 ? e - 2 : 0;
+		d += L + 1;
+	} while (d < 64);
+	return (u32)(d - 64) | ((u32)k << 6);
 }
+
+// same walk, also counting the members (run + 1) and tokens of the tokens that start in the slice
+__device__ __forceinline__ u32 slice_walk(u64 a, u64 b, int avail, u32 entry, u64 &mem, u32 &ntok)
+{
+	mem = 0;
+	ntok = 0;
+	if (entry == PDEAD)
+		return PDEAD;
+	int d = (int)(entry & 63u), k = (int)(entry >> 6);
+	do {
+		const u64 w = bits_from(a, b, d);
+		const u32 lo = (u32)w;
+		const int u = lo ? __ffs((int)lo) - 1 : 32;
+		const int e = k + u;
+		const int L = u + 1 + e;
+		if (e > 31 || d + L > avail)
+			return PDEAD;
+		const u32 payload = (u32)(w >> (u + 1)) & ((1u << e) - 1u);
+		mem += (u64)((1u << e) - (1u << k)) + payload + 1ull;
+		++ntok;
+		k = e >= 2 ? e - 2 : 0;
+		d += L + 1;
+	} while (d < 64);
+	return (u32)(d - 64) | ((u32)k << 6);
+}
+
+// ---------------------------------------------------------------------------------------------- scan
+
+__global__ void __launch_bounds__(WS) dec_scan_kernel(const u32 *__restrict__ stream, u64 end_bits, u32 *E, ulonglong2 *P,
+                                                       u32 *TK, u32 *winX, ulonglong2 *winPT, u32 *winTT)
+{
+	__shared__ u32 sx[WS];
+	__shared__ u32 wmap[WS / 32];
+	__shared__ u64 ws[32];
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const u64 gs = (u64)blockIdx.x * WS + tid;
+	u64 a, b;
+	load_slice(stream, end_bits, gs, a, b);
+	const int avail = clamp_avail(end_bits, gs << 6);
+	// exits for a first token at offset 0 / 1 with order 0
+	const u32 xs0 = slice_exit(a, b, avail, 0u), xs1 = slice_exit(a, b, avail, 1u);
+	// At order 0 every token has an even length, so a chain keeps the parity of its offsets.  Chain c enters the
+	// window at offset c; the parity class it enters every later slice with comes from a scan of 2-state maps.
+	u32 mymap = 0;
+	if (xs0 != PDEAD && (xs0 >> 6) == 0)
+		mymap |= xs0 & 1u;
+	if (xs1 != PDEAD && (xs1 >> 6) == 0)
+		mymap |= (xs1 & 1u) << 1;
+	u32 inc = mymap; // bit b = class behind this slice when it is entered with class b
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const u32 t = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= d)
+			inc = ((inc >> (t & 1u)) & 1u) | (((inc >> ((t >> 1) & 1u)) & 1u) << 1);
+	}
+	if (lane == 31)
+		wmap[wid] = inc;
+	__syncthreads();
+	u32 pre = 2u; // identity: class 0 -> 0, class 1 -> 1
+	for (int i = 0; i < wid; ++i) {
+		const u32 m = wmap[i];
+		pre = ((m >> (pre & 1u)) & 1u) | (((m >> ((pre >> 1) & 1u)) & 1u) << 1);
+	}
+	const u32 excl = __shfl_up_sync(0xffffffffu, inc, 1);
+	if (lane > 0)
+		pre = ((excl >> (pre & 1u)) & 1u) | (((excl >> ((pre >> 1) & 1u)) & 1u) << 1);
+	// predicted exits: as if the chains entered at offset 0 / 1 of their class
+	sx[tid] = ((pre & 1u) ? xs1 : xs0) | ((((pre >> 1) & 1u) ? xs1 : xs0) << 16);
+	__syncthreads();
+	// a canonical chain that dies (garbage in front of a chunk, EOF) starts again at its seed offset in the next
+	// slice, so that chunks further on in the window still find a chain to join; the slice it dies in is charged
+	// DEATH members, which ends every search for a chain that was following it
+	u32 e0 = 0u, e1 = 1u;
+	if (tid > 0) {
+		const u32 v = sx[tid - 1];
+		e0 = v & 0xffffu;
+		e1 = v >> 16;
+		if (e0 == PDEAD)
+			e0 = 0u;
+		if (e1 == PDEAD)
+			e1 = 1u;
+	}
+	u32 x0 = e0 == 0u ? xs0 : (e0 == 1u ? xs1 : slice_exit(a, b, avail, e0));
+	u32 x1 = e1 == e0 ? x0 : (e1 == 0u ? xs0 : (e1 == 1u ? xs1 : slice_exit(a, b, avail, e1)));
+	__syncthreads();
+	// fixed point: entry <- the predecessor's exact exit.  Slice i is exact after i rounds at the latest; in
+	// practice a wrong prediction is repaired where the chains join again, a few slices further on.
+	for (;;) {
+		sx[tid] = x0 | (x1 << 16);
+		__syncthreads();
+		int changed = 0;
+		if (tid > 0) {
+			const u32 v = sx[tid - 1];
+			u32 n0 = v & 0xffffu, n1 = v >> 16;
+			if (n0 == PDEAD)
+				n0 = 0u;
+			if (n1 == PDEAD)
+				n1 = 1u;
+			if (n0 != e0) {
+				e0 = n0;
+				x0 = slice_exit(a, b, avail, e0);
+				changed = 1;
+			}
+			if (n1 != e1) {
+				e1 = n1;
+				x1 = e1 == e0 ? x0 : slice_exit(a, b, avail, e1);
+				changed = 1;
+			}
+		}
+		if (!__syncthreads_or(changed))
+			break;
+	}
+	u64 m0, m1;
+	u32 t0, t1;
+	if (slice_walk(a, b, avail, e0, m0, t0) == PDEAD)
+		m0 += DEATH;
+	if (e1 == e0) {
+		m1 = m0;
+		t1 = t0;
+	} else if (slice_walk(a, b, avail, e1, m1, t1) == PDEAD) {
+		m1 += DEATH;
+	}
+	u64 tot0, tot1, tott;
+	const u64 p0 = block_exscan_u64(m0, ws, &tot0);
+	const u64 p1 = block_exscan_u64(m1, ws, &tot1);
+	const u64 pt = block_exscan_u64((u64)t0 | ((u64)t1 << 32), ws, &tott);
+	E[gs] = e0 | (e1 << 16);
+	P[gs] = make_ulonglong2(p0, p1);
+	TK[gs] = (u32)(pt & 0xffffu) | ((u32)(pt >> 32) << 16);
+	if (tid == WS - 1)
+		winX[blockIdx.x] = x0 | (x1 << 16);
+	if (tid == 0) {
+		winPT[blockIdx.x] = make_ulonglong2(tot0, tot1);
+		winTT[blockIdx.x] = (u32)(tott & 0xffffu) | ((u32)(tott >> 32) << 16);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------- link
+
+__global__ void __launch_bounds__(128) dec_link_kernel(const u32 *__restrict__ stream, u64 end_bits, u32 nwin,
+                                                        const u32 *__restrict__ E, const ulonglong2 *__restrict__ P,
+                                                        const u32 *__restrict__ TK, const u32 *__restrict__ winX,
+                                                        const ulonglong2 *__restrict__ winPT,
+                                                        const u32 *__restrict__ winTT, DecLink *link)
+{
+	const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+	const u32 w = t >> 1, q = t & 1u;
+	if (w >= nwin)
+		return;
+	DecLink L;
+	L.mem = 0;
+	L.tok = 0;
+	L.stray_mem = 0;
+	L.stray_tok = 0;
+	L.exit_state = (unsigned short)PDEAD;
+	L.m = WS;
+	L.qn = 3;
+	L.qm = 0;
+	if (w > 0) {
+		u32 st = (winX[w - 1] >> (16 * q)) & 0xffffu;
+		u64 smem = 0;
+		u32 stok = 0;
+		int i = 0, qm = -1;
+		if (st != PDEAD) {
+			for (; i < WS; ++i) {
+				const u64 gs = (u64)w * WS + i;
+				const u32 e = E[gs];
+				if (st == (e & 0xffffu)) {
+					qm = 0;
+					break;
+				}
+				if (st == (e >> 16)) {
+					qm = 1;
+					break;
+				}
+				u64 a, b, mm;
+				u32 tt;
+				load_slice(stream, end_bits, gs, a, b);
+				st = slice_walk(a, b, clamp_avail(end_bits, gs << 6), st, mm, tt);
+				smem += mm;
+				stok += tt;
+				if (st == PDEAD)
+					break;
+			}
+		}
+		L.stray_mem = smem > 0xffffffffull ? 0xffffffffu : (u32)smem;
+		L.stray_tok = stok;
+		if (qm >= 0) {
+			const u64 gs = (u64)w * WS + i;
+			const ulonglong2 pm = P[gs], pt = winPT[w];
+			const u32 tkm = TK[gs], tt = winTT[w];
+			L.m = (unsigned short)i;
+			L.qm = (unsigned char)qm;
+			L.mem = smem + (qm ? pt.y - pm.y : pt.x - pm.x);
+			L.tok = stok + (qm ? (tt >> 16) - (tkm >> 16) : (tt & 0xffffu) - (tkm & 0xffffu));
+			const u32 x = (winX[w] >> (16 * qm)) & 0xffffu;
+			L.qn = x == PDEAD ? 3 : (unsigned char)qm;
+		} else {
+			L.mem = smem;
+			L.tok = stok;
+			L.qn = st == PDEAD ? 3 : 2;
+			L.exit_state = (unsigned short)st;
+		}
+	}
+	uint4 r0, r1;
+	r0.x = (u32)L.mem;
+	r0.y = (u32)(L.mem >> 32);
+	r0.z = L.tok;
+	r0.w = L.stray_mem;
+	r1.x = L.stray_tok;
+	r1.y = (u32)L.exit_state | ((u32)L.m << 16);
+	r1.z = (u32)L.qn | ((u32)L.qm << 8);
+	r1.w = 0;
+	((uint4 *)link)[2 * (size_t)t] = r0;
+	((uint4 *)link)[2 * (size_t)t + 1] = r1;
+}
+
+// ---------------------------------------------------------------------------------------------- resolve
+
+// tokens that start in the slice (a, b) from offset d with order k, against the member budget T.
+// Returns EV_NONE when the slice is left (d >= 64 then), otherwise the event that ends the pass.
+__device__ __forceinline__ int walk_events(u64 a, u64 b, int avail, u64 T, int &d, int &k, u64 &cum, u32 &ones,
+                                           u32 &ev_pending)
+{
+	for (;;) {
+		if (cum >= T)
+			return EV_COVERED; // every member has its symbol; the pass ends in front of the token at d
+		if (d >= 64)
+			return EV_NONE;
+		const u64 w = bits_from(a, b, d);
+		const u32 lo = (u32)w;
+		const int u = lo ? __ffs((int)lo) - 1 : 32;
+		const int e = k + u;
+		const int L = u + 1 + e;
+		if (e > 31 || d + L > avail)
+			return EV_STOP; // the token cannot be read completely (vli.h:88-95): decoding ends
+		const u32 payload = (u32)(w >> (u + 1)) & ((1u << e) - 1u);
+		const u64 n = (u64)((1u << e) - (1u << k)) + payload;
+		const int kn = e >= 2 ? e - 2 : 0;
+		if (cum + n >= T) { // the run reaches past this chunk's members (rle.h:74-76)
+			ev_pending = (u32)(n - (T - cum) + 1);
+			d += L;
+			k = kn;
+			return EV_PENDING;
+		}
+		++ones;
+		if (d + L + 1 > avail)
+			return EV_STOP; // sign bit beyond EOF: the magnitude bit stays (decode.c:80-86)
+		cum += n + 1;
+		d += L + 1;
+		k = kn;
+	}
+}
+
+__device__ __forceinline__ u32 map_compose(u32 first, u32 second) // class maps: 2 bits per entry class 0 / 1
+{
+	const u32 a0 = first & 3u, a1 = (first >> 2) & 3u;
+	const u32 r0 = a0 >= 2u ? a0 : (second >> (2 * a0)) & 3u;
+	const u32 r1 = a1 >= 2u ? a1 : (second >> (2 * a1)) & 3u;
+	return r0 | (r1 << 2);
+}
+
+__device__ __forceinline__ void load_link(const DecLink *src, DecLink &L) // two 16-byte loads, unpacked in registers
+{
+	const uint4 r0 = __ldg((const uint4 *)src), r1 = __ldg((const uint4 *)src + 1);
+	L.mem = (u64)r0.x | ((u64)r0.y << 32);
+	L.tok = r0.z;
+	L.stray_mem = r0.w;
+	L.stray_tok = r1.x;
+	L.exit_state = (unsigned short)(r1.y & 0xffffu);
+	L.m = (unsigned short)(r1.y >> 16);
+	L.qn = (unsigned char)(r1.z & 0xffu);
+	L.qm = (unsigned char)((r1.z >> 8) & 0xffu);
+}
+
+__global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__ Geom G, int nchunks,
+                                                          const __grid_constant__ DecBuffers B)
+{
+	__shared__ u32 sigcount[48];
+	__shared__ int missing[48];
+	const int lane = threadIdx.x;
+	const u32 FULL = 0xffffffffu;
+	DecState *st = B.state;
+	const Sched *S = B.sched;
+	const u32 *__restrict__ stream = B.stream;
+	const u64 end_bits = B.end_bits;
+	const u32 nwin = B.nwin;
+	for (int i = lane; i < 48; i += 32) {
+		sigcount[i] = 0;
+		missing[i] = st->missing[i];
+	}
+	__syncwarp();
+	u64 bitpos = st->bitpos;
+	int order = st->order;
+	u32 pending = 0;
+	int level = -1;
+	bool stopped = false;
+	u64 rank_base = 0;
+	u32 nseg = 0, dbg_slow = 0, dbg_stray = 0;
+	long long cyc[4] = {0, 0, 0, 0};
+	const long long t_begin = clock64();
+
+	for (int j = 0; j < nchunks && !stopped; ++j) {
+		const int c = S->chan[j], l = S->level[j];
+		if (level < l)
+			level = l; // decode.c:203,219-220,236-237: the chunk is started
+		const u32 nsig = sigcount[c * 16 + l];
+		const u64 R = (u64)G.num[l] - nsig;
+		const u32 nref = nsig;
+		const u64 my_rank_base = rank_base;
+		rank_base += ((u64)G.num[l] + 63) & ~63ull;
+		u64 r0 = 0;
+		bool stop = false;
+		u32 ones = 0;
+		// a run carried in from earlier chunks (rle.h:66-77): (pending - 1) zeros, then a one
+		if (pending > 0) {
+			if ((u64)pending - 1 >= R) {
+				pending -= (u32)R;
+				r0 = R;
+			} else {
+				const u64 rk = my_rank_base + pending - 1;
+				++ones;
+				if (lane == 0)
+					atomicOr(B.ones_rank + (rk >> 5), 1u << (rk & 31));
+				if (bitpos < end_bits) {
+					const u32 wd = __ldg(stream + (bitpos >> 5));
+					if (lane == 0 && ((wd >> (bitpos & 31)) & 1u))
+						atomicOr(B.sign_rank + (rk >> 5), 1u << (rk & 31));
+					bitpos += 1;
+				} else {
+					stop = true; // the sign bit hits EOF: the magnitude bit stays (decode.c:80-86)
+				}
+				r0 = (u64)pending;
+				pending = 0;
+			}
+		}
+		int event = EV_NONE;
+		u64 f_pos = bitpos;
+		int f_k = order;
+		u32 f_pending = pending;
+		const u64 T = R > r0 ? R - r0 : 0;
+		if (stop) {
+			event = EV_STOP;
+		} else if (pending == 0 && r0 < R) {
+			// ------------------------------------------------ the chunk's own tokens: find where the pass ends
+			u64 cum = 0;
+			u64 gs = bitpos >> 6;
+			int d = (int)(bitpos & 63), k = order;
+			int mode = 0;        // 0 stray (exact steps), 1 linked (whole windows)
+			u32 w = 0, q = 0;    // linked mode: next window, class of the chain behind window w-1
+			u32 carry_state = PDEAD;
+			// end search on class sq of window sw from slice sm (cum = members before slice sm)
+			bool search = false;
+			u32 sw = 0, sq = 0;
+			int sm = 0;
+			++dbg_slow;
+			const u32 stray_before = dbg_stray;
+			while (event == EV_NONE) {
+				const long long t0 = clock64();
+				if (mode == 0) {
+					// ---- exact steps from slice gs until the chain joins a canonical chain, the window ends or the pass ends
+					const u32 cw = (u32)(gs / WS);
+					const int i0 = (int)(gs - (u64)cw * WS);
+					if (cw >= nwin) {
+						event = EV_STOP; // behind the scanned stream: nothing left to read
+						break;
+					}
+					const u32 seg_state = (u32)d | ((u32)k << 6);
+					const u64 seg_cum0 = cum;
+					int i = i0, m = WS, qm = 0;
+					while (i < WS && event == EV_NONE && m == WS) {
+						const int nb = min(32, WS - i);
+						const u64 mgs = (u64)cw * WS + i + lane;
+						u64 ma = 0, mb = 0;
+						u32 me = 0;
+						if (lane < nb) {
+							load_slice(stream, end_bits, mgs, ma, mb);
+							me = B.E[mgs];
+						}
+						for (int t = 0; t < nb; ++t) {
+							const u64 a = __shfl_sync(FULL, ma, t), b = __shfl_sync(FULL, mb, t);
+							const u32 e = __shfl_sync(FULL, me, t);
+							const u32 state = (u32)d | ((u32)k << 6);
+							if (state == (e & 0xffffu)) {
+								m = i + t;
+								qm = 0;
+								break;
+							}
+							if (state == (e >> 16)) {
+								m = i + t;
+								qm = 1;
+								break;
+							}
+							++dbg_stray;
+							const u64 sgs = (u64)cw * WS + i + t;
+							event = walk_events(a, b, clamp_avail(end_bits, sgs << 6), T, d, k, cum, ones, f_pending);
+							if (event != EV_NONE) {
+								f_pos = (sgs << 6) + (u64)d;
+								f_k = k;
+								break;
+							}
+							d -= 64;
+						}
+						i += nb;
+					}
+					if (lane == 0) {
+						DecSeg sg;
+						sg.w = cw;
+						sg.j = (unsigned short)j;
+						sg.state = (unsigned short)seg_state;
+						sg.i0 = (unsigned short)i0;
+						sg.m = (unsigned short)m;
+						sg.qm = (u32)qm;
+						sg.cum0 = (u32)seg_cum0;
+						sg.cum_m = (u32)cum;
+						B.seg[nseg] = sg;
+					}
+					++nseg;
+					cyc[0] += clock64() - t0;
+					if (event != EV_NONE)
+						break;
+					if (m == WS) { // the window ended before the chain joined: go on exactly in the next one
+						gs = ((u64)cw + 1) * WS;
+						continue;
+					}
+					// joined class qm at slice m: is the rest of the window enough to end the pass?
+					const u64 mgs = (u64)cw * WS + m;
+					const ulonglong2 pm = B.P[mgs], pt = B.winPT[cw];
+					const u64 rest = qm ? pt.y - pm.y : pt.x - pm.x;
+					if (cum + rest >= T) {
+						search = true;
+						sw = cw;
+						sq = (u32)qm;
+						sm = m;
+					} else {
+						const u32 tkm = B.TK[mgs], tt = B.winTT[cw];
+						cum += rest;
+						ones += qm ? (tt >> 16) - (tkm >> 16) : (tt & 0xffffu) - (tkm & 0xffffu);
+						const u32 x = (B.winX[cw] >> (16 * qm)) & 0xffffu;
+						if (x == PDEAD) {
+							event = EV_STOP; // the chain dies inside this window
+							break;
+						}
+						mode = 1;
+						w = cw + 1;
+						q = (u32)qm;
+					}
+				} else {
+					// ---- whole windows, 32 at a time: lane i looks at window w + i
+					const u32 wl = w + lane;
+					const bool valid = wl < nwin;
+					DecLink L0, L1;
+					if (valid) {
+						load_link(B.link + 2 * (u64)wl, L0);
+						load_link(B.link + 2 * (u64)wl + 1, L1);
+					} else {
+						L0.qn = L1.qn = 3;
+						L0.mem = L1.mem = 0;
+						L0.tok = L1.tok = 0;
+						L0.exit_state = L1.exit_state = (unsigned short)PDEAD;
+						L0.m = L1.m = WS;
+						L0.qm = L1.qm = 0;
+						L0.stray_mem = L1.stray_mem = 0;
+						L0.stray_tok = L1.stray_tok = 0;
+					}
+					const u32 xprev = valid ? B.winX[wl - 1] : 0xffffffffu; // w >= 1 in linked mode
+					u32 inc = (u32)L0.qn | ((u32)L1.qn << 2);
+#pragma unroll
+					for (int dd = 1; dd < 32; dd <<= 1) {
+						const u32 t = __shfl_up_sync(FULL, inc, dd);
+						if (lane >= dd)
+							inc = map_compose(t, inc);
+					}
+					const u32 excl = __shfl_up_sync(FULL, inc, 1);
+					// class the chain enters my window with
+					const u32 cls = q >= 2u ? q : (lane == 0 ? q : (excl >> (2 * q)) & 3u);
+					const bool canon = cls < 2u && valid;
+					const DecLink &my = cls == 1u ? L1 : L0;
+					const u64 mymem = canon ? my.mem : 0ull;
+					const u32 mytok = canon ? my.tok : 0u;
+					u64 incm = mymem;
+					u32 inct = mytok;
+#pragma unroll
+					for (int dd = 1; dd < 32; dd <<= 1) {
+						const u64 tm = __shfl_up_sync(FULL, incm, dd);
+						const u32 tt = __shfl_up_sync(FULL, inct, dd);
+						if (lane >= dd) {
+							incm += tm;
+							inct += tt;
+						}
+					}
+					const u64 pre = incm - mymem;
+					const bool reached = canon && cum + incm >= T;
+					const u32 bal = __ballot_sync(FULL, reached || !canon);
+					const int f = bal ? __ffs((int)bal) - 1 : 32;
+					const u32 my_entry = (xprev >> (16 * (cls & 1u))) & 0xffffu;
+					if (lane < f) { // consumed completely
+						DecSeg sg;
+						sg.w = wl;
+						sg.j = (unsigned short)j;
+						sg.state = (unsigned short)my_entry;
+						sg.i0 = 0;
+						sg.m = my.m;
+						sg.qm = my.qm;
+						sg.cum0 = (u32)(cum + pre);
+						sg.cum_m = (u32)(cum + pre + my.stray_mem);
+						B.seg[nseg + lane] = sg;
+					}
+					nseg += (u32)f;
+					cyc[1] += clock64() - t0;
+					if (f == 32) {
+						cum += __shfl_sync(FULL, incm, 31);
+						ones += __shfl_sync(FULL, inct, 31);
+						carry_state = __shfl_sync(FULL, (u32)L0.exit_state | ((u32)L1.exit_state << 16), 31);
+						const u32 last = __shfl_sync(FULL, inc, 31);
+						const u32 qn = (last >> (2 * q)) & 3u;
+						carry_state = (carry_state >> (16 * ((__shfl_sync(FULL, cls, 31)) & 1u))) & 0xffffu;
+						q = qn;
+						w += 32;
+						continue;
+					}
+					// lane f holds the window where something happens
+					const u32 wf = w + (u32)f;
+					const u32 cls_f = __shfl_sync(FULL, cls, f);
+					const bool valid_f = __shfl_sync(FULL, (int)valid, f) != 0;
+					const u64 cum_f = cum + __shfl_sync(FULL, pre, f);
+					const u32 ones_f = ones + __shfl_sync(FULL, inct - mytok, f);
+					if (f > 0) {
+						const u32 pcls = __shfl_sync(FULL, cls, f - 1);
+						const u32 ex = __shfl_sync(FULL, (u32)L0.exit_state | ((u32)L1.exit_state << 16), f - 1);
+						carry_state = (ex >> (16 * (pcls & 1u))) & 0xffffu;
+					}
+					cum = cum_f;
+					ones = ones_f;
+					if (!valid_f || cls_f == 3u) {
+						event = EV_STOP; // the chain died, or the stream is used up
+						break;
+					}
+					if (cls_f == 2u) { // the chain left the previous window without joining: exact steps again
+						mode = 0;
+						gs = (u64)wf * WS;
+						d = (int)(carry_state & 63u);
+						k = (int)(carry_state >> 6);
+						++dbg_slow;
+						continue;
+					}
+					const u32 m_f = __shfl_sync(FULL, (u32)my.m, f), qm_f = __shfl_sync(FULL, (u32)my.qm, f);
+					const u32 smem_f = __shfl_sync(FULL, my.stray_mem, f), stok_f = __shfl_sync(FULL, my.stray_tok, f);
+					const u32 entry_f = __shfl_sync(FULL, my_entry, f);
+					if (m_f >= (u32)WS || T - cum_f <= (u64)smem_f) { // the pass ends before the chain joins
+						mode = 0;
+						gs = (u64)wf * WS;
+						d = (int)(entry_f & 63u);
+						k = (int)(entry_f >> 6);
+						++dbg_slow;
+						continue;
+					}
+					if (lane == 0) {
+						DecSeg sg;
+						sg.w = wf;
+						sg.j = (unsigned short)j;
+						sg.state = (unsigned short)entry_f;
+						sg.i0 = 0;
+						sg.m = (unsigned short)m_f;
+						sg.qm = qm_f;
+						sg.cum0 = (u32)cum_f;
+						sg.cum_m = (u32)(cum_f + smem_f);
+						B.seg[nseg] = sg;
+					}
+					++nseg;
+					cum = cum_f + smem_f;
+					ones = ones_f + stok_f;
+					search = true;
+					sw = wf;
+					sq = qm_f;
+					sm = (int)m_f;
+				}
+				if (search) {
+					// ---- the pass ends on class sq of window sw at or behind slice sm: smallest slice i with
+					// cum + P(i + 1) - P(sm) >= T, by a 32-ary search on the member prefixes
+					search = false;
+					const long long t1 = clock64();
+					const u64 wbase = (u64)sw * WS;
+					const ulonglong2 pm2 = B.P[wbase + sm], pt2 = B.winPT[sw];
+					const u64 pm = sq ? pm2.y : pm2.x, ptot = sq ? pt2.y : pt2.x;
+					int lo = sm, hi = WS - 1;
+					while (hi > lo) {
+						const int span = hi - lo + 1;
+						const int step = (span + 31) / 32;
+						int probe = lo + lane * step + step - 1;
+						if (probe > hi)
+							probe = hi;
+						u64 pn;
+						if (probe + 1 < WS) {
+							const ulonglong2 v = B.P[wbase + probe + 1];
+							pn = sq ? v.y : v.x;
+						} else {
+							pn = ptot;
+						}
+						const u32 bal = __ballot_sync(FULL, cum + (pn - pm) >= T);
+						const int f = bal ? __ffs((int)bal) - 1 : 31; // bal != 0 by construction
+						const int nlo = lo + f * step;
+						int nhi = nlo + step - 1;
+						if (nhi > hi)
+							nhi = hi;
+						lo = nlo < hi ? nlo : hi;
+						hi = nhi;
+					}
+					const u64 egs = wbase + lo;
+					const ulonglong2 pi2 = B.P[egs];
+					const u32 tki = B.TK[egs], tkm = B.TK[wbase + sm];
+					const u32 e = (B.E[egs] >> (16 * sq)) & 0xffffu;
+					cum += (sq ? pi2.y : pi2.x) - pm;
+					ones += sq ? (tki >> 16) - (tkm >> 16) : (tki & 0xffffu) - (tkm & 0xffffu);
+					u64 a, b;
+					load_slice(stream, end_bits, egs, a, b);
+					d = (int)(e & 63u);
+					k = (int)(e >> 6);
+					if (e == PDEAD) {
+						event = EV_STOP; // cannot happen: the prefixes say tokens start here
+					} else {
+						event = walk_events(a, b, clamp_avail(end_bits, egs << 6), T, d, k, cum, ones, f_pending);
+						if (event == EV_NONE && cum >= T)
+							event = EV_COVERED; // the pass ends exactly with the slice's last token
+						if (event == EV_NONE)
+							event = EV_STOP; // cannot happen
+					}
+					f_pos = (egs << 6) + (u64)d;
+					f_k = k;
+					cyc[2] += clock64() - t1;
+				}
+			}
+			if (lane == 0)
+				st->dbg_cs[j] = (unsigned short)min(dbg_stray - stray_before, 65535u);
+			if (event == EV_COVERED)
+				f_pending = 0;
+		}
+		// ---------------------------------------------------- refinement pass bookkeeping (decode.c:89-98,206,223,240)
+		if (event == EV_STOP) {
+			stop = true;
+			f_pos = bitpos;
+			f_k = order;
+			f_pending = 0;
+		}
+		bool complete = !stop;
+		int ref_valid = 0;
+		const u64 ref_pos = f_pos;
+		if (!stop && nref > 0) {
+			if (f_pending > 1) {
+				stop = true; // rle.h:98-99: a pending run must end exactly at the phantom one
+				complete = false;
+			} else {
+				f_pending = 0;
+				ref_valid = 1;
+				if (f_pos + nref > end_bits) {
+					stop = true; // partial refinement: the deposit keeps the bits before EOF
+					complete = false;
+				} else {
+					f_pos += nref;
+				}
+			}
+		}
+		bitpos = f_pos;
+		order = f_k;
+		pending = f_pending;
+		stopped = stop;
+		if (lane == 0) {
+			DecChunk ck;
+			ck.rank_base = my_rank_base;
+			ck.ref_bitpos = ref_pos;
+			ck.r0 = (u32)r0;
+			ck.T = (u32)T;
+			ck.parsed = 1;
+			ck.ref_valid = ref_valid;
+			B.chunks[j] = ck;
+			if (complete)
+				missing[c * 16 + l] -= 1;
+			sigcount[c * 16 + l] = nsig + ones;
+		}
+		__syncwarp();
+	}
+	__syncwarp();
+	for (int i = lane; i < 48; i += 32)
+		st->missing[i] = missing[i];
+	if (lane == 0) {
+		st->bitpos = bitpos;
+		st->order = order;
+		st->pending = pending;
+		st->stopped = stopped ? 1 : 0;
+		st->level = level;
+		st->nseg = nseg;
+		st->dbg_slow = dbg_slow;
+		st->dbg_stray = dbg_stray;
+		st->dbg_cyc[0] = (u64)cyc[0];
+		st->dbg_cyc[1] = (u64)cyc[1];
+		st->dbg_cyc[2] = (u64)cyc[2];
+		st->dbg_cyc[3] = (u64)(clock64() - t_begin);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------- emit
+
+// ones and signs of the tokens that start in one slice; false when the chain ends here
+__device__ __forceinline__ bool emit_slice(u64 a, u64 b, int avail, u64 T, u64 base, int &d, int &k, u64 &cum,
+                                           u32 *ones_rank, u32 *sign_rank)
+{
+	while (d < 64) {
+		const u64 w = bits_from(a, b, d);
+		const u32 lo = (u32)w;
+		const int u = lo ? __ffs((int)lo) - 1 : 32;
+		const int e = k + u;
+		const int L = u + 1 + e;
+		if (e > 31 || d + L > avail)
+			return false;
+		const u32 payload = (u32)(w >> (u + 1)) & ((1u << e) - 1u);
+		const u64 one = cum + (u64)((1u << e) - (1u << k)) + payload;
+		if (one >= T)
+			return false;
+		const u64 rk = base + one;
+		atomicOr(ones_rank + (rk >> 5), 1u << (rk & 31));
+		if (d + L + 1 > avail)
+			return false;
+		if ((w >> L) & 1ull)
+			atomicOr(sign_rank + (rk >> 5), 1u << (rk & 31));
+		cum = one + 1;
+		d += L + 1;
+		k = e >= 2 ? e - 2 : 0;
+	}
+	return cum < T;
+}
+
+__global__ void __launch_bounds__(WS) dec_emit_kernel(const __grid_constant__ DecBuffers B)
+{
+	if (blockIdx.x >= B.state->nseg)
+		return;
+	const DecSeg s = B.seg[blockIdx.x];
+	const DecChunk ck = B.chunks[s.j];
+	const int i = threadIdx.x;
+	const int m = s.m;
+	const u64 T = ck.T;
+	const u64 base = ck.rank_base + ck.r0;
+	const u64 wbase = (u64)s.w * WS;
+	if (i == s.i0 && m > i) {
+		// exact steps through the slices in front of the join
+		int d = (int)(s.state & 63u), k = (int)(s.state >> 6);
+		u64 cum = s.cum0;
+		for (int ii = i; ii < m; ++ii) {
+			u64 a, b;
+			const u64 gs = wbase + ii;
+			load_slice(B.stream, B.end_bits, gs, a, b);
+			if (!emit_slice(a, b, clamp_avail(B.end_bits, gs << 6), T, base, d, k, cum, B.ones_rank, B.sign_rank))
+				break;
+			d -= 64;
+		}
+	} else if (i >= m) {
+		const u64 gs = wbase + i;
+		const u32 e = (B.E[gs] >> (16 * s.qm)) & 0xffffu;
+		if (e == PDEAD)
+			return;
+		const ulonglong2 pi = B.P[gs], pm = B.P[wbase + m];
+		u64 cum = (u64)s.cum_m + (s.qm ? pi.y - pm.y : pi.x - pm.x);
+		if (cum >= T)
+			return;
+		u64 a, b;
+		load_slice(B.stream, B.end_bits, gs, a, b);
+		int d = (int)(e & 63u), k = (int)(e >> 6);
+		emit_slice(a, b, clamp_avail(B.end_bits, gs << 6), T, base, d, k, cum, B.ones_rank, B.sign_rank);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------- deposit
 
 __device__ __forceinline__ u32 group_valid_mask(const Geom &G, int l, int g)
 {
@@ -71,732 +855,177 @@ __device__ __forceinline__ u32 group_valid_mask(const Geom &G, int l, int g)
 	return rem >= 32 ? 0xffffffffu : ((1u << (int)rem) - 1u);
 }
 
-__global__ void __launch_bounds__(TG) dec_prep_kernel(const __grid_constant__ Geom G, int l, const u32 *__restrict__ sig,
-                                                       u32 *tile_sums)
+__device__ __forceinline__ int level_of_tile(const Geom &G, int tile)
+{
+	int l = 0;
+	while (l + 1 < G.levels && G.tbase[l + 1] <= tile)
+		++l;
+	return l;
+}
+
+// chunk of (channel c, level l) at plane depth `depth` (0 = the channel's top plane), or -1
+__device__ __forceinline__ int chunk_at(const Sched *S, const DecChunk *chunks, int nchunks, int c, int l, int depth,
+                                        int *plane)
+{
+	const int p = S->planes[c] - 1 - depth;
+	if (p < 0)
+		return -1;
+	const int j = S->chunk_of[c][l][p];
+	if (j < 0 || j >= nchunks || !chunks[j].parsed)
+		return -1;
+	*plane = p;
+	return j;
+}
+
+// members (still insignificant) and refinement positions per tile of 256 groups
+__global__ void __launch_bounds__(TG) dec_prep_kernel(const __grid_constant__ Geom G, const __grid_constant__ DecBuffers B,
+                                                       int nchunks, int depth)
 {
 	__shared__ u32 acc[2];
+	const int c = blockIdx.y, tile = blockIdx.x;
+	const int l = level_of_tile(G, tile);
+	int p;
+	if (chunk_at(B.sched, B.chunks, nchunks, c, l, depth, &p) < 0)
+		return;
 	if (threadIdx.x < 2)
 		acc[threadIdx.x] = 0;
 	__syncthreads();
-	const int g = blockIdx.x * TG + threadIdx.x;
+	const int g = (tile - G.tbase[l]) * TG + threadIdx.x;
 	const u32 vm = group_valid_mask(G, l, g);
-	const u32 s = vm ? sig[g] : 0u;
-	u32 m = __reduce_add_sync(0xffffffffu, (u32)__popc(vm & ~s));
-	u32 r = __reduce_add_sync(0xffffffffu, (u32)__popc(s));
+	const u32 s = vm ? B.sig[(size_t)c * G.GT + G.gbase[l] + g] : 0u;
+	const u32 m = __reduce_add_sync(0xffffffffu, (u32)__popc(vm & ~s));
+	const u32 r = __reduce_add_sync(0xffffffffu, (u32)__popc(s));
 	if ((threadIdx.x & 31) == 0) {
 		atomicAdd(&acc[0], m);
 		atomicAdd(&acc[1], r);
 	}
 	__syncthreads();
 	if (threadIdx.x < 2)
-		tile_sums[2 * blockIdx.x + threadIdx.x] = acc[threadIdx.x];
+		B.tile_sums[2 * ((size_t)c * G.tbase[G.levels] + tile) + threadIdx.x] = acc[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(1024) dec_tilescan_kernel(DecState *st, const u32 *__restrict__ tile_sums, u32 *tile_base,
-                                                             int ntile, u64 *win_state, u64 *win_rank, int nwin_cap,
-                                                             int level)
+// exclusive prefixes of the tile counts inside every (channel, level)
+__global__ void __launch_bounds__(1024) dec_tilescan_kernel(const __grid_constant__ Geom G,
+                                                             const __grid_constant__ DecBuffers B, int nchunks, int depth)
 {
 	__shared__ u64 ws[32];
-	const int tid = threadIdx.x;
-	if (st->stopped)
+	const int l = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+	int p;
+	if (chunk_at(B.sched, B.chunks, nchunks, c, l, depth, &p) < 0)
 		return;
+	const int ntile = G.ntile[l];
+	const u32 *sums = B.tile_sums + 2 * ((size_t)c * G.tbase[G.levels] + G.tbase[l]);
+	u32 *base = B.tile_base + 2 * ((size_t)c * G.tbase[G.levels] + G.tbase[l]);
 	const int per = (ntile + 1023) / 1024;
 	const int b = tid * per, e = min(b + per, ntile);
 	u64 sm = 0, sr = 0;
 	for (int i = b; i < e; ++i) {
-		sm += tile_sums[2 * i];
-		sr += tile_sums[2 * i + 1];
+		sm += sums[2 * i];
+		sr += sums[2 * i + 1];
 	}
 	u64 tm, tr;
-	u64 bm = block_exscan_u64(sm, ws, &tm);
-	u64 br = block_exscan_u64(sr, ws, &tr);
+	const u64 bm = block_exscan_u64(sm, ws, &tm);
+	const u64 br = block_exscan_u64(sr, ws, &tr);
 	u32 rm = (u32)bm, rr = (u32)br;
 	for (int i = b; i < e; ++i) {
-		u32 m = tile_sums[2 * i], r = tile_sums[2 * i + 1];
-		tile_base[2 * i] = rm;
-		tile_base[2 * i + 1] = rr;
+		const u32 m = sums[2 * i], r = sums[2 * i + 1];
+		base[2 * i] = rm;
+		base[2 * i + 1] = rr;
 		rm += m;
 		rr += r;
 	}
-	// windows this chunk can touch at most: from its first slice to the end of the stream
-	const u64 first = st->bitpos & ~63ull;
-	u64 nwin = windows_for((st->end_bits > first ? (st->end_bits - first) >> 6 : 0) + 2) + 1;
-	if (nwin > (u64)nwin_cap)
-		nwin = nwin_cap;
-	for (u64 w = tid; w < nwin; w += 1024) {
-		win_state[w] = 0;
-		win_rank[w] = 0;
-	}
-	if (tid == 0) {
-		st->n_member = (u32)tm;
-		st->n_ref = (u32)tr;
-		if (st->level < level)
-			st->level = level; // decode.c:203,219-220,236-237: the chunk is started
-		st->ticket = 0;
-		st->published = 0;
-		st->done = 0;
-		st->c_bitpos = st->bitpos;
-		st->c_order = st->order;
-		st->c_pending = st->pending;
-	}
 }
 
-__device__ __forceinline__ u64 peek64(const u32 *__restrict__ s, u64 pos)
-{
-	const u64 w = pos >> 5;
-	const int sh = (int)(pos & 31);
-	const u64 lo = (u64)__ldg(s + w) | ((u64)__ldg(s + w + 1) << 32);
-	u64 v = lo >> sh;
-	if (sh)
-		v |= (u64)__ldg(s + w + 2) << (64 - sh);
-	return v;
-}
-
-// one [VLI] token at (pos, k): returns false when it cannot be read completely (EOF / invalid)
-__device__ __forceinline__ bool read_vli(const u32 *__restrict__ s, u64 end_bits, u64 pos, int k, u64 *n, int *len,
-                                         int *knext, u64 *word)
-{
-	if (pos >= end_bits)
-		return false;
-	const u64 w = peek64(s, pos);
-	const int u = w ? __ffsll((long long)w) - 1 : 64;
-	const int e = k + u;
-	if (e > 31)
-		return false;
-	const int L = u + 1 + e;
-	if (pos + L > end_bits)
-		return false;
-	const u32 payload = (u32)(w >> (u + 1)) & (u32)((1ull << e) - 1ull);
-	*n = ((1ull << e) - (1ull << k)) + payload;
-	*len = L;
-	*knext = e >= 2 ? e - 2 : 0;
-	*word = w;
-	return true;
-}
-
-// slice-local token step on the two 64-bit words of a slice (w0 = the slice, w1 = the 64 bits behind it):
-// token at offset d (< 64) with order k; avail = stream bits left from the slice start.
-// Returns the offset behind [VLI][sign] (may be >= 64) or -1 when the chain dies.
-// Only the unary prefix decides a token's length, and it is at most 31 zeros, so a 32-bit window suffices.
-__device__ __forceinline__ int slice_step(u64 w0, u64 w1, int avail, int d, int &k)
-{
-	const u32 lo = d < 32 ? (u32)w0 : (u32)(w0 >> 32);
-	const u32 hi = d < 32 ? (u32)(w0 >> 32) : (u32)w1;
-	const u32 bits = __funnelshift_r(lo, hi, d & 31);
-	const int u = bits ? __ffs((int)bits) - 1 : 32;
-	const int e = k + u;
-	const int L = u + 1 + e;
-	if (e > 31 || d >= avail || d + L > avail)
-		return -1;
-	k = e >= 2 ? e - 2 : 0;
-	return d + L + 1;
-}
-
-__device__ __forceinline__ int clamp_avail(u64 end_bits, u64 lo_bit)
-{
-	const long long av = (long long)end_bits - (long long)lo_bit;
-	return av > (1 << 30) ? (1 << 30) : (av < -(1 << 30) ? -(1 << 30) : (int)av);
-}
-
-// the two 64-bit words a slice's token steps can touch (zero behind the padded end of the stream)
-__device__ __forceinline__ void load_slice(const u32 *__restrict__ stream, u64 end_bits, u64 slice, u64 &w0, u64 &w1)
-{
-	const u64 lo = slice << 6;
-	w0 = lo < end_bits + 128 ? __ldg((const u64 *)stream + slice) : 0ull;
-	w1 = lo < end_bits + 64 ? __ldg((const u64 *)stream + slice + 1) : 0ull;
-}
-
-// exit state of a slice for the entry (off, k), using the slice's order-0 table for the order-0 part
-__device__ __forceinline__ unsigned short slice_exit(const unsigned short *row, u64 w0, u64 w1, int avail,
-                                                     unsigned short entry)
-{
-	if (entry == PDEAD)
-		return PDEAD;
-	int d = st_off(entry), k = st_k(entry);
-	while (k != 0) { // excursion at a non-zero order: plain token steps until the order is back to 0
-		d = slice_step(w0, w1, avail, d, k);
-		if (d < 0)
-			return PDEAD;
-		if (d >= 64)
-			return pack_state(d - 64, k);
-	}
-	return row[d];
-}
-
-// members consumed by the tokens that start inside the slice [lo, lo+64), beginning at (pos, k)
-__device__ __forceinline__ u64 count_slice(const u32 *__restrict__ s, u64 end_bits, u64 lo, u64 pos, int k)
-{
-	const u64 lim = lo + SLICE;
-	u64 csum = 0;
-	while (k != KDEAD && pos < lim) {
-		u64 n, w;
-		int len, kn;
-		if (!read_vli(s, end_bits, pos, k, &n, &len, &kn, &w))
-			break;
-		csum += n + 1;
-		pos += len + 1;
-		k = kn;
-	}
-	return csum;
-}
-
-enum { EV_NONE = 0, EV_COVERED = 1, EV_PENDING = 2, EV_STOP = 3 };
-
-// refinement pass bookkeeping of one chunk (decode.c:89-98,206,223,240); runs in exactly one thread
-__device__ void finish_chunk(DecState *st, bool stop, u64 bitpos, int order, u32 pending, u32 nref, int chan, int level)
-{
-	const u64 end_bits = st->end_bits;
-	const bool sig_done = !stop; // every member has its symbol (or is covered by the carried run)
-	bool complete = sig_done;
-	int ref_valid = 0;
-	const u64 ref_pos = bitpos;
-	if (sig_done && nref > 0) {
-		if (pending > 1) {
-			stop = true; // rle.h:98-99: a pending run must end exactly at the phantom one
-			complete = false;
-		} else {
-			pending = 0;
-			ref_valid = 1;
-			if (bitpos + nref > end_bits) {
-				stop = true; // partial refinement: the deposit keeps the bits before EOF
-				complete = false;
-			} else {
-				bitpos += nref;
-			}
-		}
-	}
-	st->ref_bitpos = ref_pos;
-	st->ref_valid = ref_valid;
-	st->bitpos = bitpos;
-	st->order = order == KDEAD ? 0 : order;
-	st->pending = pending;
-	st->stopped = stop ? 1 : 0;
-	st->chunk_done += 1;
-	if (complete)
-		st->missing[chan * 16 + level] -= 1;
-	__threadfence();
-	st->done = 1;
-}
-
-__global__ void __launch_bounds__(PT, 1) dec_parse_kernel(DecState *st, const u32 *__restrict__ stream, u32 *ones_rank,
-                                                           u32 *sign_rank, u64 *win_state, u64 *win_rank, int nwin_cap,
-                                                           int chan, int level)
-{
-	extern __shared__ unsigned short T[];        // [PT][ROW] order-0 transfer tables of the window's slices
-	__shared__ u64 ws[32];
-	__shared__ u32 wmap[32];
-	__shared__ unsigned short ecan[2][PT];       // entries of the two canonical chains
-	__shared__ unsigned short xcan[2][PT];       // their exits
-	__shared__ unsigned short etrue[PT];         // entries of the true chain where it was stepped exactly
-	__shared__ u64 winfo[PT];                    // per slice: predicted entries of both chains + their next wrong link
-	__shared__ u32 xpair[PT];                    // per slice: exact exits of both chains for those entries
-	__shared__ unsigned char mark[PT];           // walker marks: 1/2 = follows predicted chain 0/1 from here, 3 = exact, 4 = dead
-	__shared__ u64 sw[PT + 1];                   // the window's stream words
-	__shared__ u32 s_w;
-	__shared__ int s_done, s_merge_at, winner;
-	__shared__ u64 s_rank_excl;
-	__shared__ u64 f_pos;
-	__shared__ int f_k, f_event;
-	__shared__ u32 f_pending;
-	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	if (st->stopped)
-		return;
-
-	// ---- chunk entry state (identical in every CTA; side effects only in block 0)
-	const u64 end_bits = st->end_bits;
-	const u64 R = st->n_member;
-	const u32 nref = st->n_ref;
-	u64 bitpos = st->c_bitpos; // entry snapshot taken by dec_tilescan_kernel: never written while this kernel runs
-	const int order = st->c_order;
-	u32 pending = st->c_pending;
-	u64 r0 = 0; // members already accounted for
-	bool stop = false;
-	// a run carried in from earlier chunks (rle.h:66-77): (pending-1) zeros, then a one
-	if (pending > 0) {
-		if ((u64)pending - 1 >= R) {
-			pending -= (u32)R;
-			r0 = R;
-		} else {
-			const u64 rk = pending - 1;
-			if (blockIdx.x == 0 && tid == 0)
-				atomicOr(ones_rank + (rk >> 5), 1u << (rk & 31));
-			if (bitpos < end_bits) {
-				if (blockIdx.x == 0 && tid == 0 && (peek64(stream, bitpos) & 1ull))
-					atomicOr(sign_rank + (rk >> 5), 1u << (rk & 31));
-				bitpos += 1;
-			} else {
-				stop = true; // the sign bit hits EOF: the magnitude bit stays (decode.c:80-86)
-			}
-			r0 = (u64)pending;
-			pending = 0;
-		}
-	}
-	if (stop || pending != 0 || r0 >= R) { // no token to parse in this chunk
-		__syncthreads(); // every thread has read the entry state before it is overwritten
-		if (blockIdx.x == 0 && tid == 0)
-			finish_chunk(st, stop, bitpos, order, pending, nref, chan, level);
-		return;
-	}
-	const u64 Rrem = R - r0;
-	const u64 S0 = bitpos >> 6; // first slice of window 0
-	u64 nwin = windows_for(((end_bits - (S0 << 6)) >> 6) + 2) + 1;
-	{
-		// a token is at most 33 bits per member it covers (order <= 31), so the pass cannot reach further
-		const u64 bound = windows_for((Rrem * 33 + 63) / 64 + 2) + 1;
-		if (nwin > bound)
-			nwin = bound;
-	}
-	if (nwin > (u64)nwin_cap)
-		nwin = nwin_cap;
-
-	for (;;) {
-		__syncthreads();
-		if (tid == 0) {
-			const u32 tk = atomicAdd(&st->ticket, 1u);
-			// speculation is throttled: at most as many unconfirmed windows as confirmed ones (+2), so a chunk
-			// that ends in its first window does not pay for 148 table builds behind it
-			volatile u32 *pub = &st->published;
-			volatile int *dn = &st->done;
-			int d = *dn;
-			while (!d && tk < nwin && tk >= 2u * *pub + 2u)
-				d = *dn;
-			s_w = tk;
-			s_done = d;
-			winner = PT;
-		}
-		__syncthreads();
-		const u32 w = s_w;
-		if (s_done || w >= nwin) {
-			// a ticket holder must publish even when the pass is over: a later window may be waiting on it
-			if (tid == 0 && w < nwin) {
-				win_state[w] = FLAG | PDEAD;
-				win_rank[w] = FLAG | (FLAG - 1);
-				__threadfence();
-			}
-			break;
-		}
-		const long long t_win0 = clock64();
-		const int sz = win_size(w);                 // active slices (threads) of this window
-		const u64 wslice0 = S0 + win_start(w);      // its first slice
-		const u64 slice = wslice0 + tid;
-		const u64 sub_lo = slice << 6;
-		const int avail = clamp_avail(end_bits, sub_lo);
-		u64 w0, w1;
-		load_slice(stream, end_bits, slice, w0, w1);
-		unsigned short *row = T + tid * ROW;
-
-		// (1) order-0 transfer table of my slice, by dynamic programming from the slice end
-		for (int d = tid < sz ? 63 : -1; d >= 0; --d) {
-			int k = 0;
-			int nd = slice_step(w0, w1, avail, d, k);
-			unsigned short v = PDEAD;
-			while (nd >= 0) {
-				if (nd >= 64) {
-					v = pack_state(nd - 64, k);
-					break;
-				}
-				if (k == 0) {
-					v = row[nd];
-					break;
-				}
-				nd = slice_step(w0, w1, avail, nd, k);
-			}
-			row[d] = v;
-		}
-		// (2) predicted chains.  Chain c starts with a token at offset c of the window at order 0.  The parity
-		// class every slice is entered with comes from a scan of 2-state maps; the predicted entry of a slice is
-		// the table exit of its predecessor, and ONE exact evaluation per slice tells which links
-		// (slice i -> i+1) the prediction got right.  No iteration: wrong links are repaired by the walker.
-		sw[tid] = w0;
-		if (tid == sz - 1)
-			sw[sz] = w1;
-		mark[tid] = 0;
-		u32 mymap = 0;
-#pragma unroll
-		for (int c = 0; c < 2; ++c) {
-			unsigned short x = row[c];
-			u32 out = (x != PDEAD && st_k(x) == 0) ? (u32)(st_off(x) & 1) : 0u;
-			mymap |= out << c;
-		}
-		u32 inc = mymap; // bit b = class after this slice when entered with class b
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			u32 t = __shfl_up_sync(0xffffffffu, inc, d);
-			if (lane >= d)
-				inc = ((inc >> (t & 1u)) & 1u) | (((inc >> ((t >> 1) & 1u)) & 1u) << 1);
-		}
-		if (lane == 31)
-			wmap[wid] = inc;
-		__syncthreads();
-		u32 pre = 2u; // identity: class 0 -> 0, class 1 -> 1
-		for (int i = 0; i < wid; ++i) {
-			u32 m = wmap[i];
-			pre = ((m >> (pre & 1u)) & 1u) | (((m >> ((pre >> 1) & 1u)) & 1u) << 1);
-		}
-		u32 excl = __shfl_up_sync(0xffffffffu, inc, 1);
-		if (lane > 0)
-			pre = ((excl >> (pre & 1u)) & 1u) | (((excl >> ((pre >> 1) & 1u)) & 1u) << 1);
-		// pre: class my slice is entered with on chain 0 (bit 0) and chain 1 (bit 1)
-		xcan[0][tid] = row[pre & 1u];
-		xcan[1][tid] = row[(pre >> 1) & 1u];
-		__syncthreads();
-		unsigned short e_c[2], x_c[2];
-#pragma unroll
-		for (int c = 0; c < 2; ++c)
-			e_c[c] = tid == 0 ? pack_state(c, 0) : xcan[c][tid - 1];
-		__syncthreads();
-#pragma unroll
-		for (int c = 0; c < 2; ++c)
-			x_c[c] = tid < sz ? slice_exit(row, w0, w1, avail, e_c[c]) : PDEAD;
-		// a fixed number of refinement rounds (entry <- predecessor's exact exit) repairs the links where the
-		// predicted entry needed more than one slice to join the chain
-		for (int it = 0; it < REFINE_ROUNDS; ++it) {
-			xcan[0][tid] = x_c[0];
-			xcan[1][tid] = x_c[1];
-			__syncthreads();
-			if (tid > 0 && tid < sz) {
-#pragma unroll
-				for (int c = 0; c < 2; ++c) {
-					const unsigned short ne = xcan[c][tid - 1];
-					if (ne != e_c[c]) {
-						e_c[c] = ne;
-						x_c[c] = slice_exit(row, w0, w1, avail, ne);
-					}
-				}
-			}
-			__syncthreads();
-		}
-#pragma unroll
-		for (int c = 0; c < 2; ++c) {
-			ecan[c][tid] = e_c[c];
-			xcan[c][tid] = x_c[c];
-		}
-		__syncthreads();
-		// nbad[c] = first slice j >= i whose exit does not match the predicted entry of slice j+1;
-		// everything the walker needs about slice i goes into one 64-bit record
-		u32 nb[2];
-#pragma unroll
-		for (int c = 0; c < 2; ++c) {
-			const bool ok = tid < sz - 1 && x_c[c] == ecan[c][tid + 1];
-			u32 v = ok ? 0xffffu : (u32)tid;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				u32 t = __shfl_down_sync(0xffffffffu, v, d);
-				if (lane + d < 32)
-					v = min(v, t);
-			}
-			if (lane == 0)
-				wmap[wid] = v;
-			__syncthreads();
-			for (int i = wid + 1; i < PT / 32; ++i)
-				v = min(v, wmap[i]);
-			nb[c] = v;
-			__syncthreads();
-		}
-		winfo[tid] = (u64)e_c[0] | ((u64)e_c[1] << 16) | ((u64)nb[0] << 32) | ((u64)nb[1] << 48);
-		xpair[tid] = (u32)x_c[0] | ((u32)x_c[1] << 16);
-		__syncthreads();
-
-		// (3) the serial step: previous window's exit -> walk the true chain.  Where it coincides with a predicted
-		// chain it jumps to that chain's next wrong link; elsewhere it steps exactly, one slice at a time.
-		if (tid == 0) {
-			const long long t_wait0 = clock64();
-			unsigned short state = PDEAD;
-			bool over = false;
-			if (w == 0) {
-				state = pack_state((int)(bitpos & 63), order);
-			} else {
-				volatile u64 *src = win_state + (w - 1);
-				volatile int *dn = &st->done;
-				u64 v;
-				u32 spins = 0;
-				while (!((v = *src) & FLAG))
-					if ((++spins & 31u) == 0 && *dn) {
-						over = true;
-						break;
-					}
-				state = over ? PDEAD : (unsigned short)(v & 0xffffu);
-			}
-			int i = 0;
-			u32 nexact = 0, njump = 0;
-			const long long t_walk0 = clock64();
-			if (over) {
-				i = -1; // the pass ended in an earlier window: nothing to do here
-			} else if (state == PDEAD) {
-				i = -2; // dead on arrival
-			} else {
-				long long av = (long long)end_bits - (long long)(wslice0 << 6);
-				const int availw = av > (1 << 30) ? (1 << 30) : (av < -(1 << 30) ? -(1 << 30) : (int)av);
-				u32 st32 = state;
-				while (i < sz) {
-					if (st32 == PDEAD) { // the chain died inside this window: later slices have no tokens
-						mark[i] = 4;
-						break;
-					}
-					const u64 rec = winfo[i];
-					const int c = st32 == (u32)(rec & 0xffffu) ? 0 : (st32 == (u32)((rec >> 16) & 0xffffu) ? 1 : -1);
-					if (c >= 0) {
-						const int j = (int)((rec >> (32 + 16 * c)) & 0xffffu);
-						mark[i] = (unsigned char)(1 + c);
-						st32 = (xpair[j] >> (16 * c)) & 0xffffu;
-						i = j + 1;
-						++njump;
-						continue;
-					}
-					mark[i] = 3;
-					etrue[i] = (unsigned short)st32;
-					++nexact;
-					// exact step through slice i: table look-up at order 0, plain token steps otherwise
-					int off = st32 & 63, k = (st32 >> 6) & 63;
-					const unsigned short *trow = T + i * ROW;
-					if (k != 0) {
-						const u64 a = sw[i], b = sw[i + 1];
-						const int avail_i = availw - 64 * i;
-						for (;;) {
-							const u32 lo = off < 32 ? (u32)a : (u32)(a >> 32);
-							const u32 hi = off < 32 ? (u32)(a >> 32) : (u32)b;
-							const u32 bits = __funnelshift_r(lo, hi, off & 31);
-							const int u = bits ? __ffs((int)bits) - 1 : 32;
-							const int e = k + u;
-							const int L = u + 1 + e;
-							if (e > 31 || off >= avail_i || off + L > avail_i) {
-								off = -1;
-								break;
-							}
-							k = e >= 2 ? e - 2 : 0;
-							off += L + 1;
-							if (off >= 64 || k == 0)
-								break;
-						}
-					}
-					if (off < 0)
-						st32 = PDEAD;
-					else if (off >= 64)
-						st32 = (u32)pack_state(off - 64, k);
-					else
-						st32 = trow[off];
-					++i;
-				}
-				state = (unsigned short)st32;
-				i = 0;
-			}
-			win_state[w] = FLAG | state; // flag and value travel in one 64-bit word: no fence needed
-			*(volatile u32 *)&st->published = w + 1;
-			if (over)
-				win_rank[w] = FLAG | (FLAG - 1);
-			const long long t_walk1 = clock64();
-			atomicAdd(&st->dbg_walk, nexact);
-			atomicAdd(&st->dbg_iters, njump);
-			atomicAdd(&st->dbg_cyc[0], (u64)(t_wait0 - t_win0));
-			atomicAdd(&st->dbg_cyc[1], (u64)(t_walk0 - t_wait0));
-			atomicAdd(&st->dbg_cyc[2], (u64)(t_walk1 - t_walk0));
-			s_merge_at = i;
-		}
-		__syncthreads();
-		if (s_merge_at == -1)
-			break;
-		const bool dead_window = s_merge_at == -2;
-		// every slice is governed by the last mark at or before it
-		unsigned short my_entry = PDEAD;
-		{
-			int gm = mark[tid] ? tid : -1;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				int t = __shfl_up_sync(0xffffffffu, gm, d);
-				if (lane >= d)
-					gm = max(gm, t);
-			}
-			if (lane == 31)
-				wmap[wid] = (u32)gm;
-			__syncthreads();
-			for (int i = 0; i < wid; ++i)
-				gm = max(gm, (int)wmap[i]);
-			if (!dead_window && gm >= 0) {
-				const int m = mark[gm];
-				if (m == 3)
-					my_entry = etrue[tid];
-				else if (m == 1 || m == 2)
-					my_entry = ecan[m - 1][tid];
-			}
-		}
-		if (tid >= sz)
-			my_entry = PDEAD;
-		const u64 e_pos = sub_lo + st_off(my_entry);
-		const int e_k = st_k(my_entry);
-
-		// (4) members consumed per slice -> ranks inside the window; inclusive count chained across windows
-		const u64 csum = count_slice(stream, end_bits, sub_lo, e_pos, e_k);
-		u64 total;
-		u64 cum = block_exscan_u64(csum, ws, &total); // syncs inside
-		if (tid == 0) {
-			u64 base = 0;
-			if (w > 0) {
-				volatile u64 *src = win_rank + (w - 1);
-				u64 v;
-				while (!((v = *src) & FLAG))
-					;
-				base = v & ~FLAG;
-			}
-			u64 incl = base + total;
-			if (incl >= FLAG)
-				incl = FLAG - 1;
-			win_rank[w] = FLAG | incl;
-			s_rank_excl = base;
-			f_event = EV_NONE;
-		}
-		__syncthreads();
-		const u64 rank_excl = s_rank_excl;
-		if (rank_excl > Rrem || dead_window)
-			continue; // this window lies behind the end of the chunk's significance pass
-		cum += rank_excl;
-
-		// (5) the walk that writes ones and signs, and finds where the pass ends
-		{
-			u64 pos = e_pos;
-			int k = e_k;
-			int ev = EV_NONE;
-			u64 ev_pos = 0;
-			int ev_k = 0;
-			u32 ev_pending = 0;
-			const u64 lim = sub_lo + SLICE;
-			while (k != KDEAD && pos < lim) {
-				if (cum >= Rrem) {
-					ev = EV_COVERED;
-					ev_pos = pos;
-					ev_k = k;
-					break;
-				}
-				u64 n, wd;
-				int len, kn;
-				if (!read_vli(stream, end_bits, pos, k, &n, &len, &kn, &wd)) {
-					ev = EV_STOP;
-					break;
-				}
-				const u64 one = cum + n;
-				if (one < Rrem) {
-					const u64 rk = r0 + one;
-					atomicOr(ones_rank + (rk >> 5), 1u << (rk & 31));
-					if (pos + len + 1 > end_bits) {
-						ev = EV_STOP; // sign bit beyond EOF: the magnitude bit stays
-						break;
-					}
-					if ((wd >> len) & 1ull)
-						atomicOr(sign_rank + (rk >> 5), 1u << (rk & 31));
-					cum = one + 1;
-					pos += len + 1;
-					k = kn;
-				} else {
-					ev = EV_PENDING; // the run reaches past this chunk's members (rle.h:74-76)
-					ev_pending = (u32)(n - (Rrem - cum) + 1);
-					ev_pos = pos + len;
-					ev_k = kn;
-					break;
-				}
-			}
-			if (ev != EV_NONE)
-				atomicMin(&winner, tid);
-			__syncthreads();
-			if (ev != EV_NONE && winner == tid) {
-				f_event = ev;
-				f_pos = ev_pos;
-				f_k = ev_k;
-				f_pending = ev_pending;
-			}
-			__syncthreads();
-		}
-		if (f_event != EV_NONE) {
-			if (tid == 0) {
-				atomicAdd(&st->dbg_windows, w + 1);
-				if (f_event == EV_STOP)
-					finish_chunk(st, true, bitpos, order, 0, nref, chan, level);
-				else
-					finish_chunk(st, false, f_pos, f_k, f_event == EV_PENDING ? f_pending : 0u, nref, chan, level);
-			}
-			break;
-		}
-	}
-}
-
-__global__ void __launch_bounds__(TG) dec_deposit_kernel(const __grid_constant__ Geom G, int l, int chunk_seq,
-                                                          u32 *plane_words, u32 *sign_words, u32 *sig,
-                                                          const u32 *__restrict__ tile_base,
-                                                          const u32 *__restrict__ ones_rank,
-                                                          const u32 *__restrict__ sign_rank,
-                                                          const u32 *__restrict__ stream, const DecState *st)
+__global__ void __launch_bounds__(TG) dec_deposit_kernel(const __grid_constant__ Geom G, const __grid_constant__ DecBuffers B,
+                                                          int nchunks, int depth)
 {
 	__shared__ u64 ws[32];
-	if (st->chunk_done != chunk_seq)
-		return; // the parse of this chunk never ran (decoding stopped earlier)
-	const int g = blockIdx.x * TG + threadIdx.x;
+	const int c = blockIdx.y, tile = blockIdx.x;
+	const int l = level_of_tile(G, tile);
+	int p;
+	const int j = chunk_at(B.sched, B.chunks, nchunks, c, l, depth, &p);
+	if (j < 0)
+		return;
+	const DecChunk ck = B.chunks[j];
+	const Sched *S = B.sched;
+	const int g = (tile - G.tbase[l]) * TG + threadIdx.x;
+	const size_t gi = (size_t)G.gbase[l] + g;
+	u32 *sig = B.sig + (size_t)c * G.GT;
 	const u32 vm = group_valid_mask(G, l, g);
-	const u32 s = vm ? sig[g] : 0u;
+	const u32 s = vm ? sig[gi] : 0u;
 	const u32 member = vm & ~s;
 	const u32 nm = __popc(member), nr = __popc(s);
 	u64 tot;
 	const u64 ex = block_exscan_u64((u64)nm | ((u64)nr << 32), ws, &tot);
 	if (!vm)
 		return;
-	u32 B = 0;
+	const u32 *tb = B.tile_base + 2 * ((size_t)c * G.tbase[G.levels] + tile);
+	u32 *plane_words = B.bs + S->bsbase[c] + (long long)p * G.GT;
+	u32 *sign_words = B.bs + S->bsbase[c] + (long long)S->planes[c] * G.GT;
+	u32 Bw = 0;
 	if (nm) {
-		const u64 off = (u64)tile_base[2 * blockIdx.x] + (u32)ex;
-		u32 ob = bits_get32(ones_rank, off);
+		const u64 off = ck.rank_base + tb[0] + (u32)ex;
+		u32 ob = bits_get32(B.ones_rank, off);
 		if (nm < 32)
 			ob &= (1u << nm) - 1u;
 		if (ob) {
-			B = bit_expand(ob, member);
-			u32 sb = bits_get32(sign_rank, off) & ob;
+			Bw = bit_expand(ob, member);
+			const u32 sb = bits_get32(B.sign_rank, off) & ob;
 			if (sb)
-				sign_words[g] |= bit_expand(sb, member);
+				sign_words[gi] |= bit_expand(sb, member);
 		}
 	}
-	if (nr && st->ref_valid) {
-		const u64 pos = st->ref_bitpos + tile_base[2 * blockIdx.x + 1] + (u32)(ex >> 32);
-		const u64 end = st->end_bits;
+	if (nr && ck.ref_valid) {
+		const u64 pos = ck.ref_bitpos + tb[1] + (u32)(ex >> 32);
+		const u64 end = B.end_bits;
 		if (pos < end) {
-			u32 rb = (u32)peek64(stream, pos);
-			u64 avail = end - pos;
+			const u64 w = pos >> 5;
+			const int sh = (int)(pos & 31);
+			u32 rb = __funnelshift_r(__ldg(B.stream + w), __ldg(B.stream + w + 1), sh);
+			const u64 avail = end - pos;
 			u32 take = nr;
 			if (avail < take)
 				take = (u32)avail;
 			if (take < 32)
 				rb &= (1u << take) - 1u;
-			B |= bit_expand(rb, s);
+			Bw |= bit_expand(rb, s);
 		}
 	}
-	plane_words[g] = B;
-	if (B)
-		sig[g] = s | B;
+	plane_words[gi] = Bw;
+	if (Bw)
+		sig[gi] = s | Bw;
 }
-
-constexpr size_t PARSE_SMEM = (size_t)PT * ROW * sizeof(unsigned short);
 
 } // namespace
 
-int dec_setup(void)
+u64 dec_rank_bits(const Geom &g, const Sched &hs, int nchunks)
 {
-	CUDA_OK(cudaFuncSetAttribute(dec_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PARSE_SMEM));
-	return 0;
+	u64 bits = 0;
+	for (int j = 0; j < nchunks; ++j)
+		bits += ((u64)g.num[hs.level[j]] + 63) & ~63ull;
+	return bits;
 }
 
-int dec_chunk(const Geom &g, const Sched &hs, const DecBuffers &b, int j, cudaStream_t st, long long *launches)
+int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b, int nchunks, cudaStream_t st, long long *launches)
 {
-	const int c = hs.chan[j], l = hs.level[j], p = hs.plane[j];
-	const int ntile = g.ntile[l];
-	const size_t rank_words = (size_t)g.G[l] + 4;
-	// ones_rank and sign_rank are adjacent halves of one buffer
-	CUDA_OK(cudaMemsetAsync(b.ones_rank, 0, rank_words * 4, st));
-	CUDA_OK(cudaMemsetAsync(b.sign_rank, 0, rank_words * 4, st));
-	u32 *sig = b.sig + (size_t)c * g.GT + g.gbase[l];
-	u32 *plane_words = b.bs + hs.bsbase[c] + (long long)p * g.GT + g.gbase[l];
-	u32 *sign_words = b.bs + hs.bsbase[c] + (long long)hs.planes[c] * g.GT + g.gbase[l];
-	dec_prep_kernel<<<ntile, TG, 0, st>>>(g, l, sig, b.tile_sums);
-	dec_tilescan_kernel<<<1, 1024, 0, st>>>(b.state, b.tile_sums, b.tile_base, ntile, b.win_state, b.win_rank, b.nwin_cap,
-	                                        l);
-	dec_parse_kernel<<<b.parse_ctas, PT, PARSE_SMEM, st>>>(b.state, b.stream, b.ones_rank, b.sign_rank, b.win_state,
-	                                                       b.win_rank, b.nwin_cap, c, l);
-	dec_deposit_kernel<<<ntile, TG, 0, st>>>(g, l, j + 1, plane_words, sign_words, sig, b.tile_base, b.ones_rank,
-	                                         b.sign_rank, b.stream, b.state);
+	dec_scan_kernel<<<b.nwin, WS, 0, st>>>(b.stream, b.end_bits, b.E, b.P, b.TK, b.winX, b.winPT, b.winTT);
+	dec_link_kernel<<<(2 * b.nwin + 127) / 128, 128, 0, st>>>(b.stream, b.end_bits, b.nwin, b.E, b.P, b.TK, b.winX, b.winPT,
+	                                                           b.winTT, b.link);
+	dec_resolve_kernel<<<1, 32, 0, st>>>(g, nchunks, b);
+	dec_emit_kernel<<<b.nwin + (u32)nchunks, WS, 0, st>>>(b);
 	*launches += 4;
+	int depth_max = 0;
+	for (int c = 0; c < g.channels; ++c)
+		if (hs.planes[c] > depth_max)
+			depth_max = hs.planes[c];
+	const dim3 tiles((unsigned)g.tbase[g.levels], (unsigned)g.channels);
+	const dim3 lv((unsigned)g.levels, (unsigned)g.channels);
+	for (int depth = 0; depth < depth_max; ++depth) {
+		dec_prep_kernel<<<tiles, TG, 0, st>>>(g, b, nchunks, depth);
+		dec_tilescan_kernel<<<lv, 1024, 0, st>>>(g, b, nchunks, depth);
+		dec_deposit_kernel<<<tiles, TG, 0, st>>>(g, b, nchunks, depth);
+		*launches += 3;
+	}
 	CUDA_OK(cudaGetLastError());
 	return 0;
 }

@@ -47,7 +47,7 @@ struct dwt_ctx {
 	// coder buffers
 	DevBuf bs, sig, ent, Z, signbuf, specbuf, refbuf, tiles, thr_state, chunks, info, dsched, out, stream;
 	DevBuf mem_pref, ref_pref, ones_rank, sign_rank, dstate, win, flush;
-	bool dec_ready = false;
+	DevBuf dec_scan, dec_seg, dec_chunks; // decoder: per-slice chain tables, segment and chunk records
 	int sm_count = 1;
 	PinBuf pin_small, pin_io, pin_stream;
 

@@ -203,46 +203,55 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 	} else if (nchunks > 0) {
 		const size_t bs_words = (size_t)S.bsbase[C];
 		const size_t sig_words = (size_t)g.GT * C;
-		int gmax = 0, tmax = 0;
-		for (int l = 0; l < L; ++l) {
-			if (g.G[l] > gmax)
-				gmax = g.G[l];
-			if (g.ntile[l] > tmax)
-				tmax = g.ntile[l];
-		}
-		const int nwin_cap = (int)(len * 8 / 65536 + 4);
+		const size_t ntiles = (size_t)g.tbase[L] * C;
+		const u64 end_bits = (u64)len * 8;
+		const size_t nwin = (size_t)((end_bits / 64 + 2 + DWT_DEC_WS - 1) / DWT_DEC_WS);
+		const size_t nslice = nwin * DWT_DEC_WS;
+		const size_t rank_words = (size_t)(dec_rank_bits(g, S, nchunks) / 32) + 8;
+		// per slice: E 4 B + P 16 B + TK 4 B; per window: X 4 B + PT 16 B + TT 4 B + two link records
+		const size_t scan_bytes = nslice * 24 + nwin * (24 + 2 * sizeof(DecLink)) + 256;
 		if (c->bs.ensure(bs_words * 4 + 64) || c->sig.ensure(sig_words * 4 + 64) || c->dstate.ensure(sizeof(DecState)) ||
-		    c->mem_pref.ensure((size_t)tmax * 8 + 64) || c->ref_pref.ensure((size_t)tmax * 8 + 64) ||
-		    c->ones_rank.ensure((size_t)gmax * 4 + 64) || c->sign_rank.ensure((size_t)gmax * 4 + 64) ||
-		    c->win.ensure((size_t)nwin_cap * 16 + 64))
+		    c->mem_pref.ensure(ntiles * 8 + 64) || c->ref_pref.ensure(ntiles * 8 + 64) ||
+		    c->ones_rank.ensure(rank_words * 8 + 64) || c->dec_scan.ensure(scan_bytes) ||
+		    c->dec_seg.ensure((nwin + (size_t)nchunks + 1) * sizeof(DecSeg)) ||
+		    c->dec_chunks.ensure((size_t)DWT_MAX_CHUNKS * sizeof(DecChunk)) || c->dsched.ensure(sizeof(Sched)))
 			return -1;
-		if (!c->dec_ready) {
-			if (dec_setup())
-				return -1;
-			int sms = 0;
-			CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-			c->sm_count = sms > 0 ? sms : 1;
-			c->dec_ready = true;
-		}
 		CUDA_OK(cudaMemsetAsync(c->bs.p, 0, bs_words * 4, st));
 		CUDA_OK(cudaMemsetAsync(c->sig.p, 0, sig_words * 4, st));
+		CUDA_OK(cudaMemsetAsync(c->ones_rank.p, 0, rank_words * 8, st));
+		CUDA_OK(cudaMemsetAsync(c->dec_chunks.p, 0, (size_t)DWT_MAX_CHUNKS * sizeof(DecChunk), st));
 		CUDA_OK(cudaMemcpyAsync(c->dstate.p, h_state, sizeof(DecState), cudaMemcpyHostToDevice, st));
+		CUDA_OK(cudaMemcpyAsync(c->dsched.p, &c->sched, sizeof(Sched), cudaMemcpyHostToDevice, st));
 		DecBuffers b;
 		b.bs = c->bs.as<u32>();
 		b.sig = c->sig.as<u32>();
 		b.stream = c->stream.as<u32>();
+		b.end_bits = end_bits;
+		b.nwin = (u32)nwin;
+		char *sp = c->dec_scan.as<char>();
+		b.P = (ulonglong2 *)sp;
+		sp += nslice * 16;
+		b.winPT = (ulonglong2 *)sp;
+		sp += nwin * 16;
+		b.link = (DecLink *)sp;
+		sp += nwin * 2 * sizeof(DecLink);
+		b.E = (u32 *)sp;
+		sp += nslice * 4;
+		b.TK = (u32 *)sp;
+		sp += nslice * 4;
+		b.winX = (u32 *)sp;
+		sp += nwin * 4;
+		b.winTT = (u32 *)sp;
+		b.seg = c->dec_seg.as<DecSeg>();
+		b.chunks = c->dec_chunks.as<DecChunk>();
 		b.tile_sums = c->mem_pref.as<u32>();
 		b.tile_base = c->ref_pref.as<u32>();
 		b.ones_rank = c->ones_rank.as<u32>();
-		b.sign_rank = c->sign_rank.as<u32>();
-		b.win_state = c->win.as<u64>();
-		b.win_rank = b.win_state + nwin_cap;
-		b.nwin_cap = nwin_cap;
-		b.parse_ctas = c->sm_count;
+		b.sign_rank = b.ones_rank + rank_words;
 		b.state = c->dstate.as<DecState>();
-		for (int j = 0; j < nchunks; ++j)
-			if (dec_chunk(g, S, b, j, st, &c->launches))
-				return -1;
+		b.sched = c->dsched.as<Sched>();
+		if (dec_run(g, S, b, nchunks, st, &c->launches))
+			return -1;
 		CUDA_OK(cudaMemcpyAsync(h_state, c->dstate.p, sizeof(DecState), cudaMemcpyDeviceToHost, st));
 		CUDA_OK(cudaEventRecord(c->ev[1], st));
 		CUDA_OK(cudaStreamSynchronize(st));
@@ -289,11 +298,17 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		stt->ms_lift = ev_ms(c->ev[2], c->ev[3]);
 		stt->ms_total = ev_ms(c->ev[0], c->ev[3]);
 		stt->full_bits = (long long)h_state->bitpos;
-		stt->parse_windows = h_state->dbg_windows;
-		stt->parse_jumps = h_state->dbg_iters;
-		stt->parse_exact = h_state->dbg_walk;
-		if (getenv("DWT_DEBUG"))
-			fprintf(stderr, "parse cycles: setup %llu wait %llu walk %llu\n", h_state->dbg_cyc[0], h_state->dbg_cyc[1], h_state->dbg_cyc[2]);
+		stt->parse_windows = h_state->nseg;
+		stt->parse_jumps = h_state->dbg_slow;
+		stt->parse_exact = h_state->dbg_stray;
+		if (getenv("DWT_DEBUG")) {
+			fprintf(stderr, "resolve cycles: exact %llu linked %llu search %llu total %llu\n", h_state->dbg_cyc[0],
+			        h_state->dbg_cyc[1], h_state->dbg_cyc[2], h_state->dbg_cyc[3]);
+			for (int j = 0; j < nchunks; ++j)
+				if (h_state->dbg_cs[j] > 8)
+					fprintf(stderr, "  chunk %d (c%d l%d p%d): %u stray slices\n", j, S.chan[j], S.level[j], S.plane[j],
+					        h_state->dbg_cs[j]);
+		}
 	}
 	return 0;
 }
