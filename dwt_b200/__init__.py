@@ -242,6 +242,18 @@ class Codec:
     def event_elapsed_ms(self, a, b):
         return float(lib().dwt_ctx_event_elapsed_ms(self._h, a, b))
 
+    # ---- parity taps
+    def front_end(self, img):
+        """(pyramid int32 (h,w,ch) in the reference's interleaved Mallat layout, planar (ch, w*h), planes)"""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        w, h, ch = _shape(img)
+        pyr = np.zeros((h, w, ch), dtype=np.int32)
+        lin = np.zeros((ch, w * h), dtype=np.int32)
+        planes = (C.c_int * 3)()
+        if lib().dwt_debug_front_end(self._h, _u8p(img), w, h, ch, _ip(pyr), _ip(lin), planes):
+            raise DwtError("dwt_debug_front_end failed: " + last_error())
+        return pyr, lin, list(planes)[:ch]
+
 
 def pinned_array(nbytes):
     """uint8 numpy view of page-locked host memory (dwt_host_alloc); keep the returned owner alive"""
@@ -260,18 +272,6 @@ def pinned_array(nbytes):
             except Exception:
                 pass
     return arr, _Owner(p)
-
-    # ---- parity taps
-    def front_end(self, img):
-        """(pyramid int32 (h,w,ch) in the reference's interleaved Mallat layout, planar (ch, w*h), planes)"""
-        img = np.ascontiguousarray(img, dtype=np.uint8)
-        w, h, ch = _shape(img)
-        pyr = np.zeros((h, w, ch), dtype=np.int32)
-        lin = np.zeros((ch, w * h), dtype=np.int32)
-        planes = (C.c_int * 3)()
-        if lib().dwt_debug_front_end(self._h, _u8p(img), w, h, ch, _ip(pyr), _ip(lin), planes):
-            raise DwtError("dwt_debug_front_end failed: " + last_error())
-        return pyr, lin, list(planes)[:ch]
 
 
 # ---- transform entry points with the reference's argument meaning (host buffers)

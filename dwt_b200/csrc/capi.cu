@@ -25,6 +25,7 @@ int ctx_inverse_transform(dwt_ctx *c, int levels_used, bool to_u8, int *planar_o
 	const int top = levels_used > 0 ? levels_used : 0;
 	const long long pyr_stride = g.pix[top];
 	const int pyr_pitch = g.w[top];
+	CUDA_OK(cudaMemsetAsync(c->small.as<int>() + 64, 0, 32 * sizeof(int), st)); // work counters of the level launches
 	if (levels_used == 0) {
 		// decode.c:258 with levels == 0 still runs one inverse level on the w0 x h0 root, reading the root
 		// itself as a one-level Mallat pyramid
@@ -39,6 +40,7 @@ int ctx_inverse_transform(dwt_ctx *c, int levels_used, bool to_u8, int *planar_o
 		p.pyr_chan_stride = g.pix[0];
 		p.pyr_pitch = g.w[0];
 		p.maxabs = nullptr;
+		p.work = c->small.as<int>() + 64;
 		int mode = 2;
 		if (to_u8) {
 			p.out = c->img.p;
@@ -52,18 +54,45 @@ int ctx_inverse_transform(dwt_ctx *c, int levels_used, bool to_u8, int *planar_o
 		}
 		return lift_inverse_level(p, mode, st, &c->launches);
 	}
-	for (int lv = 1; lv <= levels_used; ++lv) {
+	// the coarsest levels that fit one CTA's shared memory run fused (root in ll[0] -> level T in ll[1])
+	int first = 1, cur = 0;
+	for (int T = levels_used - 1; T >= 1; --T) {
+		if (!lift_tail_fits(g.w[T], g.h[T]))
+			continue;
+		LiftTail t;
+		t.ll_in = c->ll[0].as<int>();
+		t.in_chan_stride = g.pix[0];
+		t.in_pitch = g.w[0];
+		t.ll_out = c->ll[1].as<int>();
+		t.out_chan_stride = g.pix[T];
+		t.out_pitch = g.w[T];
+		t.pyr = c->pyr.as<int>();
+		t.pyr_chan_stride = pyr_stride;
+		t.pyr_pitch = pyr_pitch;
+		t.W = g.w[T];
+		t.H = g.h[T];
+		t.nlev = T;
+		t.channels = g.channels;
+		t.maxabs = nullptr;
+		if (lift_tail(t, true, st, &c->launches))
+			return -1;
+		first = T + 1;
+		cur = 1;
+		break;
+	}
+	for (int lv = first; lv <= levels_used; ++lv) {
 		LiftLevel p;
 		p.W = g.w[lv];
 		p.H = g.h[lv];
 		p.channels = g.channels;
-		p.in = c->ll[(lv - 1) & 1].p;
+		p.in = c->ll[cur].p;
 		p.in_chan_stride = g.pix[lv - 1];
 		p.in_pitch = g.w[lv - 1];
 		p.pyr = c->pyr.as<int>();
 		p.pyr_chan_stride = pyr_stride;
 		p.pyr_pitch = pyr_pitch;
 		p.maxabs = nullptr;
+		p.work = c->small.as<int>() + 64 + lv;
 		int mode = 2;
 		if (lv == levels_used && to_u8) {
 			p.out = c->img.p;
@@ -75,12 +104,13 @@ int ctx_inverse_transform(dwt_ctx *c, int levels_used, bool to_u8, int *planar_o
 			p.out_chan_stride = g.pix[lv];
 			p.out_pitch = g.w[lv];
 		} else {
-			p.out = c->ll[lv & 1].p;
+			p.out = c->ll[cur ^ 1].p;
 			p.out_chan_stride = g.pix[lv];
 			p.out_pitch = g.w[lv];
 		}
 		if (lift_inverse_level(p, mode, st, &c->launches))
 			return -1;
+		cur ^= 1;
 	}
 	return 0;
 }

@@ -16,356 +16,760 @@
 
 namespace {
 
-constexpr int STRIP_OUT = 60; // output columns per warp
+constexpr int STRIP_OUT = 120; // output columns per warp: 30 lanes x 4 columns (one halo lane on each side)
 constexpr int WARPS_PER_BLOCK = 4;
+constexpr u32 FULLMASK = 0xffffffffu;
 
 __device__ __forceinline__ int clampi(int x, int a, int b)
 {
 	return min(max(x, a), b);
 }
 
-// ------------------------------------------------------------------------------------------------ forward
-
 template <int MODE>
 struct FwdTraits {
 	static constexpr int NC = MODE == 0 ? 3 : 1;
 };
 
-// raw samples of this lane's even / odd column in row y (colour transform fused for MODE 0)
+// four consecutive columns of one row as they sit in memory: 12 bytes of RGB, 4 bytes of gray, or 4 ints
 template <int MODE>
-__device__ __forceinline__ void fwd_load(const LiftLevel &p, int ch, int y, int cx0, int cx1,
-                                         int (&a)[FwdTraits<MODE>::NC], int (&b)[FwdTraits<MODE>::NC])
+struct Raw {
+	u32 w[MODE == 0 ? 3 : (MODE == 1 ? 1 : 4)];
+};
+
+__device__ __forceinline__ void store2(int *q, int a, int b, bool vec)
 {
-	int cy = clampi(y, 0, p.H - 1);
-	if constexpr (MODE == 0) {
-		const uint8_t *row = (const uint8_t *)p.in + (size_t)cy * p.in_pitch * 3;
-		const uint8_t *q0 = row + (size_t)cx0 * 3, *q1 = row + (size_t)cx1 * 3;
-		int r0 = __ldg(q0), g0 = __ldg(q0 + 1), b0 = __ldg(q0 + 2);
-		int r1 = __ldg(q1), g1 = __ldg(q1 + 1), b1 = __ldg(q1 + 2);
-		// image.h:58-61
-		int u0 = r0 - b0, t0 = b0 + u0 / 2, v0 = g0 - t0;
-		int u1 = r1 - b1, t1 = b1 + u1 / 2, v1 = g1 - t1;
-		a[0] = t0 + v0 / 2;
-		a[1] = u0;
-		a[2] = v0;
-		b[0] = t1 + v1 / 2;
-		b[1] = u1;
-		b[2] = v1;
-	} else if constexpr (MODE == 1) {
-		const uint8_t *row = (const uint8_t *)p.in + (size_t)cy * p.in_pitch;
-		a[0] = __ldg(row + cx0);
-		b[0] = __ldg(row + cx1);
+	if (vec) {
+		*reinterpret_cast<int2 *>(q) = make_int2(a, b);
 	} else {
-		const int *row = (const int *)p.in + (size_t)ch * p.in_chan_stride + (size_t)cy * p.in_pitch;
-		a[0] = __ldg(row + cx0);
-		b[0] = __ldg(row + cx1);
+		q[0] = a;
+		q[1] = b;
 	}
 }
 
-// horizontal lifting of one row: in (a,b) = x[xe], x[xe+1]; out (a,b) = s[xe], d[xe+1]  (cdf53.h:12-23)
+// ------------------------------------------------------------------------------------------------ forward
+
+// columns x .. x+3 of row y (clamped to the image); `fast`: all four exist and the row is 4-byte / 16-byte aligned
+template <int MODE>
+__device__ __forceinline__ void fwd_load(const LiftLevel &p, int ch, int y, int x, bool fast, Raw<MODE> &r)
+{
+	const int cy = clampi(y, 0, p.H - 1);
+	if constexpr (MODE == 0) {
+		const uint8_t *row = (const uint8_t *)p.in + (size_t)cy * p.in_pitch * 3;
+		if (fast) {
+			const u32 *q = reinterpret_cast<const u32 *>(row + (size_t)x * 3);
+			r.w[0] = __ldg(q);
+			r.w[1] = __ldg(q + 1);
+			r.w[2] = __ldg(q + 2);
+		} else {
+			r.w[0] = r.w[1] = r.w[2] = 0;
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const uint8_t *q = row + (size_t)clampi(x + k, 0, p.W - 1) * 3;
+#pragma unroll
+				for (int b = 0; b < 3; ++b) {
+					const int n = 3 * k + b;
+					r.w[n >> 2] |= (u32)__ldg(q + b) << (8 * (n & 3));
+				}
+			}
+		}
+	} else if constexpr (MODE == 1) {
+		const uint8_t *row = (const uint8_t *)p.in + (size_t)cy * p.in_pitch;
+		if (fast) {
+			r.w[0] = __ldg(reinterpret_cast<const u32 *>(row + x));
+		} else {
+			r.w[0] = 0;
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				r.w[0] |= (u32)__ldg(row + clampi(x + k, 0, p.W - 1)) << (8 * k);
+		}
+	} else {
+		const int *row = (const int *)p.in + (size_t)ch * p.in_chan_stride + (size_t)cy * p.in_pitch;
+		if (fast) {
+			const int4 v = __ldg(reinterpret_cast<const int4 *>(row + x));
+			r.w[0] = (u32)v.x;
+			r.w[1] = (u32)v.y;
+			r.w[2] = (u32)v.z;
+			r.w[3] = (u32)v.w;
+		} else {
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				r.w[k] = (u32)__ldg(row + clampi(x + k, 0, p.W - 1));
+		}
+	}
+}
+
+// raw columns -> samples v[channel][column]; the colour transform image.h:58-61 is fused for MODE 0
+template <int MODE>
+__device__ __forceinline__ void fwd_expand(const Raw<MODE> &r, int (&v)[FwdTraits<MODE>::NC][4])
+{
+	if constexpr (MODE == 0) {
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			const int R = (int)((r.w[(3 * k) >> 2] >> (8 * ((3 * k) & 3))) & 255u);
+			const int G = (int)((r.w[(3 * k + 1) >> 2] >> (8 * ((3 * k + 1) & 3))) & 255u);
+			const int B = (int)((r.w[(3 * k + 2) >> 2] >> (8 * ((3 * k + 2) & 3))) & 255u);
+			const int U = R - B, T = B + U / 2, V = G - T;
+			v[0][k] = T + V / 2;
+			v[1][k] = U;
+			v[2][k] = V;
+		}
+	} else if constexpr (MODE == 1) {
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			v[0][k] = (int)((r.w[0] >> (8 * k)) & 255u);
+	} else {
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			v[0][k] = (int)r.w[k];
+	}
+}
+
+struct HPred { // horizontal boundary rules of this lane's four columns (cdf53.h:12-23 / 49-60), row independent
+	bool d1_int, d3_int, s0_first, s0_upd, s2_upd;
+};
+
+// horizontal lifting of one row: in v[c] = X[x..x+3]; out v[c] = s[x], d[x+1], s[x+2], d[x+3]
 template <int NC>
-__device__ __forceinline__ void fwd_hlift(int (&a)[NC], int (&b)[NC], int xe, int N)
+__device__ __forceinline__ void fwd_hlift(int (&v)[NC][4], const HPred &hp)
 {
 #pragma unroll
 	for (int c = 0; c < NC; ++c) {
-		int right = __shfl_down_sync(0xffffffffu, a[c], 1); // x[xe+2]
-		int d;
-		if (xe + 1 < N - 1)
-			d = b[c] - (a[c] + right) / 2;
-		else
-			d = b[c] - a[c]; // xe+1 == N-1 (N even); garbage beyond the row, never stored
-		int left = __shfl_up_sync(0xffffffffu, d, 1); // d[xe-1]
-		int s;
-		if (xe == 0)
-			s = a[c] + d / 2;
-		else if (xe + 1 <= N - 1)
-			s = a[c] + (left + d) / 4;
-		else
-			s = a[c]; // xe == N-1 (N odd): the tail even sample is not updated (cdf53.h:21)
-		a[c] = s;
-		b[c] = d;
+		const int X0 = v[c][0], X1 = v[c][1], X2 = v[c][2], X3 = v[c][3];
+		const int X4 = __shfl_down_sync(FULLMASK, X0, 1);
+		const int d1 = hp.d1_int ? X1 - (X0 + X2) / 2 : X1 - X0; // x+1 == N-1 (N even); garbage beyond the row
+		const int d3 = hp.d3_int ? X3 - (X2 + X4) / 2 : X3 - X2;
+		const int dm1 = __shfl_up_sync(FULLMASK, d3, 1);
+		// x == 0: first sample; x == N-1 (N odd): the tail even sample is not updated (cdf53.h:21)
+		const int s0 = hp.s0_first ? X0 + d1 / 2 : (hp.s0_upd ? X0 + (dm1 + d1) / 4 : X0);
+		const int s2 = hp.s2_upd ? X2 + (d1 + d3) / 4 : X2;
+		v[c][0] = s0;
+		v[c][1] = d1;
+		v[c][2] = s2;
+		v[c][3] = d3;
 	}
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) lift_fwd_kernel(LiftLevel p, int RS)
+// HI: the whole strip is horizontally interior and every buffer is aligned for vector access, so the boundary
+// rules, clamps and alignment fall-backs are compiled out (all but the two edge strips of a level take this path)
+template <int MODE, bool HI>
+__device__ __forceinline__ void fwd_body(const LiftLevel &p, const int RS, const int strip, const int seg, const int ch,
+                                         const int lane)
 {
 	constexpr int NC = FwdTraits<MODE>::NC;
-	const int lane = threadIdx.x & 31;
-	const int strip = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
 	const int W = p.W, H = p.H;
-	if (strip * STRIP_OUT >= W)
-		return;
-	const int ch = MODE == 2 ? blockIdx.z : 0;
-	const int xe = strip * STRIP_OUT - 2 + 2 * lane; // this lane's even column
-	const int cx0 = clampi(xe, 0, W - 1), cx1 = clampi(xe + 1, 0, W - 1);
-	const int y0 = blockIdx.y * RS;
-	if (y0 >= H)
-		return;
+	const int x = strip * STRIP_OUT - 4 + 4 * lane; // this lane's first column (a multiple of 4)
+	const int y0 = seg * RS;
 	const int y1 = min(y0 + RS, H);
 	const int w2 = (W + 1) / 2, h2 = (H + 1) / 2;
-	const bool vs = lane >= 1 && lane <= 30 && xe < W; // this lane stores its even column
-	const bool vd = vs && xe + 1 < W;                  // ... and its odd column
+	const bool vs = lane >= 1 && lane <= 30 && (HI || x < W); // this lane stores
+	const bool full = vs && (HI || x + 3 < W);                // ... all four columns
+	const bool aligned_in = MODE == 2 ? ((p.in_pitch | (int)p.in_chan_stride) & 3) == 0 : (p.in_pitch & 3) == 0;
+	const bool fast = HI || (aligned_in && x >= 0 && x + 3 < W);
+	const bool v_ll = HI || ((p.out_pitch | (int)p.out_chan_stride) & 1) == 0;
+	const bool v_lh = HI || ((p.pyr_pitch | (int)p.pyr_chan_stride) & 1) == 0;
+	const bool v_hl = HI || (v_lh && (w2 & 1) == 0);
+	HPred hp;
+	hp.d1_int = HI || x + 1 < W - 1;
+	hp.d3_int = HI || x + 3 < W - 1;
+	hp.s0_first = !HI && x == 0;
+	hp.s0_upd = HI || x + 1 <= W - 1;
+	hp.s2_upd = HI || x + 3 <= W - 1;
 
-	// vertical window: e = row-lifted sample of the current even row, dp = vertical detail of the row above
-	int e_s[NC], e_d[NC], dp_s[NC], dp_d[NC];
-#pragma unroll
-	for (int c = 0; c < NC; ++c)
-		dp_s[c] = dp_d[c] = 0;
-	fwd_load<MODE>(p, ch, y0, cx0, cx1, e_s, e_d);
-	fwd_hlift<NC>(e_s, e_d, xe, W);
+	// vertical window: e = row-lifted current even row, dp = vertical detail of the odd row above
+	int e[NC][4], dp[NC][4];
+	Raw<MODE> raw;
+	fwd_load<MODE>(p, ch, y0, x, fast, raw);
+	fwd_expand<MODE>(raw, e);
+	fwd_hlift<NC>(e, hp);
 	if (y0 > 0) {
-		int m2s[NC], m2d[NC], m1s[NC], m1d[NC];
-		fwd_load<MODE>(p, ch, y0 - 2, cx0, cx1, m2s, m2d);
-		fwd_load<MODE>(p, ch, y0 - 1, cx0, cx1, m1s, m1d);
-		fwd_hlift<NC>(m2s, m2d, xe, W);
-		fwd_hlift<NC>(m1s, m1d, xe, W);
+		int m2[NC][4], m1[NC][4];
+		fwd_load<MODE>(p, ch, y0 - 2, x, fast, raw);
+		fwd_expand<MODE>(raw, m2);
+		fwd_hlift<NC>(m2, hp);
+		fwd_load<MODE>(p, ch, y0 - 1, x, fast, raw);
+		fwd_expand<MODE>(raw, m1);
+		fwd_hlift<NC>(m1, hp);
 #pragma unroll
-		for (int c = 0; c < NC; ++c) { // y0-1 is an interior odd row
-			dp_s[c] = m1s[c] - (m2s[c] + e_s[c]) / 2;
-			dp_d[c] = m1d[c] - (m2d[c] + e_d[c]) / 2;
-		}
+		for (int c = 0; c < NC; ++c)
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				dp[c][k] = m1[c][k] - (m2[c][k] + e[c][k]) / 2; // y0-1 is an interior odd row
+	} else {
+#pragma unroll
+		for (int c = 0; c < NC; ++c)
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				dp[c][k] = 0;
 	}
 	int mx[NC];
 #pragma unroll
 	for (int c = 0; c < NC; ++c)
 		mx[c] = 0;
 
-	int no_s[NC], no_d[NC], ne_s[NC], ne_d[NC]; // prefetched raw rows r+1, r+2
-	fwd_load<MODE>(p, ch, y0 + 1, cx0, cx1, no_s, no_d);
-	fwd_load<MODE>(p, ch, y0 + 2, cx0, cx1, ne_s, ne_d);
+	const int xl = x >> 1, xh = w2 + (x >> 1);
+	Raw<MODE> no, ne; // prefetched raw rows r+1, r+2
+	fwd_load<MODE>(p, ch, y0 + 1, x, fast, no);
+	fwd_load<MODE>(p, ch, y0 + 2, x, fast, ne);
+#pragma unroll 1
 	for (int r = y0; r < y1; r += 2) {
-		int o_s[NC], o_d[NC], f_s[NC], f_d[NC];
-#pragma unroll
-		for (int c = 0; c < NC; ++c) {
-			o_s[c] = no_s[c];
-			o_d[c] = no_d[c];
-			f_s[c] = ne_s[c];
-			f_d[c] = ne_d[c];
-		}
+		int o[NC][4], f[NC][4];
+		fwd_expand<MODE>(no, o);
+		fwd_expand<MODE>(ne, f);
 		if (r + 2 < y1) {
-			fwd_load<MODE>(p, ch, r + 3, cx0, cx1, no_s, no_d);
-			fwd_load<MODE>(p, ch, r + 4, cx0, cx1, ne_s, ne_d);
+			fwd_load<MODE>(p, ch, r + 3, x, fast, no);
+			fwd_load<MODE>(p, ch, r + 4, x, fast, ne);
 		}
-		fwd_hlift<NC>(o_s, o_d, xe, W);
-		fwd_hlift<NC>(f_s, f_d, xe, W);
+		fwd_hlift<NC>(o, hp);
+		fwd_hlift<NC>(f, hp);
 		const bool has_odd = r + 1 < H;
+		const bool v_int = r > 0 && r + 1 < H - 1; // neither the first row pair nor the last odd row
 		const size_t lo_row = (size_t)(r >> 1), hi_row = (size_t)(h2 + (r >> 1));
-		const int xl = xe >> 1, xh = w2 + (xe >> 1);
 #pragma unroll
 		for (int c = 0; c < NC; ++c) {
 			const int cc = MODE == 2 ? ch : c;
-			int D_s, D_d, S_s, S_d;
-			if (r + 1 < H - 1) {
-				D_s = o_s[c] - (e_s[c] + f_s[c]) / 2;
-				D_d = o_d[c] - (e_d[c] + f_d[c]) / 2;
-			} else { // r+1 == H-1 (H even); unused when r+1 >= H
-				D_s = o_s[c] - e_s[c];
-				D_d = o_d[c] - e_d[c];
-			}
-			if (r == 0) {
-				S_s = e_s[c] + D_s / 2;
-				S_d = e_d[c] + D_d / 2;
-			} else if (has_odd) {
-				S_s = e_s[c] + (dp_s[c] + D_s) / 4;
-				S_d = e_d[c] + (dp_d[c] + D_d) / 4;
-			} else { // r == H-1 (H odd): untouched
-				S_s = e_s[c];
-				S_d = e_d[c];
-			}
-			int *ll = (int *)p.out + (size_t)cc * p.out_chan_stride;
-			int *py = p.pyr + (size_t)cc * p.pyr_chan_stride;
-			if (vs) {
-				ll[lo_row * p.out_pitch + xl] = S_s; // LL
-				if (has_odd) {
-					py[hi_row * p.pyr_pitch + xl] = D_s; // LH (low-x, high-y)
-					mx[c] = max(mx[c], abs(D_s));
+			int D[4], S[4];
+			if (v_int) {
+#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					D[k] = o[c][k] - (e[c][k] + f[c][k]) / 2;
+					S[k] = e[c][k] + (dp[c][k] + D[k]) / 4;
+				}
+			} else {
+#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					// r+1 == H-1 (H even): plain difference; unused when r+1 >= H
+					D[k] = r + 1 < H - 1 ? o[c][k] - (e[c][k] + f[c][k]) / 2 : o[c][k] - e[c][k];
+					// r == 0: first row; r == H-1 (H odd): untouched
+					S[k] = r == 0 ? e[c][k] + D[k] / 2 : (has_odd ? e[c][k] + (dp[c][k] + D[k]) / 4 : e[c][k]);
 				}
 			}
-			if (vd) {
-				py[lo_row * p.pyr_pitch + xh] = S_d; // HL (high-x, low-y)
-				mx[c] = max(mx[c], abs(S_d));
+			int *ll = (int *)p.out + (size_t)cc * p.out_chan_stride + lo_row * p.out_pitch;
+			int *pl = p.pyr + (size_t)cc * p.pyr_chan_stride + lo_row * p.pyr_pitch;
+			int *ph = p.pyr + (size_t)cc * p.pyr_chan_stride + hi_row * p.pyr_pitch;
+			if (full) {
+				store2(ll + xl, S[0], S[2], v_ll);  // LL
+				store2(pl + xh, S[1], S[3], v_hl);  // HL (high-x, low-y)
+				int m = max(abs(S[1]), abs(S[3]));
 				if (has_odd) {
-					py[hi_row * p.pyr_pitch + xh] = D_d; // HH
-					mx[c] = max(mx[c], abs(D_d));
+					store2(ph + xl, D[0], D[2], v_lh); // LH (low-x, high-y)
+					store2(ph + xh, D[1], D[3], v_hl); // HH
+					m = max(max(m, abs(D[0])), max(abs(D[2]), max(abs(D[1]), abs(D[3]))));
+				}
+				mx[c] = max(mx[c], m);
+			} else if (!HI && vs) {
+#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					if (x + k >= W)
+						continue;
+					if (!(k & 1)) {
+						ll[xl + (k >> 1)] = S[k];
+						if (has_odd) {
+							ph[xl + (k >> 1)] = D[k];
+							mx[c] = max(mx[c], abs(D[k]));
+						}
+					} else {
+						pl[xh + (k >> 1)] = S[k];
+						mx[c] = max(mx[c], abs(S[k]));
+						if (has_odd) {
+							ph[xh + (k >> 1)] = D[k];
+							mx[c] = max(mx[c], abs(D[k]));
+						}
+					}
 				}
 			}
-			e_s[c] = f_s[c];
-			e_d[c] = f_d[c];
-			dp_s[c] = D_s;
-			dp_d[c] = D_d;
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				e[c][k] = f[c][k];
+				dp[c][k] = D[k];
+			}
 		}
 	}
 #pragma unroll
 	for (int c = 0; c < NC; ++c) {
-		int m = __reduce_max_sync(0xffffffffu, mx[c]);
+		const int m = __reduce_max_sync(FULLMASK, mx[c]);
 		if (lane == 0 && m > 0)
 			atomicMax(p.maxabs + (MODE == 2 ? ch : c), m);
 	}
 }
 
+// work items (strip, row segment, channel) are handed out through a counter, strips fastest: the grid is sized to
+// what is resident, every warp keeps taking items until they run out, and no partial last wave is left over
+__device__ __forceinline__ bool next_item(const LiftLevel &p, int nstrip, int nseg, int planes, int lane, int &strip, int &seg,
+                                          int &ch)
+{
+	int item = 0;
+	if (lane == 0)
+		item = atomicAdd(p.work, 1);
+	item = __shfl_sync(FULLMASK, item, 0);
+	if (item >= nstrip * nseg * planes)
+		return false;
+	strip = item % nstrip;
+	const int r = item / nstrip;
+	seg = r % nseg;
+	ch = r / nseg;
+	return true;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 6) lift_fwd_kernel(const __grid_constant__ LiftLevel p, int RS,
+                                                                            int nstrip, int nseg, int planes)
+{
+	const int lane = threadIdx.x & 31;
+	const int W = p.W;
+	const int w2 = (W + 1) / 2;
+	const bool aligned = (MODE == 2 ? ((p.in_pitch | (int)p.in_chan_stride) & 3) == 0 : (p.in_pitch & 3) == 0) &&
+	                     ((p.out_pitch | (int)p.out_chan_stride | p.pyr_pitch | (int)p.pyr_chan_stride | w2) & 1) == 0;
+	int strip, seg, ch;
+	while (next_item(p, nstrip, nseg, planes, lane, strip, seg, ch)) {
+		if (aligned && strip > 0 && strip * STRIP_OUT + 124 < W)
+			fwd_body<MODE, true>(p, RS, strip, seg, ch, lane);
+		else
+			fwd_body<MODE, false>(p, RS, strip, seg, ch, lane);
+	}
+}
+
 // ------------------------------------------------------------------------------------------------ inverse
 
-// horizontal inverse of one row (cdf53.h:49-60): in (a,b) = s_i, d_i; out (a,b) = x[2i], x[2i+1]
+struct IPred { // horizontal boundary rules of this lane's two column pairs (cdf53.h:49-60)
+	bool e0_first, e0_upd, e1_upd, o0_int, o1_int;
+};
+
+// horizontal inverse of one row: in s[c][0..1] = s_j, s_j+1 and d[c][0..1] = d_j, d_j+1;
+// out v[c] = x[2j], x[2j+1], x[2j+2], x[2j+3]
 template <int NC>
-__device__ __forceinline__ void inv_hlift(int (&a)[NC], int (&b)[NC], int i, int N)
+__device__ __forceinline__ void inv_hlift(const int (&s)[NC][2], const int (&d)[NC][2], int (&v)[NC][4], const IPred &ip)
 {
 #pragma unroll
 	for (int c = 0; c < NC; ++c) {
-		int left = __shfl_up_sync(0xffffffffu, b[c], 1); // d_{i-1}
-		int e;
-		if (i == 0)
-			e = a[c] - b[c] / 2;
-		else if (2 * i + 1 <= N - 1)
-			e = a[c] - (left + b[c]) / 4;
-		else
-			e = a[c]; // 2i == N-1 (N odd)
-		int right = __shfl_down_sync(0xffffffffu, e, 1); // x[2i+2]
-		int o;
-		if (2 * i + 1 < N - 1)
-			o = b[c] + (e + right) / 2;
-		else
-			o = b[c] + e; // 2i+1 == N-1 (N even)
-		a[c] = e;
-		b[c] = o;
+		const int dm1 = __shfl_up_sync(FULLMASK, d[c][1], 1); // d_{j-1}
+		const int e0 = ip.e0_first ? s[c][0] - d[c][0] / 2 : (ip.e0_upd ? s[c][0] - (dm1 + d[c][0]) / 4 : s[c][0]);
+		const int e1 = ip.e1_upd ? s[c][1] - (d[c][0] + d[c][1]) / 4 : s[c][1];
+		const int e2 = __shfl_down_sync(FULLMASK, e0, 1); // x[2j+4]
+		v[c][0] = e0;
+		v[c][1] = ip.o0_int ? d[c][0] + (e0 + e1) / 2 : d[c][0] + e0; // 2j+1 == N-1 (N even)
+		v[c][2] = e1;
+		v[c][3] = ip.o1_int ? d[c][1] + (e1 + e2) / 2 : d[c][1] + e1;
 	}
 }
 
 template <int MODE>
-__device__ __forceinline__ void inv_store_row(const LiftLevel &p, int ch, int y, int i, bool v0, bool v1,
-                                              int (&a)[FwdTraits<MODE>::NC], int (&b)[FwdTraits<MODE>::NC])
+__device__ __forceinline__ void inv_store_row(const LiftLevel &p, int ch, int y, int x, bool vs, bool full, bool vec,
+                                              const int (&v)[FwdTraits<MODE>::NC][4])
 {
+	if (!vs)
+		return;
 	if constexpr (MODE == 2) {
 		int *row = (int *)p.out + (size_t)ch * p.out_chan_stride + (size_t)y * p.out_pitch;
-		if (v0)
-			row[2 * i] = a[0];
-		if (v1)
-			row[2 * i + 1] = b[0];
+		if (full && vec) {
+			*reinterpret_cast<int4 *>(row + x) = make_int4(v[0][0], v[0][1], v[0][2], v[0][3]);
+		} else {
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				if (x + k < p.W)
+					row[x + k] = v[0][k];
+		}
 	} else if constexpr (MODE == 1) {
 		uint8_t *row = (uint8_t *)p.out + (size_t)y * p.out_pitch;
-		if (v0)
-			row[2 * i] = (uint8_t)clampi(a[0], 0, 255);
-		if (v1)
-			row[2 * i + 1] = (uint8_t)clampi(b[0], 0, 255);
+		u32 w = 0;
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			w |= (u32)clampi(v[0][k], 0, 255) << (8 * k);
+		if (full && vec) {
+			*reinterpret_cast<u32 *>(row + x) = w;
+		} else {
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				if (x + k < p.W)
+					row[x + k] = (uint8_t)(w >> (8 * k));
+		}
 	} else {
 		uint8_t *row = (uint8_t *)p.out + (size_t)y * p.out_pitch * 3;
+		u32 w[3] = {0u, 0u, 0u};
 #pragma unroll
-		for (int k = 0; k < 2; ++k) {
-			int(&q)[3] = k ? b : a;
-			if (k ? v1 : v0) {
-				// image.h:41-50 then pnm.h:108
-				int Y = clampi(q[0], 0, 255), U = clampi(q[1], -255, 255), V = clampi(q[2], -255, 255);
-				int T = Y - V / 2, G = V + T, B = T - U / 2, R = B + U;
-				uint8_t *px = row + (size_t)(2 * i + k) * 3;
-				px[0] = (uint8_t)clampi(R, 0, 255);
-				px[1] = (uint8_t)clampi(G, 0, 255);
-				px[2] = (uint8_t)clampi(B, 0, 255);
+		for (int k = 0; k < 4; ++k) {
+			// image.h:41-50 then pnm.h:108
+			const int Y = clampi(v[0][k], 0, 255), U = clampi(v[1][k], -255, 255), V = clampi(v[2][k], -255, 255);
+			const int T = Y - V / 2, G = V + T, B = T - U / 2, R = B + U;
+			const u32 px[3] = {(u32)clampi(R, 0, 255), (u32)clampi(G, 0, 255), (u32)clampi(B, 0, 255)};
+#pragma unroll
+			for (int b = 0; b < 3; ++b) {
+				const int n = 3 * k + b;
+				w[n >> 2] |= px[b] << (8 * (n & 3));
 			}
+		}
+		if (full && vec) {
+			u32 *q = reinterpret_cast<u32 *>(row + (size_t)x * 3);
+			q[0] = w[0];
+			q[1] = w[1];
+			q[2] = w[2];
+		} else {
+#pragma unroll
+			for (int n = 0; n < 12; ++n)
+				if (x + n / 3 < p.W)
+					row[(size_t)x * 3 + n] = (uint8_t)(w[n >> 2] >> (8 * (n & 3)));
 		}
 	}
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) lift_inv_kernel(LiftLevel p, int RS)
+template <int MODE, bool HI>
+__device__ __forceinline__ void inv_body(const LiftLevel &p, const int RS, const int strip, const int seg, const int chz,
+                                         const int lane)
 {
 	constexpr int NC = FwdTraits<MODE>::NC;
-	const int lane = threadIdx.x & 31;
-	const int strip = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
 	const int W = p.W, H = p.H;
-	if (strip * STRIP_OUT >= W)
-		return;
-	const int chz = MODE == 2 ? blockIdx.z : 0;
-	const int i = strip * (STRIP_OUT / 2) - 1 + lane; // column pair index: output columns 2i, 2i+1
+	const int x = strip * STRIP_OUT - 4 + 4 * lane; // output columns x .. x+3 = column pairs j, j+1
+	const int j = x >> 1;
 	const int w2 = (W + 1) / 2, h2 = (H + 1) / 2, wd = W / 2, hd = H / 2;
-	const int y0 = blockIdx.y * RS;
-	if (y0 >= H)
-		return;
+	const int y0 = seg * RS;
 	const int y1 = min(y0 + RS, H);
-	const bool v0 = lane >= 1 && lane <= 30 && 2 * i < W;
-	const bool v1 = v0 && 2 * i + 1 < W;
-	const int ci = clampi(i, 0, w2 - 1);                  // clamped low-x column
-	const int cj = w2 + clampi(i, 0, max(wd - 1, 0));     // clamped high-x column (Mallat position)
+	const bool vs = lane >= 1 && lane <= 30 && (HI || x < W);
+	const bool full = vs && (HI || x + 3 < W);
+	// clamped band columns: low-x pair and high-x pair (Mallat position)
+	const int cl0 = HI ? j : clampi(j, 0, w2 - 1), cl1 = HI ? j + 1 : clampi(j + 1, 0, w2 - 1);
+	const int chh0 = w2 + (HI ? j : clampi(j, 0, max(wd - 1, 0))), chh1 = w2 + (HI ? j + 1 : clampi(j + 1, 0, max(wd - 1, 0)));
+	const bool in_range = HI || (j >= 0 && j + 1 < wd);
+	const bool v_ll = HI || (in_range && ((p.in_pitch | (int)p.in_chan_stride) & 1) == 0);
+	const bool v_lh = HI || (in_range && ((p.pyr_pitch | (int)p.pyr_chan_stride) & 1) == 0);
+	const bool v_hl = HI || (v_lh && (w2 & 1) == 0);
+	const bool vec_out = HI || (MODE == 2 ? ((p.out_pitch | (int)p.out_chan_stride) & 3) == 0 : (p.out_pitch & 3) == 0);
+	IPred ip;
+	ip.e0_first = !HI && j == 0;
+	ip.e0_upd = HI || x + 1 <= W - 1;
+	ip.e1_upd = HI || x + 3 <= W - 1;
+	ip.o0_int = HI || x + 1 < W - 1;
+	ip.o1_int = HI || x + 3 < W - 1;
 
-	// loads the four band samples of pair row m: S (low-y) and D (high-y) for the low-x and high-x column
-	auto load = [&](int m, int(&S_s)[NC], int(&S_d)[NC], int(&D_s)[NC], int(&D_d)[NC]) {
-		int ms = clampi(m, 0, h2 - 1), md = h2 + clampi(m, 0, max(hd - 1, 0));
+	// the four band samples of pair row m: S (low-y) and D (high-y), each for the low-x pair and the high-x pair
+	auto load = [&](int m, int(&S_s)[NC][2], int(&S_d)[NC][2], int(&D_s)[NC][2], int(&D_d)[NC][2]) {
+		const int ms = clampi(m, 0, h2 - 1), md = h2 + clampi(m, 0, max(hd - 1, 0));
 #pragma unroll
 		for (int c = 0; c < NC; ++c) {
 			const int cc = MODE == 2 ? chz : c;
-			const int *ll = (const int *)p.in + (size_t)cc * p.in_chan_stride;
-			const int *py = p.pyr + (size_t)cc * p.pyr_chan_stride;
-			S_s[c] = __ldg(ll + (size_t)ms * p.in_pitch + ci);
-			S_d[c] = __ldg(py + (size_t)ms * p.pyr_pitch + cj);
-			D_s[c] = __ldg(py + (size_t)md * p.pyr_pitch + ci);
-			D_d[c] = __ldg(py + (size_t)md * p.pyr_pitch + cj);
+			const int *ll = (const int *)p.in + (size_t)cc * p.in_chan_stride + (size_t)ms * p.in_pitch;
+			const int *ps = p.pyr + (size_t)cc * p.pyr_chan_stride + (size_t)ms * p.pyr_pitch;
+			const int *pd = p.pyr + (size_t)cc * p.pyr_chan_stride + (size_t)md * p.pyr_pitch;
+			if (v_ll) {
+				const int2 t = __ldg(reinterpret_cast<const int2 *>(ll + cl0));
+				S_s[c][0] = t.x;
+				S_s[c][1] = t.y;
+			} else {
+				S_s[c][0] = __ldg(ll + cl0);
+				S_s[c][1] = __ldg(ll + cl1);
+			}
+			if (v_hl) {
+				const int2 t = __ldg(reinterpret_cast<const int2 *>(ps + chh0));
+				const int2 u = __ldg(reinterpret_cast<const int2 *>(pd + chh0));
+				S_d[c][0] = t.x;
+				S_d[c][1] = t.y;
+				D_d[c][0] = u.x;
+				D_d[c][1] = u.y;
+			} else {
+				S_d[c][0] = __ldg(ps + chh0);
+				S_d[c][1] = __ldg(ps + chh1);
+				D_d[c][0] = __ldg(pd + chh0);
+				D_d[c][1] = __ldg(pd + chh1);
+			}
+			if (v_lh) {
+				const int2 t = __ldg(reinterpret_cast<const int2 *>(pd + cl0));
+				D_s[c][0] = t.x;
+				D_s[c][1] = t.y;
+			} else {
+				D_s[c][0] = __ldg(pd + cl0);
+				D_s[c][1] = __ldg(pd + cl1);
+			}
 		}
 	};
 
 	const int m0 = y0 >> 1;
-	int Dm_s[NC], Dm_d[NC], Ep_s[NC], Ep_d[NC];
+	int Dm_s[NC][2], Dm_d[NC][2], Ep_s[NC][2], Ep_d[NC][2];
 #pragma unroll
 	for (int c = 0; c < NC; ++c)
-		Dm_s[c] = Dm_d[c] = Ep_s[c] = Ep_d[c] = 0;
+#pragma unroll
+		for (int k = 0; k < 2; ++k)
+			Dm_s[c][k] = Dm_d[c][k] = Ep_s[c][k] = Ep_d[c][k] = 0;
 	if (m0 > 0) {
-		int t0[NC], t1[NC];
+		int t0[NC][2], t1[NC][2];
 		load(m0 - 1, t0, t1, Dm_s, Dm_d);
 	}
-	int nS_s[NC], nS_d[NC], nD_s[NC], nD_d[NC];
+	int nS_s[NC][2], nS_d[NC][2], nD_s[NC][2], nD_d[NC][2];
 	load(m0, nS_s, nS_d, nD_s, nD_d);
 	for (int m = m0; 2 * m - 1 < y1; ++m) {
-		int S_s[NC], S_d[NC], D_s[NC], D_d[NC];
+		int S_s[NC][2], S_d[NC][2], D_s[NC][2], D_d[NC][2];
 #pragma unroll
-		for (int c = 0; c < NC; ++c) {
-			S_s[c] = nS_s[c];
-			S_d[c] = nS_d[c];
-			D_s[c] = nD_s[c];
-			D_d[c] = nD_d[c];
-		}
+		for (int c = 0; c < NC; ++c)
+#pragma unroll
+			for (int k = 0; k < 2; ++k) {
+				S_s[c][k] = nS_s[c][k];
+				S_d[c][k] = nS_d[c][k];
+				D_s[c][k] = nD_s[c][k];
+				D_d[c][k] = nD_d[c][k];
+			}
 		if (2 * m + 1 < y1)
 			load(m + 1, nS_s, nS_d, nD_s, nD_d);
 		const bool hasE = 2 * m < H;
-		int E_s[NC], E_d[NC], O_s[NC], O_d[NC];
+		int E_s[NC][2], E_d[NC][2], O_s[NC][2], O_d[NC][2];
 #pragma unroll
-		for (int c = 0; c < NC; ++c) {
-			// vertical inverse (cdf53.h:49-60 along columns)
-			if (m == 0) {
-				E_s[c] = S_s[c] - D_s[c] / 2;
-				E_d[c] = S_d[c] - D_d[c] / 2;
-			} else if (2 * m + 1 <= H - 1) {
-				E_s[c] = S_s[c] - (Dm_s[c] + D_s[c]) / 4;
-				E_d[c] = S_d[c] - (Dm_d[c] + D_d[c]) / 4;
-			} else { // 2m == H-1 (H odd)
-				E_s[c] = S_s[c];
-				E_d[c] = S_d[c];
+		for (int c = 0; c < NC; ++c)
+#pragma unroll
+			for (int k = 0; k < 2; ++k) {
+				// vertical inverse (cdf53.h:49-60 along columns)
+				if (m == 0) {
+					E_s[c][k] = S_s[c][k] - D_s[c][k] / 2;
+					E_d[c][k] = S_d[c][k] - D_d[c][k] / 2;
+				} else if (2 * m + 1 <= H - 1) {
+					E_s[c][k] = S_s[c][k] - (Dm_s[c][k] + D_s[c][k]) / 4;
+					E_d[c][k] = S_d[c][k] - (Dm_d[c][k] + D_d[c][k]) / 4;
+				} else { // 2m == H-1 (H odd)
+					E_s[c][k] = S_s[c][k];
+					E_d[c][k] = S_d[c][k];
+				}
+				if (hasE) {
+					O_s[c][k] = Dm_s[c][k] + (Ep_s[c][k] + E_s[c][k]) / 2;
+					O_d[c][k] = Dm_d[c][k] + (Ep_d[c][k] + E_d[c][k]) / 2;
+				} else { // 2m-1 == H-1 (H even)
+					O_s[c][k] = Dm_s[c][k] + Ep_s[c][k];
+					O_d[c][k] = Dm_d[c][k] + Ep_d[c][k];
+				}
 			}
-			if (hasE) {
-				O_s[c] = Dm_s[c] + (Ep_s[c] + E_s[c]) / 2;
-				O_d[c] = Dm_d[c] + (Ep_d[c] + E_d[c]) / 2;
-			} else { // 2m-1 == H-1 (H even)
-				O_s[c] = Dm_s[c] + Ep_s[c];
-				O_d[c] = Dm_d[c] + Ep_d[c];
-			}
-		}
+		int v[NC][4];
 		if (m > m0) { // odd row 2m-1 (uniform branch: shuffles stay converged)
-			inv_hlift<NC>(O_s, O_d, i, W);
-			inv_store_row<MODE>(p, chz, 2 * m - 1, i, v0, v1, O_s, O_d);
+			inv_hlift<NC>(O_s, O_d, v, ip);
+			inv_store_row<MODE>(p, chz, 2 * m - 1, x, vs, full, vec_out, v);
 		}
 		if (hasE && 2 * m < y1) { // even row 2m
-			int T_s[NC], T_d[NC];
-#pragma unroll
-			for (int c = 0; c < NC; ++c) {
-				T_s[c] = E_s[c];
-				T_d[c] = E_d[c];
-			}
-			inv_hlift<NC>(T_s, T_d, i, W);
-			inv_store_row<MODE>(p, chz, 2 * m, i, v0, v1, T_s, T_d);
+			inv_hlift<NC>(E_s, E_d, v, ip);
+			inv_store_row<MODE>(p, chz, 2 * m, x, vs, full, vec_out, v);
 		}
 #pragma unroll
-		for (int c = 0; c < NC; ++c) {
-			Ep_s[c] = E_s[c];
-			Ep_d[c] = E_d[c];
-			Dm_s[c] = D_s[c];
-			Dm_d[c] = D_d[c];
+		for (int c = 0; c < NC; ++c)
+#pragma unroll
+			for (int k = 0; k < 2; ++k) {
+				Ep_s[c][k] = E_s[c][k];
+				Ep_d[c][k] = E_d[c][k];
+				Dm_s[c][k] = D_s[c][k];
+				Dm_d[c][k] = D_d[c][k];
+			}
+	}
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) lift_inv_kernel(const __grid_constant__ LiftLevel p, int RS,
+                                                                         int nstrip, int nseg, int planes)
+{
+	const int lane = threadIdx.x & 31;
+	const int W = p.W;
+	const int w2 = (W + 1) / 2;
+	const bool aligned = ((p.in_pitch | (int)p.in_chan_stride | p.pyr_pitch | (int)p.pyr_chan_stride | w2) & 1) == 0 &&
+	                     (MODE == 2 ? ((p.out_pitch | (int)p.out_chan_stride) & 3) == 0 : (p.out_pitch & 3) == 0);
+	int strip, seg, ch;
+	while (next_item(p, nstrip, nseg, planes, lane, strip, seg, ch)) {
+		if (aligned && strip > 0 && strip * STRIP_OUT + 124 < W)
+			inv_body<MODE, true>(p, RS, strip, seg, ch, lane);
+		else
+			inv_body<MODE, false>(p, RS, strip, seg, ch, lane);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ fused tail levels
+//
+// Below ~256 columns a level is launch-latency bound, so the remaining levels of a channel run in ONE CTA with
+// the LL image resident in shared memory: rows in place (a warp owns a row: read, lift, write back deinterleaved),
+// then columns into a second buffer that only has to keep the new LL quadrant -- the detail bands go straight
+// to the pyramid.  The inverse mirrors it.  Same arithmetic and order as the per-level kernels (encode.c:16-30).
+
+template <typename F>
+__device__ __forceinline__ int fwd_d_at(F X, int i, int N) // detail at odd i (cdf53.h:12-16)
+{
+	return i < N - 1 ? X(i) - (X(i - 1) + X(i + 1)) / 2 : X(i) - X(i - 1);
+}
+
+template <typename F>
+__device__ __forceinline__ int fwd_s_at(F X, int i, int N) // smooth at even i (cdf53.h:17-23)
+{
+	if (i == 0)
+		return X(0) + fwd_d_at(X, 1, N) / 2;
+	if (i + 1 <= N - 1)
+		return X(i) + (fwd_d_at(X, i - 1, N) + fwd_d_at(X, i + 1, N)) / 4;
+	return X(i);
+}
+
+template <typename FS, typename FD>
+__device__ __forceinline__ int inv_e_at(FS S, FD D, int j, int N) // x[2j] (cdf53.h:49-55)
+{
+	if (j == 0)
+		return S(0) - D(0) / 2;
+	if (2 * j + 1 <= N - 1)
+		return S(j) - (D(j - 1) + D(j)) / 4;
+	return S(j);
+}
+
+template <typename FS, typename FD>
+__device__ __forceinline__ int inv_o_at(FS S, FD D, int j, int N) // x[2j+1] (cdf53.h:56-60)
+{
+	const int e = inv_e_at(S, D, j, N);
+	return 2 * j + 1 < N - 1 ? D(j) + (e + inv_e_at(S, D, j + 1, N)) / 2 : D(j) + e;
+}
+
+constexpr int TAIL_THREADS = 1024;
+constexpr int TAIL_MAX_W = 128;      // wider levels have enough rows and strips to fill the machine
+constexpr int TAIL_MAX_INTS = 56000; // shared memory budget (both buffers), in ints
+
+__global__ void __launch_bounds__(TAIL_THREADS) lift_tail_fwd_kernel(LiftTail t)
+{
+	extern __shared__ int sm[];
+	__shared__ int smax;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int ch = blockIdx.x;
+	int w = t.W, h = t.H;
+	int *src = sm, *dst = sm + t.W * t.H;
+	int ps = t.W;
+	if (tid == 0)
+		smax = 0;
+	{
+		const int *in = t.ll_in + (size_t)ch * t.in_chan_stride;
+		for (int i = tid; i < w * h; i += TAIL_THREADS) {
+			const int y = i / w, x = i - y * w;
+			src[i] = in[(size_t)y * t.in_pitch + x];
+		}
+	}
+	__syncthreads();
+	int *pyr = t.pyr + (size_t)ch * t.pyr_chan_stride;
+	int mx = 0;
+	for (int lev = 0; lev < t.nlev; ++lev) {
+		const int w2 = (w + 1) / 2, h2 = (h + 1) / 2;
+		for (int y = wid; y < h; y += TAIL_THREADS / 32) { // rows, in place
+			int *row = src + y * ps;
+			auto X = [&](int i) { return row[i]; };
+			int sv[4], dv[4];
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const int i = lane + 32 * q;
+				sv[q] = 2 * i < w ? fwd_s_at(X, 2 * i, w) : 0;
+				dv[q] = 2 * i + 1 < w ? fwd_d_at(X, 2 * i + 1, w) : 0;
+			}
+			__syncwarp();
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const int i = lane + 32 * q;
+				if (2 * i < w)
+					row[i] = sv[q];
+				if (2 * i + 1 < w)
+					row[w2 + i] = dv[q];
+			}
+		}
+		__syncthreads();
+		const int pd = w2;
+		for (int i = tid; i < h2 * w; i += TAIL_THREADS) { // columns: LL -> dst, everything else -> pyramid
+			const int j = i / w, x = i - j * w;
+			auto X = [&](int y) { return src[y * ps + x]; };
+			const int S = fwd_s_at(X, 2 * j, h);
+			if (x < w2) {
+				dst[j * pd + x] = S;
+			} else {
+				pyr[(size_t)j * t.pyr_pitch + x] = S;
+				mx = max(mx, abs(S));
+			}
+			if (2 * j + 1 < h) {
+				const int D = fwd_d_at(X, 2 * j + 1, h);
+				pyr[(size_t)(h2 + j) * t.pyr_pitch + x] = D;
+				mx = max(mx, abs(D));
+			}
+		}
+		__syncthreads();
+		int *tmp = src;
+		src = dst;
+		dst = tmp;
+		ps = pd;
+		w = w2;
+		h = h2;
+	}
+	{
+		int *out = t.ll_out + (size_t)ch * t.out_chan_stride;
+		for (int i = tid; i < w * h; i += TAIL_THREADS) {
+			const int y = i / w, x = i - y * w;
+			out[(size_t)y * t.out_pitch + x] = src[y * ps + x];
+		}
+	}
+	mx = __reduce_max_sync(FULLMASK, mx);
+	if (lane == 0 && mx > 0)
+		atomicMax(&smax, mx);
+	__syncthreads();
+	if (tid == 0 && smax > 0)
+		atomicMax(t.maxabs + ch, smax);
+}
+
+// inverse: t.W x t.H is the size of the FINEST fused level; t.ll_in holds the root, t.ll_out receives W x H
+__global__ void __launch_bounds__(TAIL_THREADS) lift_tail_inv_kernel(LiftTail t)
+{
+	extern __shared__ int sm[];
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int ch = blockIdx.x;
+	// level sizes, coarse to fine: ws[0] x hs[0] is the root
+	int ws[DWT_MAX_LEVELS + 1], hs[DWT_MAX_LEVELS + 1];
+	ws[t.nlev] = t.W;
+	hs[t.nlev] = t.H;
+	for (int l = t.nlev; l > 0; --l) {
+		ws[l - 1] = (ws[l] + 1) / 2;
+		hs[l - 1] = (hs[l] + 1) / 2;
+	}
+	int *big = sm, *small = sm + t.W * t.H;
+	// buffers alternate so that the finest level lands in `big`
+	int *cur = (t.nlev & 1) ? small : big;
+	int pc = ws[0];
+	{
+		const int *in = t.ll_in + (size_t)ch * t.in_chan_stride;
+		const int w = ws[0], h = hs[0];
+		for (int i = tid; i < w * h; i += TAIL_THREADS) {
+			const int y = i / w, x = i - y * w;
+			cur[y * pc + x] = in[(size_t)y * t.in_pitch + x];
+		}
+	}
+	__syncthreads();
+	const int *pyr = t.pyr + (size_t)ch * t.pyr_chan_stride;
+	for (int lev = 1; lev <= t.nlev; ++lev) {
+		const int w = ws[lev], h = hs[lev], w2 = ws[lev - 1], h2 = hs[lev - 1];
+		int *nxt = cur == big ? small : big;
+		const int pn = w;
+		for (int i = tid; i < h2 * w; i += TAIL_THREADS) { // columns (decode.c:21): pair row j of column x
+			const int j = i / w, x = i - j * w;
+			auto S = [&](int m) { return x < w2 ? cur[m * pc + x] : __ldg(pyr + (size_t)m * t.pyr_pitch + x); };
+			auto D = [&](int m) { return __ldg(pyr + (size_t)(h2 + m) * t.pyr_pitch + x); };
+			nxt[(2 * j) * pn + x] = inv_e_at(S, D, j, h);
+			if (2 * j + 1 < h)
+				nxt[(2 * j + 1) * pn + x] = inv_o_at(S, D, j, h);
+		}
+		__syncthreads();
+		for (int y = wid; y < h; y += TAIL_THREADS / 32) { // rows, in place (decode.c:25-29)
+			int *row = nxt + y * pn;
+			auto S = [&](int m) { return row[m]; };
+			auto D = [&](int m) { return row[w2 + m]; };
+			int ev[4], ov[4];
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const int jj = lane + 32 * q;
+				ev[q] = 2 * jj < w ? inv_e_at(S, D, jj, w) : 0;
+				ov[q] = 2 * jj + 1 < w ? inv_o_at(S, D, jj, w) : 0;
+			}
+			__syncwarp();
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const int jj = lane + 32 * q;
+				if (2 * jj < w)
+					row[2 * jj] = ev[q];
+				if (2 * jj + 1 < w)
+					row[2 * jj + 1] = ov[q];
+			}
+		}
+		__syncthreads();
+		cur = nxt;
+		pc = pn;
+	}
+	{
+		int *out = t.ll_out + (size_t)ch * t.out_chan_stride;
+		const int w = t.W, h = t.H;
+		for (int i = tid; i < w * h; i += TAIL_THREADS) {
+			const int y = i / w, x = i - y * w;
+			out[(size_t)y * t.out_pitch + x] = cur[y * pc + x];
 		}
 	}
 }
@@ -375,7 +779,7 @@ int pick_rows(int W, int H, int planes)
 	// aim for >= ~4k warps in flight; rows per segment even, 8..64
 	long long strips = (W + STRIP_OUT - 1) / STRIP_OUT;
 	int rs = 64;
-	while (rs > 8 && strips * planes * ((H + rs - 1) / rs) < 4096)
+	while (rs > 8 && strips * planes * ((H + rs - 1) / rs) < 8192)
 		rs >>= 1;
 	return rs;
 }
@@ -458,19 +862,33 @@ __global__ void colour_kernel(int *buf, int total, bool inverse)
 
 } // namespace
 
+static int resident_blocks()
+{
+	static int n = 0;
+	if (!n) {
+		int dev = 0, sms = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		n = (sms > 0 ? sms : 1) * 8;
+	}
+	return n;
+}
+
+// lv.work must point at a zeroed device counter (one per launch)
 int lift_forward_level(const LiftLevel &lv, int mode, cudaStream_t st, long long *launches)
 {
-	int planes = mode == 2 ? lv.channels : 1;
-	int RS = pick_rows(lv.W, lv.H, planes);
-	int strips = (lv.W + STRIP_OUT - 1) / STRIP_OUT;
-	dim3 grid((strips + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (lv.H + RS - 1) / RS, planes);
+	const int planes = mode == 2 ? lv.channels : 1;
+	const int RS = pick_rows(lv.W, lv.H, planes);
+	const int strips = (lv.W + STRIP_OUT - 1) / STRIP_OUT, nseg = (lv.H + RS - 1) / RS;
+	const long long items = (long long)strips * nseg * planes;
+	const int grid = (int)min((items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (long long)resident_blocks());
 	dim3 block(WARPS_PER_BLOCK * 32);
 	if (mode == 0)
-		lift_fwd_kernel<0><<<grid, block, 0, st>>>(lv, RS);
+		lift_fwd_kernel<0><<<grid, block, 0, st>>>(lv, RS, strips, nseg, planes);
 	else if (mode == 1)
-		lift_fwd_kernel<1><<<grid, block, 0, st>>>(lv, RS);
+		lift_fwd_kernel<1><<<grid, block, 0, st>>>(lv, RS, strips, nseg, planes);
 	else
-		lift_fwd_kernel<2><<<grid, block, 0, st>>>(lv, RS);
+		lift_fwd_kernel<2><<<grid, block, 0, st>>>(lv, RS, strips, nseg, planes);
 	if (launches)
 		++*launches;
 	CUDA_OK(cudaGetLastError());
@@ -479,17 +897,45 @@ int lift_forward_level(const LiftLevel &lv, int mode, cudaStream_t st, long long
 
 int lift_inverse_level(const LiftLevel &lv, int mode, cudaStream_t st, long long *launches)
 {
-	int planes = mode == 2 ? lv.channels : 1;
-	int RS = pick_rows(lv.W, lv.H, planes);
-	int strips = (lv.W + STRIP_OUT - 1) / STRIP_OUT;
-	dim3 grid((strips + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (lv.H + RS - 1) / RS, planes);
+	const int planes = mode == 2 ? lv.channels : 1;
+	const int RS = pick_rows(lv.W, lv.H, planes);
+	const int strips = (lv.W + STRIP_OUT - 1) / STRIP_OUT, nseg = (lv.H + RS - 1) / RS;
+	const long long items = (long long)strips * nseg * planes;
+	const int grid = (int)min((items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (long long)resident_blocks());
 	dim3 block(WARPS_PER_BLOCK * 32);
 	if (mode == 0)
-		lift_inv_kernel<0><<<grid, block, 0, st>>>(lv, RS);
+		lift_inv_kernel<0><<<grid, block, 0, st>>>(lv, RS, strips, nseg, planes);
 	else if (mode == 1)
-		lift_inv_kernel<1><<<grid, block, 0, st>>>(lv, RS);
+		lift_inv_kernel<1><<<grid, block, 0, st>>>(lv, RS, strips, nseg, planes);
 	else
-		lift_inv_kernel<2><<<grid, block, 0, st>>>(lv, RS);
+		lift_inv_kernel<2><<<grid, block, 0, st>>>(lv, RS, strips, nseg, planes);
+	if (launches)
+		++*launches;
+	CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
+bool lift_tail_fits(int W, int H)
+{
+	const long long ints = (long long)W * H + (long long)((W + 1) / 2) * ((H + 1) / 2);
+	return W <= TAIL_MAX_W && ints <= TAIL_MAX_INTS;
+}
+
+int lift_tail(const LiftTail &t, bool inverse, cudaStream_t st, long long *launches)
+{
+	static bool configured = false;
+	const size_t smem = sizeof(int) * ((size_t)t.W * t.H + (size_t)((t.W + 1) / 2) * ((t.H + 1) / 2));
+	if (!configured) {
+		CUDA_OK(cudaFuncSetAttribute(lift_tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                             (int)(TAIL_MAX_INTS * sizeof(int))));
+		CUDA_OK(cudaFuncSetAttribute(lift_tail_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                             (int)(TAIL_MAX_INTS * sizeof(int))));
+		configured = true;
+	}
+	if (inverse)
+		lift_tail_inv_kernel<<<t.channels, TAIL_THREADS, smem, st>>>(t);
+	else
+		lift_tail_fwd_kernel<<<t.channels, TAIL_THREADS, smem, st>>>(t);
 	if (launches)
 		++*launches;
 	CUDA_OK(cudaGetLastError());

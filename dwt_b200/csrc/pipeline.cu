@@ -259,8 +259,31 @@ int ctx_forward_transform(dwt_ctx *c, const int *planar_in)
 	if (ensure_transform_buffers(c))
 		return -1;
 	CUDA_OK(cudaMemsetAsync(c->small.p, 0, 16, c->st));
+	CUDA_OK(cudaMemsetAsync(c->small.as<int>() + 64, 0, 32 * sizeof(int), c->st)); // work counters of the level launches
 	int cur = 0;
 	for (int lv = L; lv >= 1; --lv) {
+		if (lv < L && lift_tail_fits(g.w[lv], g.h[lv])) {
+			// the remaining levels in one launch, one CTA per channel (shared-memory resident)
+			LiftTail t;
+			t.ll_in = c->ll[cur ^ 1].as<int>();
+			t.in_chan_stride = g.pix[lv];
+			t.in_pitch = g.w[lv];
+			t.ll_out = c->ll[cur].as<int>();
+			t.out_chan_stride = g.pix[0];
+			t.out_pitch = g.w[0];
+			t.pyr = c->pyr.as<int>();
+			t.pyr_chan_stride = g.pix[L];
+			t.pyr_pitch = g.w[L];
+			t.W = g.w[lv];
+			t.H = g.h[lv];
+			t.nlev = lv;
+			t.channels = g.channels;
+			t.maxabs = c->small.as<int>();
+			if (lift_tail(t, false, c->st, &c->launches))
+				return -1;
+			c->root_buf = cur;
+			return 0;
+		}
 		LiftLevel p;
 		p.W = g.w[lv];
 		p.H = g.h[lv];
@@ -289,8 +312,10 @@ int ctx_forward_transform(dwt_ctx *c, const int *planar_in)
 		p.pyr_chan_stride = g.pix[L];
 		p.pyr_pitch = g.w[L];
 		p.maxabs = c->small.as<int>();
+		p.work = c->small.as<int>() + 64 + (L - lv);
 		if (lift_forward_level(p, mode, c->st, &c->launches))
 			return -1;
+		c->root_buf = cur;
 		cur ^= 1;
 	}
 	return 0;
@@ -299,8 +324,7 @@ int ctx_forward_transform(dwt_ctx *c, const int *planar_in)
 const int *ctx_root_ll(dwt_ctx *c)
 {
 	// after ctx_forward_transform the last written LL buffer holds the root (planar, pitch w[0])
-	const int L = c->geom.levels;
-	return c->ll[(L - 1) & 1].as<int>();
+	return c->ll[c->root_buf].as<int>();
 }
 
 // ------------------------------------------------------------------------------------------------ encode

@@ -40,6 +40,7 @@ struct dwt_ctx {
 	DevBuf img;        // u8 interleaved
 	DevBuf pyr;        // planar int32 Mallat pyramid
 	DevBuf ll[2];      // ping-pong LL
+	int root_buf = 0;  // which of them holds the root after a forward transform
 	DevBuf small;      // maxabs[4] | missing[48] | misc
 	int img_w = 0, img_h = 0, img_ch = 0;
 	bool img_resident = false;
