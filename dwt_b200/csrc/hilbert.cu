@@ -11,9 +11,11 @@
 // word, which is what the coder kernels consume.
 #include "hilbert.cuh"
 
+#include <vector>
+
 namespace {
 
-__device__ __forceinline__ void hilbert_d2xy(int n, u32 d, int &x, int &y) // hilbert.h:15-34
+__host__ __device__ __forceinline__ void hilbert_d2xy(int n, u32 d, int &x, int &y) // hilbert.h:15-34
 {
 	x = 0;
 	y = 0;
@@ -34,42 +36,10 @@ __device__ __forceinline__ void hilbert_d2xy(int n, u32 d, int &x, int &y) // hi
 	}
 }
 
-__device__ __forceinline__ int overlap(int o, int cs, int lim) // |[o, o+cs) n [0, lim)|
+inline int overlap(int o, int cs, int lim) // |[o, o+cs) n [0, lim)|
 {
-	int hi = min(o + cs, lim);
+	int hi = o + cs < lim ? o + cs : lim;
 	return hi > o ? hi - o : 0;
-}
-
-__global__ void cell_count_kernel(int n, int cs, int w1, int h1, int w0, int h0, int ncell, u32 *counts)
-{
-	int q = blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= ncell)
-		return;
-	int x, y;
-	hilbert_d2xy(n, (u32)q * (u32)(cs * cs), x, y);
-	int ox = x & ~(cs - 1), oy = y & ~(cs - 1);
-	int inside = overlap(ox, cs, w1) * overlap(oy, cs, h1);
-	int ll = overlap(ox, cs, w0) * overlap(oy, cs, h0);
-	counts[q] = (u32)(inside - ll);
-}
-
-// single-block in-place exclusive scan
-__global__ void __launch_bounds__(1024) exscan_u32_kernel(u32 *data, int n)
-{
-	__shared__ u64 ws[32];
-	int per = (n + blockDim.x - 1) / blockDim.x;
-	int b = threadIdx.x * per, e = min(b + per, n);
-	u64 s = 0;
-	for (int i = b; i < e; ++i)
-		s += data[i];
-	u64 tot;
-	u64 base = block_exscan_u64(s, ws, &tot);
-	u32 run = (u32)base;
-	for (int i = b; i < e; ++i) {
-		u32 v = data[i];
-		data[i] = run;
-		run += v;
-	}
 }
 
 struct ChanLayout {
@@ -77,23 +47,212 @@ struct ChanLayout {
 	long long bsbase[4];
 };
 
-struct CellParams {
-	int n, cs, w1, h1, w0, h0;
-	int channels;
-	int GT, gbase;   // groups per channel, first group of this level
-	const u32 *cell_base;
-	ChanLayout lay;
+struct HLevel {
+	int n, cs, w1, h1, w0, h0, gbase;
+	u32 cell_off;
 };
 
-__global__ void __launch_bounds__(256) linearize_kernel(CellParams P, const int *pyr, long long chan_stride,
-                                                         int pitch, u32 *bs)
+struct HParams {
+	HLevel lv[DWT_MAX_LEVELS];
+	int channels, GT;
+	ChanLayout lay;
+	const u32 *cell_base, *cell_info;
+};
+
+constexpr int PMAX = 12; // bit planes (+ sign) the warp-per-cell kernels keep in registers
+
+__device__ __forceinline__ void build_lut(unsigned short *lut)
+{
+	for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+		int x, y;
+		hilbert_d2xy(32, (u32)i, x, y);
+		lut[i] = (unsigned short)(x | (y << 8));
+	}
+	__syncthreads();
+}
+
+// position of curve index dloc of a cell with orientation o (bit 0 transpose, bit 1 point reflection)
+__device__ __forceinline__ void cell_xy(const unsigned short *lut, int dloc, u32 o, int &x, int &y)
+{
+	const u32 e = lut[dloc];
+	int lx = (int)(e & 255u), ly = (int)(e >> 8);
+	if (o & 1u) {
+		const int t = lx;
+		lx = ly;
+		ly = t;
+	}
+	if (o & 2u) {
+		lx = 31 - lx;
+		ly = 31 - ly;
+	}
+	x = lx;
+	y = ly;
+}
+
+// ---- cells whose 1024 positions are all valid: one warp per cell, no shared staging.  The warp walks the cell's
+// groups of 32 ranks; lane i of iteration k holds the coefficient of rank 32 (g0 + k) + i, a ballot per bit-plane
+// gives the group's words, lane k keeps them, and at the end every plane row is written as one contiguous run.
+__global__ void __launch_bounds__(256) linearize_full_kernel(const __grid_constant__ HParams P, const u32 *__restrict__ list,
+                                                              int nlist, const int *__restrict__ pyr, long long chan_stride,
+                                                              int pitch, u32 *bs)
+{
+	__shared__ unsigned short lut[1024];
+	build_lut(lut);
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	for (int item = blockIdx.x * 8 + wid; item < nlist; item += gridDim.x * 8) {
+		const u32 ent = list[item];
+		const HLevel &L = P.lv[ent >> 28];
+		const u32 q = ent & 0x0fffffffu;
+		const u32 R0 = P.cell_base[L.cell_off + q], info = P.cell_info[L.cell_off + q];
+		const int ox = (int)(info & 0xfffu) * 32, oy = (int)((info >> 12) & 0xfffu) * 32;
+		const u32 orient = info >> 24;
+		const u32 g0 = R0 >> 5;
+		const int s = (int)(R0 & 31u);
+		const int *base = pyr + (size_t)oy * pitch + ox;
+		for (int c = 0; c < P.channels; ++c) {
+			const int planes = P.lay.planes[c];
+			const int *src = base + (size_t)c * chan_stride;
+			u32 *dst = bs + P.lay.bsbase[c] + L.gbase + g0;
+			u32 keep[PMAX + 1];
+#pragma unroll
+			for (int p = 0; p <= PMAX; ++p)
+				keep[p] = 0;
+#pragma unroll 4
+			for (int k = 0; k < 32; ++k) {
+				const int dloc = 32 * k + lane - s;
+				u32 v = 0;
+				if (dloc >= 0) {
+					int x, y;
+					cell_xy(lut, dloc, orient, x, y);
+					const int t = __ldg(src + (size_t)y * pitch + x);
+					v = (t < 0 ? 0x80000000u : 0u) | (u32)abs(t); // encode.c:124-128
+				}
+				const bool mine = lane == k;
+#pragma unroll
+				for (int p = 0; p < PMAX; ++p) {
+					if (p < planes) {
+						const u32 w = __ballot_sync(0xffffffffu, (v >> p) & 1u);
+						if (mine)
+							keep[p] = w;
+					}
+				}
+				const u32 w = __ballot_sync(0xffffffffu, v >> 31);
+				if (mine)
+					keep[PMAX] = w;
+			}
+			// group g0 + lane: whole unless it is the first one of a cell that does not start on a group boundary
+			const bool whole = lane > 0 || s == 0;
+#pragma unroll
+			for (int p = 0; p <= PMAX; ++p) {
+				if (p < planes || p == PMAX) {
+					u32 *d = dst + (long long)(p == PMAX ? planes : p) * P.GT + lane;
+					if (whole)
+						*d = keep[p];
+					else if (keep[p])
+						atomicOr(d, keep[p]);
+				}
+			}
+			if (s) { // the 33rd group holds the cell's last s positions
+				const int dloc = 1024 + lane - s;
+				u32 v = 0;
+				if (lane < s) {
+					int x, y;
+					cell_xy(lut, dloc, orient, x, y);
+					const int t = __ldg(src + (size_t)y * pitch + x);
+					v = (t < 0 ? 0x80000000u : 0u) | (u32)abs(t);
+				}
+				u32 mine = 0;
+				for (int p = 0; p < planes; ++p) {
+					const u32 w = __ballot_sync(0xffffffffu, (v >> p) & 1u);
+					if (lane == p)
+						mine = w;
+				}
+				const u32 sb = __ballot_sync(0xffffffffu, v >> 31);
+				if (lane == planes)
+					mine = sb;
+				if (lane <= planes && mine)
+					atomicOr(dst + (long long)lane * P.GT + 32, mine);
+			}
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) reconstruct_full_kernel(const __grid_constant__ HParams P,
+                                                                const u32 *__restrict__ list, int nlist,
+                                                                const u32 *__restrict__ bs, const int *__restrict__ missing,
+                                                                int levels_used, int *pyr, long long chan_stride, int pitch)
+{
+	__shared__ unsigned short lut[1024];
+	build_lut(lut);
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	for (int item = blockIdx.x * 8 + wid; item < nlist; item += gridDim.x * 8) {
+		const u32 ent = list[item];
+		const int level = (int)(ent >> 28);
+		if (level >= levels_used)
+			continue;
+		const HLevel &L = P.lv[level];
+		const u32 q = ent & 0x0fffffffu;
+		const u32 R0 = P.cell_base[L.cell_off + q], info = P.cell_info[L.cell_off + q];
+		const int ox = (int)(info & 0xfffu) * 32, oy = (int)((info >> 12) & 0xfffu) * 32;
+		const u32 orient = info >> 24;
+		const u32 g0 = R0 >> 5;
+		const int s = (int)(R0 & 31u);
+		int *base = pyr + (size_t)oy * pitch + ox;
+		for (int c = 0; c < P.channels; ++c) {
+			const int planes = P.lay.planes[c];
+			int *dstp = base + (size_t)c * chan_stride;
+			const u32 *src = bs + P.lay.bsbase[c] + L.gbase + g0;
+			const int m = missing[c * 16 + level] - 2; // decode.c:51-58
+			const int bias = m >= 0 ? 1 << m : 0;
+			u32 keep[PMAX + 1], last[PMAX + 1];
+#pragma unroll
+			for (int p = 0; p <= PMAX; ++p) {
+				keep[p] = 0;
+				last[p] = 0;
+				if (p < planes || p == PMAX) {
+					const u32 *r = src + (long long)(p == PMAX ? planes : p) * P.GT;
+					keep[p] = __ldg(r + lane);
+					if (s)
+						last[p] = __ldg(r + 32);
+				}
+			}
+			const int iters = s ? 33 : 32;
+			for (int k = 0; k < iters; ++k) {
+				const int dloc = 32 * k + lane - s;
+				int mag = 0;
+#pragma unroll
+				for (int p = 0; p < PMAX; ++p) {
+					if (p < planes) {
+						const u32 w = k < 32 ? __shfl_sync(0xffffffffu, keep[p], k) : last[p];
+						mag |= (int)((w >> lane) & 1u) << p;
+					}
+				}
+				const u32 sw = k < 32 ? __shfl_sync(0xffffffffu, keep[PMAX], k) : last[PMAX];
+				if (dloc >= 0 && dloc < 1024) {
+					int v = (sw >> lane) & 1u ? -mag : mag;
+					if (v != 0)
+						v += v < 0 ? -bias : bias;
+					int x, y;
+					cell_xy(lut, dloc, orient, x, y);
+					dstp[(size_t)y * pitch + x] = v;
+				}
+			}
+		}
+	}
+}
+
+// ---- cells cut by the image or the LL boundary: one CTA per cell, ranks by ballot / popc
+__global__ void __launch_bounds__(256) linearize_kernel(const __grid_constant__ HParams P, const u32 *__restrict__ list,
+                                                         const int *pyr, long long chan_stride, int pitch, u32 *bs)
 {
 	__shared__ u32 vals[3][1024];
 	__shared__ int wcnt[4][8];
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	const int q = blockIdx.x;
-	const int npos = P.cs * P.cs;
-	const u32 R0 = P.cell_base[q];
+	const u32 ent = list[blockIdx.x];
+	const HLevel &L = P.lv[ent >> 28];
+	const int q = (int)(ent & 0x0fffffffu);
+	const int npos = L.cs * L.cs;
+	const u32 R0 = P.cell_base[L.cell_off + q];
 	int px[4], py[4], rk[4];
 	bool ok[4];
 #pragma unroll
@@ -102,8 +261,8 @@ __global__ void __launch_bounds__(256) linearize_kernel(CellParams P, const int 
 		bool act = dloc < npos;
 		int x = 0, y = 0;
 		if (act)
-			hilbert_d2xy(P.n, (u32)q * (u32)npos + (u32)dloc, x, y);
-		bool v = act && x < P.w1 && y < P.h1 && (x >= P.w0 || y >= P.h0);
+			hilbert_d2xy(L.n, (u32)q * (u32)npos + (u32)dloc, x, y);
+		bool v = act && x < L.w1 && y < L.h1 && (x >= L.w0 || y >= L.h0);
 		u32 bal = __ballot_sync(0xffffffffu, v);
 		px[it] = x;
 		py[it] = y;
@@ -157,7 +316,7 @@ __global__ void __launch_bounds__(256) linearize_kernel(CellParams P, const int 
 			mine = sb;
 		bool whole = (u64)g * 32 >= R0 && (u64)g * 32 + 32 <= (u64)R0 + (u64)nv;
 		if (lane <= planes) {
-			u32 *dst = bs + P.lay.bsbase[c] + (long long)lane * P.GT + P.gbase + g;
+			u32 *dst = bs + P.lay.bsbase[c] + (long long)lane * P.GT + L.gbase + g;
 			if (whole)
 				*dst = mine;
 			else if (mine)
@@ -166,14 +325,20 @@ __global__ void __launch_bounds__(256) linearize_kernel(CellParams P, const int 
 	}
 }
 
-__global__ void __launch_bounds__(256) reconstruct_kernel(CellParams P, const u32 *bs, const int *missing, int level,
-                                                           int *pyr, long long chan_stride, int pitch)
+__global__ void __launch_bounds__(256) reconstruct_kernel(const __grid_constant__ HParams P, const u32 *__restrict__ list,
+                                                           const u32 *bs, const int *missing, int levels_used, int *pyr,
+                                                           long long chan_stride, int pitch)
 {
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	__shared__ int wcnt[4][8];
-	const int q = blockIdx.x;
-	const int npos = P.cs * P.cs;
-	const u32 R0 = P.cell_base[q];
+	const u32 ent = list[blockIdx.x];
+	const int level = (int)(ent >> 28);
+	if (level >= levels_used)
+		return;
+	const HLevel &L = P.lv[level];
+	const int q = (int)(ent & 0x0fffffffu);
+	const int npos = L.cs * L.cs;
+	const u32 R0 = P.cell_base[L.cell_off + q];
 	int px[4], py[4], rk[4];
 	bool ok[4];
 #pragma unroll
@@ -182,8 +347,8 @@ __global__ void __launch_bounds__(256) reconstruct_kernel(CellParams P, const u3
 		bool act = dloc < npos;
 		int x = 0, y = 0;
 		if (act)
-			hilbert_d2xy(P.n, (u32)q * (u32)npos + (u32)dloc, x, y);
-		bool v = act && x < P.w1 && y < P.h1 && (x >= P.w0 || y >= P.h0);
+			hilbert_d2xy(L.n, (u32)q * (u32)npos + (u32)dloc, x, y);
+		bool v = act && x < L.w1 && y < L.h1 && (x >= L.w0 || y >= L.h0);
 		u32 bal = __ballot_sync(0xffffffffu, v);
 		px[it] = x;
 		py[it] = y;
@@ -208,7 +373,7 @@ __global__ void __launch_bounds__(256) reconstruct_kernel(CellParams P, const u3
 		u32 g = r >> 5, bit = r & 31;
 		for (int c = 0; c < P.channels; ++c) {
 			const int planes = P.lay.planes[c];
-			const u32 *src = bs + P.lay.bsbase[c] + P.gbase + g;
+			const u32 *src = bs + P.lay.bsbase[c] + L.gbase + g;
 			int mag = 0;
 			for (int p = 0; p < planes; ++p)
 				mag |= (int)((__ldg(src + (long long)p * P.GT) >> bit) & 1u) << p;
@@ -253,27 +418,46 @@ ChanLayout make_layout(const Sched &s, int channels)
 	return lay;
 }
 
-CellParams make_cell_params(const Geom &g, const HilbertPlan &plan, const Sched &s, int l)
+HParams make_params(const Geom &g, const HilbertPlan &plan, const Sched &s)
 {
-	CellParams P;
-	P.n = g.len[l + 1];
-	P.cs = plan.cs[l];
-	P.w1 = g.w[l + 1];
-	P.h1 = g.h[l + 1];
-	P.w0 = g.w[l];
-	P.h0 = g.h[l];
+	HParams P;
+	for (int l = 0; l < DWT_MAX_LEVELS; ++l) {
+		HLevel &L = P.lv[l];
+		if (l < g.levels) {
+			L.n = g.len[l + 1];
+			L.cs = plan.cs[l];
+			L.w1 = g.w[l + 1];
+			L.h1 = g.h[l + 1];
+			L.w0 = g.w[l];
+			L.h0 = g.h[l];
+			L.gbase = g.gbase[l];
+			L.cell_off = (u32)plan.cell_off[l];
+		} else {
+			L.n = L.cs = L.w1 = L.h1 = L.w0 = L.h0 = L.gbase = 0;
+			L.cell_off = 0;
+		}
+	}
 	P.channels = g.channels;
 	P.GT = g.GT;
-	P.gbase = g.gbase[l];
-	P.cell_base = plan.cell_base + plan.cell_off[l];
 	P.lay = make_layout(s, g.channels);
+	P.cell_base = plan.cell_base;
+	P.cell_info = plan.cell_info;
 	return P;
+}
+
+bool planes_fit(const Geom &g, const Sched &s)
+{
+	for (int c = 0; c < g.channels; ++c)
+		if (s.planes[c] > PMAX)
+			return false;
+	return true;
 }
 
 } // namespace
 
 int hilbert_plan_build(const Geom &g, HilbertPlan *plan, cudaStream_t st, long long *launches)
 {
+	(void)launches;
 	int off = 0;
 	for (int l = 0; l < g.levels; ++l) {
 		int n = g.len[l + 1];
@@ -284,18 +468,50 @@ int hilbert_plan_build(const Geom &g, HilbertPlan *plan, cudaStream_t st, long l
 		off += plan->ncell[l];
 	}
 	plan->cell_off[g.levels] = off;
-	plan->cell_base = nullptr;
-	CUDA_OK(cudaMalloc(&plan->cell_base, sizeof(u32) * (size_t)(off > 0 ? off : 1)));
+	const size_t ntot = (size_t)(off > 0 ? off : 1);
+	std::vector<u32> h_base(ntot), h_info(ntot), h_full, h_part;
 	for (int l = 0; l < g.levels; ++l) {
-		u32 *cb = plan->cell_base + plan->cell_off[l];
-		int nc = plan->ncell[l];
-		cell_count_kernel<<<(nc + 255) / 256, 256, 0, st>>>(g.len[l + 1], plan->cs[l], g.w[l + 1], g.h[l + 1], g.w[l],
-		                                                    g.h[l], nc, cb);
-		exscan_u32_kernel<<<1, 1024, 0, st>>>(cb, nc);
-		if (launches)
-			*launches += 2;
+		const int n = g.len[l + 1], cs = plan->cs[l], nc = plan->ncell[l];
+		const int w1 = g.w[l + 1], h1 = g.h[l + 1], w0 = g.w[l], h0 = g.h[l];
+		plan->full_off[l] = (int)h_full.size();
+		plan->part_off[l] = (int)h_part.size();
+		u32 run = 0;
+		for (int q = 0; q < nc; ++q) {
+			int x0, y0, x1, y1;
+			hilbert_d2xy(n, (u32)q * (u32)(cs * cs), x0, y0);
+			hilbert_d2xy(n, (u32)q * (u32)(cs * cs) + 1u, x1, y1);
+			const int ox = x0 & ~(cs - 1), oy = y0 & ~(cs - 1);
+			// the base curve starts at (0,0) and steps to (0,1): a start in the far corner means the cell is
+			// point-reflected, a first step along x means it is transposed
+			const u32 flip = (x0 - ox) != 0 ? 2u : 0u;
+			const u32 swap = (y1 == y0) ? 1u : 0u;
+			const int cnt = overlap(ox, cs, w1) * overlap(oy, cs, h1) - overlap(ox, cs, w0) * overlap(oy, cs, h0);
+			const size_t idx = (size_t)plan->cell_off[l] + q;
+			h_base[idx] = run;
+			h_info[idx] = (u32)(ox / cs) | ((u32)(oy / cs) << 12) | ((swap | flip) << 24);
+			run += (u32)cnt;
+			const u32 ent = ((u32)l << 28) | (u32)q;
+			if (cs == 32 && cnt == 1024)
+				h_full.push_back(ent);
+			else if (cnt > 0)
+				h_part.push_back(ent);
+		}
 	}
-	CUDA_OK(cudaGetLastError());
+	plan->full_off[g.levels] = (int)h_full.size();
+	plan->part_off[g.levels] = (int)h_part.size();
+	const size_t words = 2 * ntot + h_full.size() + h_part.size() + 4;
+	plan->cell_base = nullptr;
+	CUDA_OK(cudaMalloc(&plan->cell_base, sizeof(u32) * words));
+	plan->cell_info = plan->cell_base + ntot;
+	plan->full_list = plan->cell_info + ntot;
+	plan->part_list = plan->full_list + h_full.size();
+	CUDA_OK(cudaMemcpyAsync(plan->cell_base, h_base.data(), sizeof(u32) * ntot, cudaMemcpyHostToDevice, st));
+	CUDA_OK(cudaMemcpyAsync(plan->cell_info, h_info.data(), sizeof(u32) * ntot, cudaMemcpyHostToDevice, st));
+	if (!h_full.empty())
+		CUDA_OK(cudaMemcpyAsync(plan->full_list, h_full.data(), sizeof(u32) * h_full.size(), cudaMemcpyHostToDevice, st));
+	if (!h_part.empty())
+		CUDA_OK(cudaMemcpyAsync(plan->part_list, h_part.data(), sizeof(u32) * h_part.size(), cudaMemcpyHostToDevice, st));
+	CUDA_OK(cudaStreamSynchronize(st)); // the host vectors go out of scope
 	return 0;
 }
 
@@ -306,13 +522,39 @@ void hilbert_plan_free(HilbertPlan *plan)
 	plan->cell_base = nullptr;
 }
 
+static int full_grid(int nlist)
+{
+	static int sms = 0;
+	if (!sms) {
+		int dev = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if (sms <= 0)
+			sms = 1;
+	}
+	const int want = (nlist + 7) / 8;
+	return want < sms * 8 ? want : sms * 8;
+}
+
 int hilbert_linearize(const Geom &g, const HilbertPlan &plan, const Sched &s, const int *pyr,
                       long long pyr_chan_stride, int pyr_pitch, u32 *bs, int levels_used, cudaStream_t st,
                       long long *launches)
 {
-	for (int l = 0; l < levels_used; ++l) {
-		CellParams P = make_cell_params(g, plan, s, l);
-		linearize_kernel<<<plan.ncell[l], 256, 0, st>>>(P, pyr, pyr_chan_stride, pyr_pitch, bs);
+	const HParams P = make_params(g, plan, s);
+	const bool fast = planes_fit(g, s);
+	// lists are ordered by level: the first levels_used levels are a prefix
+	const int nfull = plan.full_off[levels_used], npart = plan.part_off[levels_used];
+	if (fast && nfull > 0) {
+		linearize_full_kernel<<<full_grid(nfull), 256, 0, st>>>(P, plan.full_list, nfull, pyr, pyr_chan_stride, pyr_pitch, bs);
+		if (launches)
+			++*launches;
+	} else if (nfull > 0) {
+		linearize_kernel<<<nfull, 256, 0, st>>>(P, plan.full_list, pyr, pyr_chan_stride, pyr_pitch, bs);
+		if (launches)
+			++*launches;
+	}
+	if (npart > 0) {
+		linearize_kernel<<<npart, 256, 0, st>>>(P, plan.part_list, pyr, pyr_chan_stride, pyr_pitch, bs);
 		if (launches)
 			++*launches;
 	}
@@ -324,9 +566,23 @@ int hilbert_reconstruct(const Geom &g, const HilbertPlan &plan, const Sched &s, 
                         const int *missing_dev, int *pyr, long long pyr_chan_stride, int pyr_pitch,
                         int levels_used, cudaStream_t st, long long *launches)
 {
-	for (int l = 0; l < levels_used; ++l) {
-		CellParams P = make_cell_params(g, plan, s, l);
-		reconstruct_kernel<<<plan.ncell[l], 256, 0, st>>>(P, bs, missing_dev, l, pyr, pyr_chan_stride, pyr_pitch);
+	const HParams P = make_params(g, plan, s);
+	const bool fast = planes_fit(g, s);
+	const int nfull = plan.full_off[levels_used], npart = plan.part_off[levels_used];
+	if (fast && nfull > 0) {
+		reconstruct_full_kernel<<<full_grid(nfull), 256, 0, st>>>(P, plan.full_list, nfull, bs, missing_dev, levels_used, pyr,
+		                                                         pyr_chan_stride, pyr_pitch);
+		if (launches)
+			++*launches;
+	} else if (nfull > 0) {
+		reconstruct_kernel<<<nfull, 256, 0, st>>>(P, plan.full_list, bs, missing_dev, levels_used, pyr, pyr_chan_stride,
+		                                          pyr_pitch);
+		if (launches)
+			++*launches;
+	}
+	if (npart > 0) {
+		reconstruct_kernel<<<npart, 256, 0, st>>>(P, plan.part_list, bs, missing_dev, levels_used, pyr, pyr_chan_stride,
+		                                          pyr_pitch);
 		if (launches)
 			++*launches;
 	}

@@ -3,15 +3,24 @@
 #pragma once
 #include "common.cuh"
 
-// Geometry-only plan: for every detail level the curve is cut into aligned cells of cs x cs positions
-// (cs = min(32, side)); cell_base[cell_off[l] + q] = number of valid positions (inside the level's
-// w x h domain, outside its LL rectangle) that precede cell q on the curve -- the closed-form rank of
-// SURVEY.md App. C.3 evaluated per cell.
+// Geometry-only plan, built on the host once per image size: for every detail level the curve is cut into aligned
+// cells of cs x cs positions (cs = min(32, side)).
+//   cell_base[cell_off[l] + q]  number of valid positions (inside the level's w x h domain, outside its LL
+//                               rectangle) that precede cell q on the curve -- the closed-form rank of SURVEY.md
+//                               App. C.3 evaluated per cell
+//   cell_info[...]              cell column | cell row << 12 | orientation << 24: inside a cell the curve is the
+//                               32 x 32 base curve transposed (bit 0) and / or point-reflected (bit 1)
+//   full_list / part_list       cells whose 1024 positions are all valid (warp-per-cell fast kernels) and cells cut
+//                               by the image or LL boundary (generic kernel); empty cells are in neither.
+//                               Entry = level << 28 | q, all levels back to back.
 struct HilbertPlan {
 	int cell_off[DWT_MAX_LEVELS + 1];
 	int ncell[DWT_MAX_LEVELS];
 	int cs[DWT_MAX_LEVELS];
-	u32 *cell_base; // device
+	int full_off[DWT_MAX_LEVELS + 1], part_off[DWT_MAX_LEVELS + 1]; // list ranges per level
+	u32 *cell_base; // device (one allocation holds all four arrays)
+	u32 *cell_info;
+	u32 *full_list, *part_list;
 };
 
 int hilbert_plan_build(const Geom &g, HilbertPlan *plan, cudaStream_t st, long long *launches);
