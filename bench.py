@@ -4,11 +4,13 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step is one pass of the hot path over one synthetic 7680x4320 RGB frame: lossless encode to a .dwt stream
-and decode of that stream back to pixels.  Mpixel/s = W*H*steps*ranks / seconds.
-  value : device-resident round trip (image and stream already in HBM), CUDA events on the codec's stream
+A step is one pass of the hot path over a batch of --frames synthetic 7680x4320 RGB frames: lossless encode to a
+.dwt stream and decode of that stream back to pixels, the frames of a step in flight together (one codec context =
+one CUDA stream + one host thread per frame; images are independent).  Mpixel/s = W*H*frames*steps*ranks / seconds.
+  value : device-resident round trips (images and streams already in HBM), one region of CUDA events per step
   e2e   : the same through the public C ABI with page-locked HOST buffers (dwt_encode_into/dwt_decode_into),
           host->device and device->host copies inside the timed region
+  single_frame / stages / roofline : a pass with ONE frame at a time, so that every kernel runs alone on the GPU
 Images are independent, so ranks shard frames with no collective on the data path ("weak" scaling: one frame
 stream per GPU); torch.distributed is only the barrier and the max-over-ranks of the timing.
 --impl reference times the UNMODIFIED reference programs (oracle/_ref, built by oracle/Makefile) on the host
@@ -187,7 +189,9 @@ def reduce_over_ranks(total_ms, e2e_ms, launches, device):
 
 
 def our_bench(args, rank, world, local):
+    import hashlib
     import torch
+    from concurrent.futures import ThreadPoolExecutor
     import dwt_b200 as D
     from oracle import pyoracle as O  # synthetic generator only (inputs); the codec never touches it
 
@@ -196,46 +200,58 @@ def our_bench(args, rank, world, local):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cod = D.Codec(local)
+    F = max(1, args.frames)              # frames per step, coded concurrently on F contexts (one CUDA stream each)
+    cods = [D.Codec(local) for _ in range(F)]
+    cod = cods[0]
     img = O.synth(W, H, "photo", frame_seed(rank))
     npx = W * H
 
-    # ---- page-locked host buffers for the end-to-end path
-    pin_flat, own1 = D.pinned_array(img.size)
-    pin_flat[:] = img.reshape(-1)
-    pin_img = pin_flat.reshape(H, W, CH)
-    pin_out, own2 = D.pinned_array(img.size * 2 + 4096)
-    pin_dec, own3 = D.pinned_array(img.size)
+    # ---- page-locked host buffers for the end-to-end path (one set per context)
+    keep = []
+    pin_img, pin_out, pin_dec = [], [], []
+    for _ in range(F):
+        a, o1 = D.pinned_array(img.size)
+        a[:] = img.reshape(-1)
+        b, o2 = D.pinned_array(img.size * 2 + 4096)
+        c, o3 = D.pinned_array(img.size)
+        keep += [o1, o2, o3]
+        pin_img.append(a.reshape(H, W, CH))
+        pin_out.append(b)
+        pin_dec.append(c)
 
-    # ---- parity gate: no number without bit-exactness (lossless round trip + pin for rank 0's frame)
-    n = cod.encode_into(pin_img, pin_out)
-    import hashlib
-    if rank == 0:
-        digest = hashlib.sha256(pin_out[:n].tobytes()).hexdigest()[:32]
-        assert (n, digest) == (48863617, "f14ef79d0680a4ace7daa2b9e8063651"), "8K stream differs from the reference pin"
-    shp = cod.decode_into(pin_out, n, pin_dec)
-    assert shp == (H, W, CH) and np.array_equal(pin_dec, pin_flat), "round trip is not lossless"
+    # ---- parity gate: no number without bit-exactness (lossless round trip + pin for rank 0's frame), every context
+    for i, cd in enumerate(cods):
+        n = cd.encode_into(pin_img[i], pin_out[i])
+        if rank == 0:
+            digest = hashlib.sha256(pin_out[i][:n].tobytes()).hexdigest()[:32]
+            assert (n, digest) == (48863617, "f14ef79d0680a4ace7daa2b9e8063651"), "8K stream differs from the reference pin"
+        shp = cd.decode_into(pin_out[i], n, pin_dec[i])
+        assert shp == (H, W, CH) and np.array_equal(pin_dec[i], pin_img[i].reshape(-1)), "round trip is not lossless"
     stream_bytes = n
 
+    def sync_all():
+        for cd in cods:
+            D.lib().dwt_ctx_sync(cd._h)
+
     def barrier():
-        cod_sync()
+        sync_all()
         if use_dist:
             dist.barrier()
 
-    def cod_sync():
-        D.lib().dwt_ctx_sync(cod._h)
+    for i, cd in enumerate(cods):
+        cd.upload_image(pin_img[i])
+        cd.upload_stream(pin_out[i][:n])
+    pool = ThreadPoolExecutor(max_workers=F)
 
-    # ---- device-resident steps: image and stream already in HBM
-    cod.upload_image(pin_img)
-    cod.upload_stream(pin_out[:n])
+    # ---- pass 1, one frame at a time (latency; every kernel alone on the GPU: the stage timings and the roofline)
     stage = dict(lift_fwd=[], linearize=[], enc_coder=[], dec_coder=[], reconstruct=[], lift_inv=[], enc=[], dec=[])
 
-    def resident_step(timed):
+    def serial_step(timed):
         cod.flush_l2()
         cod.event_record(0)
         se = cod.encode_resident(0)
         e = (se.ms_lift, se.ms_linearize, se.ms_coder, se.ms_total)
-        sd_ = cod.decode_resident(-1)
+        cod.decode_resident(-1)
         sd = cod.stats
         cod.event_record(1)
         ms = cod.event_elapsed_ms(0, 1)
@@ -246,23 +262,48 @@ def our_bench(args, rank, world, local):
         return ms
 
     for _ in range(args.warmup):
-        resident_step(False)
+        serial_step(False)
+    barrier()
+    serial_ms = [serial_step(True) for _ in range(args.steps)]
+    barrier()
+
+    # ---- pass 2, the measured throughput: F frames per step, device resident, one region of CUDA events
+    def resident_frame(i):
+        cods[i].encode_resident(0)
+        cods[i].decode_resident(-1)
+
+    def resident_step():
+        cod.flush_l2()
+        sync_all()
+        cod.event_record(0)
+        list(pool.map(resident_frame, range(F)))
+        for cd in cods[1:]:
+            cod.wait_for(cd)
+        cod.event_record(1)
+        return cod.event_elapsed_ms(0, 1)
+
+    for _ in range(args.warmup):
+        resident_step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = cod.launch_count()
+    l0 = sum(cd.launch_count() for cd in cods)
     t_wall0 = time.perf_counter()
-    dev_ms = [resident_step(True) for _ in range(args.steps)]
+    dev_ms = [resident_step() for _ in range(args.steps)]
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = cod.launch_count() - l0
+    launches = sum(cd.launch_count() for cd in cods) - l0
     total_ms = sum(dev_ms)
 
-    # ---- end-to-end steps: host buffers in, host buffers out, copies inside the timed region
+    # ---- pass 3, end to end: host buffers in, host buffers out, copies inside the timed region, F frames in flight
+    def e2e_frame(i):
+        m = cods[i].encode_into(pin_img[i], pin_out[i])
+        cods[i].decode_into(pin_out[i], m, pin_dec[i])
+
     def e2e_step():
         cod.flush_l2()
+        sync_all()
         t0 = time.perf_counter()
-        m = cod.encode_into(pin_img, pin_out)
-        cod.decode_into(pin_out, m, pin_dec)
+        list(pool.map(e2e_frame, range(F)))
         return (time.perf_counter() - t0) * 1e3
 
     for _ in range(max(1, args.warmup // 2)):
@@ -272,6 +313,7 @@ def our_bench(args, rank, world, local):
     barrier()
     clocks = sampler.stop() if sampler else None
     e2e_total = sum(e2e_ms)
+    assert np.array_equal(pin_dec[F - 1], pin_img[F - 1].reshape(-1)), "end-to-end round trip is not lossless"
 
     # ---- max over ranks
     if use_dist:
@@ -281,8 +323,8 @@ def our_bench(args, rank, world, local):
             dist.destroy_process_group()
         return None
 
-    value = job_mpixels_per_s(npx, args.steps, world, total_ms)
-    e2e_value = job_mpixels_per_s(npx, args.steps, world, e2e_total)
+    value = job_mpixels_per_s(npx * F, args.steps, world, total_ms)
+    e2e_value = job_mpixels_per_s(npx * F, args.steps, world, e2e_total)
     peak, peak_kind = peaks()
     med = {k: statistics.median(v) for k, v in stage.items()}
 
@@ -292,34 +334,40 @@ def our_bench(args, rank, world, local):
                     ms=round(ms, 4), bytes=int(nbytes))
 
     nsamples = npx * CH
-    traffic = None
+    traffic = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             traffic = json.load(f)
     except Exception:
         traffic = {}
     roofline = roof(med["lift_fwd"], LIFT_BYTES_PER_PIXEL * npx)
-    roofline.update(kernel="lift_fwd_kernel, all %d levels (colour fused into the first)" % 10, peak_source=peak_kind,
-                    traffic=traffic.get("lift_fwd"))
+    roofline.update(kernel="lift_fwd_kernel x levels + lift_tail_fwd_kernel (colour fused into the first level)",
+                    peak_source=peak_kind, traffic=traffic.get("lift_fwd"),
+                    measured_in="single-frame pass: the lifting kernels alone on the GPU, CUDA events on their stream")
     stages = dict(
         lift_fwd=roofline,
-        lift_inv=dict(roof(med["lift_inv"], LIFT_BYTES_PER_PIXEL * npx), kernel="lift_inv_kernel, all levels (colour + clamp fused into the last)",
+        lift_inv=dict(roof(med["lift_inv"], LIFT_BYTES_PER_PIXEL * npx), kernel="lift_tail_inv_kernel + lift_inv_kernel x levels (colour + clamp fused into the last)",
                       traffic=traffic.get("lift_inv")),
-        linearize=dict(roof(med["linearize"], 4 * nsamples + nsamples * 10 / 8), kernel="linearize_kernel (Hilbert gather + bit-slicing)"),
+        linearize=dict(roof(med["linearize"], 4 * nsamples + nsamples * 10 / 8), kernel="linearize_full_kernel + linearize_kernel (Hilbert gather + bit-slicing)"),
         enc_coder=dict(roof(med["enc_coder"], 4 * nsamples + stream_bytes), kernel="enc_* (count, scan, emit, VLI orders, scatter)"),
-        dec_coder=dict(roof(med["dec_coder"], 4 * nsamples + stream_bytes), kernel="dec_* (prep, tilescan, parse, deposit) x chunks"),
-        reconstruct=dict(roof(med["reconstruct"], 4 * nsamples + nsamples * 10 / 8), kernel="reconstruct_kernel (Hilbert scatter + bias)"),
+        dec_coder=dict(roof(med["dec_coder"], 4 * nsamples + stream_bytes), kernel="dec_* (scan, link, resolve, emit, prep/tilescan/deposit per plane depth)"),
+        reconstruct=dict(roof(med["reconstruct"], 4 * nsamples + nsamples * 10 / 8), kernel="reconstruct_full_kernel + reconstruct_kernel (Hilbert scatter + bias)"),
     )
     out = dict(metric="encode/decode Mpixel/s, 8K RGB", value=round(value, 2), unit="Mpixel/s", n_gpus=world, steps=args.steps,
                warmup=args.warmup, ms_per_step=round(total_ms / args.steps, 3), higher_is_better=True, scaling="weak",
                vs_baseline=None, dtype="int32", data="synthetic",
-               config=dict(workload=WORKLOAD, frames_per_step_per_gpu=1, width=W, height=H, channels=CH, l2=L2_NOTE,
-                           stream_bytes=stream_bytes, parallelism="one frame stream per GPU, no collective"),
+               config=dict(workload=WORKLOAD, frames_per_step_per_gpu=F, width=W, height=H, channels=CH, l2=L2_NOTE,
+                           stream_bytes=stream_bytes,
+                           parallelism="one frame stream per GPU, no collective; the %d frames of a step are coded concurrently "
+                                       "on %d contexts (one CUDA stream and one host thread each)" % (F, F)),
                e2e=dict(value=round(e2e_value, 2), unit="Mpixel/s", ms_per_step=round(e2e_total / args.steps, 3),
-                        h2d_bytes_per_step=int(img.size + stream_bytes), d2h_bytes_per_step=int(stream_bytes + img.size),
-                        api="dwt_encode_into + dwt_decode_into on page-locked host buffers"),
+                        h2d_bytes_per_step=int(F * (img.size + stream_bytes)), d2h_bytes_per_step=int(F * (stream_bytes + img.size)),
+                        api="dwt_encode_into + dwt_decode_into on page-locked host buffers, %d frames in flight" % F),
                gpu_launches=int(launches), clocks=clocks, roofline=roofline, stages=stages,
-               encode_mpx_s=round(npx / (med["enc"] / 1e3) / 1e6, 1), decode_mpx_s=round(npx / (med["dec"] / 1e3) / 1e6, 1),
+               single_frame=dict(ms_per_frame=round(statistics.median(serial_ms), 3),
+                                 mpixel_s=round(npx / (statistics.median(serial_ms) / 1e3) / 1e6, 1),
+                                 encode_mpx_s=round(npx / (med["enc"] / 1e3) / 1e6, 1),
+                                 decode_mpx_s=round(npx / (med["dec"] / 1e3) / 1e6, 1)),
                wall_ms_per_step=round(t_wall * 1e3 / args.steps, 3))
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -338,6 +386,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames", type=int, default=4, help="frames per step, coded concurrently (one context each)")
     args = ap.parse_args()
     rank, world, local = dist_env()
     if args.impl == "reference":

@@ -18,7 +18,7 @@ ABI_SYMBOLS = [
     "dwt_ctx_upload_image", "dwt_ctx_encode_resident", "dwt_ctx_download_stream", "dwt_ctx_upload_stream",
     "dwt_ctx_decode_resident", "dwt_ctx_download_image", "dwt_ctx_launch_count", "dwt_ctx_sync",
     "dwt_host_alloc", "dwt_host_free", "dwt_encode_into", "dwt_decode_into", "dwt_ctx_flush_l2",
-    "dwt_ctx_event_record", "dwt_ctx_event_elapsed_ms",
+    "dwt_ctx_event_record", "dwt_ctx_event_elapsed_ms", "dwt_ctx_wait_for",
     "cdf53", "icdf53", "dwt_forward", "dwt_inverse", "dwt_ycocg_from_rgb", "dwt_rgb_from_ycocg",
     "compute_lengths", "ilog2", "dwt_debug_front_end",
     "bytes_reader", "bytes_writer", "bytes_count", "close_bytes_reader", "close_bytes_writer", "put_byte",
@@ -85,6 +85,7 @@ def lib():
     L.dwt_ctx_event_record.argtypes = [vp, C.c_int]
     L.dwt_ctx_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int]
     L.dwt_ctx_event_elapsed_ms.restype = C.c_float
+    L.dwt_ctx_wait_for.argtypes = [vp, vp]
     L.cdf53.argtypes = [ip, ip, C.c_int, C.c_int, C.c_int, C.c_int]
     L.cdf53.restype = None
     L.icdf53.argtypes = [ip, ip, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -241,6 +242,11 @@ class Codec:
 
     def event_elapsed_ms(self, a, b):
         return float(lib().dwt_ctx_event_elapsed_ms(self._h, a, b))
+
+    def wait_for(self, other):
+        """this context's stream waits for the work queued so far on `other`'s stream"""
+        if lib().dwt_ctx_wait_for(self._h, other._h):
+            raise DwtError("wait_for failed: " + last_error())
 
     # ---- parity taps
     def front_end(self, img):

@@ -369,6 +369,20 @@ extern "C" int dwt_ctx_event_record(dwt_ctx *c, int slot)
 	return 0;
 }
 
+// make `c`'s stream wait for everything queued so far on `other`'s stream (frames coded concurrently on several
+// contexts are timed as one region with events of one context)
+extern "C" int dwt_ctx_wait_for(dwt_ctx *c, dwt_ctx *other)
+{
+	if (!c || !other)
+		return -1;
+	if (c == other)
+		return 0;
+	CUDA_OK(cudaSetDevice(c->device));
+	CUDA_OK(cudaEventRecord(other->ev[8], other->st));
+	CUDA_OK(cudaStreamWaitEvent(c->st, other->ev[8], 0));
+	return 0;
+}
+
 extern "C" float dwt_ctx_event_elapsed_ms(dwt_ctx *c, int slot_a, int slot_b)
 {
 	float ms = -1.f;

@@ -157,8 +157,16 @@ __global__ void __launch_bounds__(WS) dec_scan_kernel(const u32 *__restrict__ st
 		if (e1 == PDEAD)
 			e1 = 1u;
 	}
-	u32 x0 = e0 == 0u ? xs0 : (e0 == 1u ? xs1 : slice_exit(a, b, avail, e0));
-	u32 x1 = e1 == e0 ? x0 : (e1 == 0u ? xs0 : (e1 == 1u ? xs1 : slice_exit(a, b, avail, e1)));
+	// exits of the predicted entries, with the members / tokens they consume (kept up to date while the entries change)
+	u64 m0, m1;
+	u32 t0, t1;
+	u32 x0 = slice_walk(a, b, avail, e0, m0, t0), x1 = x0;
+	if (e1 == e0) {
+		m1 = m0;
+		t1 = t0;
+	} else {
+		x1 = slice_walk(a, b, avail, e1, m1, t1);
+	}
 	__syncthreads();
 	// fixed point: entry <- the predecessor's exact exit.  Slice i is exact after i rounds at the latest; in
 	// practice a wrong prediction is repaired where the chains join again, a few slices further on.
@@ -175,28 +183,28 @@ __global__ void __launch_bounds__(WS) dec_scan_kernel(const u32 *__restrict__ st
 				n1 = 1u;
 			if (n0 != e0) {
 				e0 = n0;
-				x0 = slice_exit(a, b, avail, e0);
+				x0 = slice_walk(a, b, avail, e0, m0, t0);
 				changed = 1;
 			}
 			if (n1 != e1) {
 				e1 = n1;
-				x1 = e1 == e0 ? x0 : slice_exit(a, b, avail, e1);
+				if (e1 == e0) {
+					x1 = x0;
+					m1 = m0;
+					t1 = t0;
+				} else {
+					x1 = slice_walk(a, b, avail, e1, m1, t1);
+				}
 				changed = 1;
 			}
 		}
 		if (!__syncthreads_or(changed))
 			break;
 	}
-	u64 m0, m1;
-	u32 t0, t1;
-	if (slice_walk(a, b, avail, e0, m0, t0) == PDEAD)
+	if (x0 == PDEAD)
 		m0 += DEATH;
-	if (e1 == e0) {
-		m1 = m0;
-		t1 = t0;
-	} else if (slice_walk(a, b, avail, e1, m1, t1) == PDEAD) {
+	if (x1 == PDEAD)
 		m1 += DEATH;
-	}
 	u64 tot0, tot1, tott;
 	const u64 p0 = block_exscan_u64(m0, ws, &tot0);
 	const u64 p1 = block_exscan_u64(m1, ws, &tot1);
@@ -777,8 +785,24 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 
 // ---------------------------------------------------------------------------------------------- emit
 
+// rank-space bits of consecutive tokens mostly fall into the same 32-bit word: they are collected in registers and
+// sent with one atomic per word
+struct RankAcc {
+	u64 word;
+	u32 ones, signs;
+};
+
+__device__ __forceinline__ void acc_flush(RankAcc &A, u32 *ones_rank, u32 *sign_rank)
+{
+	if (A.ones)
+		atomicOr(ones_rank + A.word, A.ones);
+	if (A.signs)
+		atomicOr(sign_rank + A.word, A.signs);
+	A.ones = A.signs = 0;
+}
+
 // ones and signs of the tokens that start in one slice; false when the chain ends here
-__device__ __forceinline__ bool emit_slice(u64 a, u64 b, int avail, u64 T, u64 base, int &d, int &k, u64 &cum,
+__device__ __forceinline__ bool emit_slice(u64 a, u64 b, int avail, u64 T, u64 base, int &d, int &k, u64 &cum, RankAcc &A,
                                            u32 *ones_rank, u32 *sign_rank)
 {
 	while (d < 64) {
@@ -794,11 +818,16 @@ __device__ __forceinline__ bool emit_slice(u64 a, u64 b, int avail, u64 T, u64 b
 		if (one >= T)
 			return false;
 		const u64 rk = base + one;
-		atomicOr(ones_rank + (rk >> 5), 1u << (rk & 31));
+		if ((rk >> 5) != A.word) {
+			acc_flush(A, ones_rank, sign_rank);
+			A.word = rk >> 5;
+		}
+		const u32 bit = 1u << (rk & 31);
+		A.ones |= bit;
 		if (d + L + 1 > avail)
 			return false;
 		if ((w >> L) & 1ull)
-			atomicOr(sign_rank + (rk >> 5), 1u << (rk & 31));
+			A.signs |= bit;
 		cum = one + 1;
 		d += L + 1;
 		k = e >= 2 ? e - 2 : 0;
@@ -821,14 +850,16 @@ __global__ void __launch_bounds__(WS) dec_emit_kernel(const __grid_constant__ De
 		// exact steps through the slices in front of the join
 		int d = (int)(s.state & 63u), k = (int)(s.state >> 6);
 		u64 cum = s.cum0;
+		RankAcc A = {~0ull, 0u, 0u};
 		for (int ii = i; ii < m; ++ii) {
 			u64 a, b;
 			const u64 gs = wbase + ii;
 			load_slice(B.stream, B.end_bits, gs, a, b);
-			if (!emit_slice(a, b, clamp_avail(B.end_bits, gs << 6), T, base, d, k, cum, B.ones_rank, B.sign_rank))
+			if (!emit_slice(a, b, clamp_avail(B.end_bits, gs << 6), T, base, d, k, cum, A, B.ones_rank, B.sign_rank))
 				break;
 			d -= 64;
 		}
+		acc_flush(A, B.ones_rank, B.sign_rank);
 	} else if (i >= m) {
 		const u64 gs = wbase + i;
 		const u32 e = (B.E[gs] >> (16 * s.qm)) & 0xffffu;
@@ -841,7 +872,9 @@ __global__ void __launch_bounds__(WS) dec_emit_kernel(const __grid_constant__ De
 		u64 a, b;
 		load_slice(B.stream, B.end_bits, gs, a, b);
 		int d = (int)(e & 63u), k = (int)(e >> 6);
-		emit_slice(a, b, clamp_avail(B.end_bits, gs << 6), T, base, d, k, cum, B.ones_rank, B.sign_rank);
+		RankAcc A = {~0ull, 0u, 0u};
+		emit_slice(a, b, clamp_avail(B.end_bits, gs << 6), T, base, d, k, cum, A, B.ones_rank, B.sign_rank);
+		acc_flush(A, B.ones_rank, B.sign_rank);
 	}
 }
 

@@ -28,7 +28,7 @@ struct dwt_ctx {
 	int device = 0;
 	cudaStream_t st = nullptr;
 	long long launches = 0;
-	cudaEvent_t ev[8] = {};
+	cudaEvent_t ev[9] = {};   // 0..3 stage timers, 4..7 caller slots, 8 cross-context waits
 
 	// geometry cache
 	bool have_geom = false;

@@ -90,6 +90,8 @@ int dwt_decode_into(dwt_ctx *ctx, const uint8_t *stream, size_t len, int pixels_
 int dwt_ctx_flush_l2(dwt_ctx *ctx);
 int dwt_ctx_event_record(dwt_ctx *ctx, int slot);
 float dwt_ctx_event_elapsed_ms(dwt_ctx *ctx, int slot_a, int slot_b);
+/* ctx's stream waits for the work queued so far on other's stream (several contexts timed as one region) */
+int dwt_ctx_wait_for(dwt_ctx *ctx, dwt_ctx *other);
 
 /* ------------------------------------------------------------------ transform entry points */
 
