@@ -101,11 +101,108 @@ __device__ __forceinline__ u32 slice_walk(u64 a, u64 b, int avail, u32 entry, u6
 	return (u32)(d - 64) | ((u32)k << 6);
 }
 
+// ---- order-0 token table.  93 % of the tokens are coded at order 0 with at most two leading zeros (run < 7):
+// "1s", "01ps", "001pps" -- 2, 4 or 6 bits, and the order stays 0.  TOKLUT[12 stream bits] decodes as many of
+// those as fit completely: bits consumed (4 bits) | start of the last token (4) | tokens (3) | members (6).
+// A window that starts with anything else (longer run, non-zero order) yields 0 and takes the generic step.
+constexpr int LUT_BITS = 12;
+
+__host__ __device__ inline u32 toklut_entry(u32 bits)
+{
+	int pos = 0, last = 0, ntok = 0, mem = 0;
+	for (;;) {
+		int u = 0;
+		while (u < 3 && pos + u < LUT_BITS && !((bits >> (pos + u)) & 1u))
+			++u;
+		if (u >= 3 || pos + 2 * u + 2 > LUT_BITS)
+			break;
+		const u32 payload = (bits >> (pos + u + 1)) & ((1u << u) - 1u);
+		mem += (1 << u) - 1 + (int)payload + 1;
+		++ntok;
+		last = pos;
+		pos += 2 * u + 2;
+	}
+	return (u32)pos | ((u32)last << 4) | ((u32)ntok << 8) | ((u32)mem << 11);
+}
+
+__device__ __forceinline__ u32 window32(u64 a, u64 b, int d) // 32 stream bits from offset d (0..63) of the pair
+{
+	const u32 lo = d < 32 ? (u32)a : (u32)(a >> 32);
+	const u32 hi = d < 32 ? (u32)(a >> 32) : (u32)b;
+	return __funnelshift_r(lo, hi, d & 31);
+}
+
+__device__ __forceinline__ u32 slice_exit_lut(const u32 *lut, u64 a, u64 b, int avail, u32 entry)
+{
+	if (entry == PDEAD)
+		return PDEAD;
+	int d = (int)(entry & 63u), k = (int)(entry >> 6);
+	const bool lut_ok = avail >= 64 + LUT_BITS + 4; // every window looked up lies inside the stream
+	do {
+		const u32 bits = window32(a, b, d);
+		if (k == 0 && lut_ok) {
+			const u32 t = lut[bits & ((1u << LUT_BITS) - 1u)];
+			if ((t & 15u) && d + (int)((t >> 4) & 15u) < 64) { // every token of the entry starts in this slice
+				d += (int)(t & 15u);
+				continue;
+			}
+		}
+		const int u = bits ? __ffs((int)bits) - 1 : 32;
+		const int e = k + u;
+		const int L = u + 1 + e;
+		if (e > 31 || d + L > avail)
+			return PDEAD;
+		k = e >= 2 ? e - 2 : 0;
+		d += L + 1;
+	} while (d < 64);
+	return (u32)(d - 64) | ((u32)k << 6);
+}
+
+__device__ __forceinline__ u32 slice_walk_lut(const u32 *lut, u64 a, u64 b, int avail, u32 entry, u64 &mem, u32 &ntok)
+{
+	mem = 0;
+	ntok = 0;
+	if (entry == PDEAD)
+		return PDEAD;
+	int d = (int)(entry & 63u), k = (int)(entry >> 6);
+	u32 msum = 0;
+	const bool lut_ok = avail >= 64 + LUT_BITS + 4;
+	do {
+		const u32 bits = window32(a, b, d);
+		if (k == 0 && lut_ok) {
+			const u32 t = lut[bits & ((1u << LUT_BITS) - 1u)];
+			if ((t & 15u) && d + (int)((t >> 4) & 15u) < 64) {
+				d += (int)(t & 15u);
+				ntok += (t >> 8) & 7u;
+				msum += t >> 11;
+				continue;
+			}
+		}
+		const int u = bits ? __ffs((int)bits) - 1 : 32;
+		const int e = k + u;
+		const int L = u + 1 + e;
+		if (e > 31 || d + L > avail) {
+			mem += msum;
+			return PDEAD;
+		}
+		const u64 w = bits_from(a, b, d);
+		const u32 payload = (u32)(w >> (u + 1)) & ((1u << e) - 1u);
+		mem += (u64)((1u << e) - (1u << k)) + payload + 1ull;
+		++ntok;
+		k = e >= 2 ? e - 2 : 0;
+		d += L + 1;
+	} while (d < 64);
+	mem += msum;
+	return (u32)(d - 64) | ((u32)k << 6);
+}
+
 // ---------------------------------------------------------------------------------------------- scan
 
-__global__ void __launch_bounds__(WS) dec_scan_kernel(const u32 *__restrict__ stream, u64 end_bits, u32 *E, ulonglong2 *P,
-                                                       u32 *TK, u32 *winX, ulonglong2 *winPT, u32 *winTT)
+__global__ void __launch_bounds__(WS) dec_scan_kernel(const u32 *__restrict__ stream, u64 end_bits,
+                                                       const u32 *__restrict__ toklut, u32 *E, ulonglong2 *P, u32 *TK,
+                                                       u32 *winX, ulonglong2 *winPT, u32 *winTT)
 {
+	__shared__ u32 lut[1 << LUT_BITS];
 	__shared__ u32 sx[WS];
 	__shared__ u32 wmap[WS / 32];
 	__shared__ u64 ws[32];
@@ -114,8 +211,11 @@ __global__ void __launch_bounds__(WS) dec_scan_kernel(const u32 *__restrict__ st
 	u64 a, b;
 	load_slice(stream, end_bits, gs, a, b);
 	const int avail = clamp_avail(end_bits, gs << 6);
+	for (int i = tid; i < (1 << LUT_BITS); i += WS)
+		lut[i] = __ldg(toklut + i);
+	__syncthreads();
 	// exits for a first token at offset 0 / 1 with order 0
-	const u32 xs0 = slice_exit(a, b, avail, 0u), xs1 = slice_exit(a, b, avail, 1u);
+	const u32 xs0 = slice_exit_lut(lut, a, b, avail, 0u), xs1 = slice_exit_lut(lut, a, b, avail, 1u);
 	// At order 0 every token has an even length, so a chain keeps the parity of its offsets.  Chain c enters the
 	// window at offset c; the parity class it enters every later slice with comes from a scan of 2-state maps.
 	u32 mymap = 0;
@@ -160,46 +260,70 @@ __global__ void __launch_bounds__(WS) dec_scan_kernel(const u32 *__restrict__ st
 	// exits of the predicted entries, with the members / tokens they consume (kept up to date while the entries change)
 	u64 m0, m1;
 	u32 t0, t1;
-	u32 x0 = slice_walk(a, b, avail, e0, m0, t0), x1 = x0;
+	u32 x0 = slice_walk_lut(lut, a, b, avail, e0, m0, t0), x1 = x0;
 	if (e1 == e0) {
 		m1 = m0;
 		t1 = t0;
 	} else {
-		x1 = slice_walk(a, b, avail, e1, m1, t1);
+		x1 = slice_walk_lut(lut, a, b, avail, e1, m1, t1);
 	}
+	// fixed point: entry <- the predecessor's exact exit.  A wrong prediction is repaired where the chains join
+	// again, a few slices further on, so the repairs are local: each warp iterates on its own 32 slices with
+	// shuffles (no block barrier) and only the warp-boundary states travel through shared memory.  Inside the loops
+	// only the exits are recomputed; the member / token counts of the slices whose entry changed follow afterwards.
+	__shared__ u32 sb[WS / 32];
+	bool dirty0 = false, dirty1 = false;
+	u32 bound = tid > 0 ? sx[tid - 1] : 0u; // what lane 0 of a warp takes as its predecessor's exits
 	__syncthreads();
-	// fixed point: entry <- the predecessor's exact exit.  Slice i is exact after i rounds at the latest; in
-	// practice a wrong prediction is repaired where the chains join again, a few slices further on.
 	for (;;) {
-		sx[tid] = x0 | (x1 << 16);
-		__syncthreads();
-		int changed = 0;
-		if (tid > 0) {
-			const u32 v = sx[tid - 1];
-			u32 n0 = v & 0xffffu, n1 = v >> 16;
-			if (n0 == PDEAD)
-				n0 = 0u;
-			if (n1 == PDEAD)
-				n1 = 1u;
-			if (n0 != e0) {
-				e0 = n0;
-				x0 = slice_walk(a, b, avail, e0, m0, t0);
-				changed = 1;
-			}
-			if (n1 != e1) {
-				e1 = n1;
-				if (e1 == e0) {
-					x1 = x0;
-					m1 = m0;
-					t1 = t0;
-				} else {
-					x1 = slice_walk(a, b, avail, e1, m1, t1);
+		for (;;) { // warp-local fixed point
+			u32 v = __shfl_up_sync(0xffffffffu, x0 | (x1 << 16), 1);
+			if (lane == 0)
+				v = bound;
+			int changed = 0;
+			if (tid > 0) {
+				u32 n0 = v & 0xffffu, n1 = v >> 16;
+				if (n0 == PDEAD)
+					n0 = 0u;
+				if (n1 == PDEAD)
+					n1 = 1u;
+				if (n0 != e0) {
+					e0 = n0;
+					x0 = slice_exit_lut(lut, a, b, avail, e0);
+					dirty0 = true;
+					changed = 1;
 				}
-				changed = 1;
+				if (n1 != e1) {
+					e1 = n1;
+					x1 = e1 == e0 ? x0 : slice_exit_lut(lut, a, b, avail, e1);
+					dirty1 = true;
+					changed = 1;
+				}
 			}
+			if (!__any_sync(0xffffffffu, changed))
+				break;
 		}
-		if (!__syncthreads_or(changed))
+		if (lane == 31)
+			sb[wid] = x0 | (x1 << 16);
+		__syncthreads();
+		int moved = 0;
+		if (lane == 0 && wid > 0) {
+			const u32 nb = sb[wid - 1];
+			moved = nb != bound;
+			bound = nb;
+		}
+		if (!__syncthreads_or(moved))
 			break;
+	}
+	if (dirty0)
+		slice_walk_lut(lut, a, b, avail, e0, m0, t0);
+	if (dirty1) {
+		if (e1 == e0) {
+			m1 = m0;
+			t1 = t0;
+		} else {
+			slice_walk_lut(lut, a, b, avail, e1, m1, t1);
+		}
 	}
 	if (x0 == PDEAD)
 		m0 += DEATH;
@@ -1039,9 +1163,15 @@ u64 dec_rank_bits(const Geom &g, const Sched &hs, int nchunks)
 	return bits;
 }
 
+void dec_token_table(u32 *host_table)
+{
+	for (u32 i = 0; i < (1u << LUT_BITS); ++i)
+		host_table[i] = toklut_entry(i);
+}
+
 int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b, int nchunks, cudaStream_t st, long long *launches)
 {
-	dec_scan_kernel<<<b.nwin, WS, 0, st>>>(b.stream, b.end_bits, b.E, b.P, b.TK, b.winX, b.winPT, b.winTT);
+	dec_scan_kernel<<<b.nwin, WS, 0, st>>>(b.stream, b.end_bits, b.toklut, b.E, b.P, b.TK, b.winX, b.winPT, b.winTT);
 	dec_link_kernel<<<(2 * b.nwin + 127) / 128, 128, 0, st>>>(b.stream, b.end_bits, b.nwin, b.E, b.P, b.TK, b.winX, b.winPT,
 	                                                           b.winTT, b.link);
 	dec_resolve_kernel<<<1, 32, 0, st>>>(g, nchunks, b);

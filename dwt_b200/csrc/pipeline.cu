@@ -118,7 +118,7 @@ extern "C" void dwt_ctx_destroy(dwt_ctx *c)
 	DevBuf *bufs[] = {&c->img, &c->pyr, &c->ll[0], &c->ll[1], &c->small, &c->bs, &c->sig, &c->ent, &c->Z,
 	                  &c->signbuf, &c->specbuf, &c->refbuf, &c->tiles, &c->thr_state, &c->chunks, &c->info,
 	                  &c->dsched, &c->out, &c->stream, &c->mem_pref, &c->ref_pref, &c->ones_rank, &c->sign_rank,
-	                  &c->dstate, &c->win, &c->flush, &c->dec_scan, &c->dec_seg, &c->dec_chunks};
+	                  &c->dstate, &c->win, &c->flush, &c->dec_scan, &c->dec_seg, &c->dec_chunks, &c->dec_lut};
 	for (DevBuf *b : bufs)
 		b->release();
 	c->pin_small.release();

@@ -49,6 +49,8 @@ struct dwt_ctx {
 	DevBuf bs, sig, ent, Z, signbuf, specbuf, refbuf, tiles, thr_state, chunks, info, dsched, out, stream;
 	DevBuf mem_pref, ref_pref, ones_rank, sign_rank, dstate, win, flush;
 	DevBuf dec_scan, dec_seg, dec_chunks; // decoder: per-slice chain tables, segment and chunk records
+	DevBuf dec_lut;    // decoder: order-0 token table
+	bool dec_lut_ready = false;
 	int sm_count = 1;
 	PinBuf pin_small, pin_io, pin_stream;
 

@@ -216,6 +216,15 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		    c->dec_seg.ensure((nwin + (size_t)nchunks + 1) * sizeof(DecSeg)) ||
 		    c->dec_chunks.ensure((size_t)DWT_MAX_CHUNKS * sizeof(DecChunk)) || c->dsched.ensure(sizeof(Sched)))
 			return -1;
+		if (!c->dec_lut_ready) {
+			static u32 table[DWT_DEC_LUT_WORDS];
+			dec_token_table(table);
+			if (c->dec_lut.ensure(sizeof(table)))
+				return -1;
+			CUDA_OK(cudaMemcpyAsync(c->dec_lut.p, table, sizeof(table), cudaMemcpyHostToDevice, st));
+			CUDA_OK(cudaStreamSynchronize(st));
+			c->dec_lut_ready = true;
+		}
 		CUDA_OK(cudaMemsetAsync(c->bs.p, 0, bs_words * 4, st));
 		CUDA_OK(cudaMemsetAsync(c->sig.p, 0, sig_words * 4, st));
 		CUDA_OK(cudaMemsetAsync(c->ones_rank.p, 0, rank_words * 8, st));
@@ -226,6 +235,7 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		b.bs = c->bs.as<u32>();
 		b.sig = c->sig.as<u32>();
 		b.stream = c->stream.as<u32>();
+		b.toklut = c->dec_lut.as<u32>();
 		b.end_bits = end_bits;
 		b.nwin = (u32)nwin;
 		char *sp = c->dec_scan.as<char>();
