@@ -91,28 +91,59 @@ __global__ void __launch_bounds__(TG) enc_count_kernel(const __grid_constant__ G
 
 // ------------------------------------------------------------------------------------------------ scans
 
-__global__ void __launch_bounds__(1024) enc_scan_kernel(u32 *ez, u32 *e1, u32 *er, int n, EncInfo *info)
+// exclusive scan of the three count arrays in two passes over blocks of SCAN_TILE entries: block-local prefixes and
+// block totals first, then every block adds the totals of the blocks in front of it (a few dozen values)
+constexpr int SCAN_TILE = 4096;
+
+__global__ void __launch_bounds__(1024) enc_scan_local_kernel(u32 *ez, u32 *e1, u32 *er, int n, u64 *bsum)
 {
 	__shared__ u64 ws[32];
-	const int per = (n + 1023) / 1024;
-	const int b = threadIdx.x * per, e = min(b + per, n);
 	u32 *arr[3] = {ez, e1, er};
+	const int base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+	for (int a = 0; a < 3; ++a) {
+		u32 v[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			v[k] = base + k < n ? arr[a][base + k] : 0u;
+		u64 tot;
+		u32 run = (u32)block_exscan_u64((u64)v[0] + v[1] + v[2] + v[3], ws, &tot);
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			if (base + k < n)
+				arr[a][base + k] = run; // prefixes are used modulo 2^32 (runs are differences)
+			run += v[k];
+		}
+		if (threadIdx.x == 0)
+			bsum[a * gridDim.x + blockIdx.x] = tot;
+	}
+}
+
+__global__ void __launch_bounds__(1024) enc_scan_fix_kernel(u32 *ez, u32 *e1, u32 *er, int n, const u64 *bsum, EncInfo *info)
+{
+	__shared__ u64 ws[32];
+	u32 *arr[3] = {ez, e1, er};
+	const int nb = gridDim.x;
+	const int base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
 	u64 tots[3];
 	for (int a = 0; a < 3; ++a) {
-		u64 s = 0;
-		for (int k = b; k < e; ++k)
-			s += arr[a][k];
-		u64 tot;
-		u64 base = block_exscan_u64(s, ws, &tot);
-		u32 run = (u32)base; // prefixes are used modulo 2^32 (runs are differences)
-		for (int k = b; k < e; ++k) {
-			u32 v = arr[a][k];
-			arr[a][k] = run;
-			run += v;
+		u64 before = 0, all = 0;
+		for (int i = threadIdx.x; i < nb; i += 1024) {
+			const u64 v = bsum[a * nb + i];
+			all += v;
+			if (i < (int)blockIdx.x)
+				before += v;
 		}
-		tots[a] = tot;
+		u64 t0, t1;
+		block_exscan_u64(before, ws, &t0);
+		block_exscan_u64(all, ws, &t1);
+		tots[a] = t1;
+		const u32 add = (u32)t0;
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			if (base + k < n)
+				arr[a][base + k] += add;
 	}
-	if (threadIdx.x == 0) {
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		info->tot_zero = tots[0];
 		info->tot_one = tots[1];
 		info->tot_ref = tots[2];
@@ -521,7 +552,11 @@ int enc_scan_and_setup(const Geom &g, const Sched &hs, const EncBuffers &b, cuda
 {
 	(void)g;
 	(void)hs;
-	enc_scan_kernel<<<1, 1024, 0, st>>>(b.ent_z, b.ent_1, b.ent_r, b.nent, b.info);
+	const int nb = (b.nent + SCAN_TILE - 1) / SCAN_TILE;
+	u64 *bsum = reinterpret_cast<u64 *>((reinterpret_cast<uintptr_t>(b.ent_r + b.nent) + 15) & ~(uintptr_t)15); // room kept by the context
+	enc_scan_local_kernel<<<nb, 1024, 0, st>>>(b.ent_z, b.ent_1, b.ent_r, b.nent, bsum);
+	enc_scan_fix_kernel<<<nb, 1024, 0, st>>>(b.ent_z, b.ent_1, b.ent_r, b.nent, bsum, b.info);
+	++*launches;
 	enc_chunk_setup_kernel<<<1, 1024, 0, st>>>(b.sched, b.ent_z, b.ent_1, b.ent_r, b.chunks, b.info, b.Z, b.specbuf,
 	                                           b.max_tokens);
 	*launches += 2;

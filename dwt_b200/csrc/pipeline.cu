@@ -483,7 +483,8 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 			ref_bound += ndet * (planes[ch] > 1 ? planes[ch] - 1 : 0);
 		const size_t ref_words = (size_t)(ref_bound / 32) + 4;
 		const size_t bit_words = tok_room / 32 + 4;
-		if (c->ent.ensure((size_t)b.nent * 12 + 64) || c->Z.ensure(tok_room * 4 + 64) ||
+		if (c->ent.ensure((size_t)b.nent * 12 + 64 + (size_t)(b.nent / 4096 + 2) * 24) || // + block totals of the scan
+		    c->Z.ensure(tok_room * 4 + 64) ||
 		    c->signbuf.ensure(bit_words * 4) || c->specbuf.ensure(bit_words * 4) || c->refbuf.ensure(ref_words * 4) ||
 		    c->tiles.ensure(ntile_max * (4 * 4 + 8) + 256) || c->thr_state.ensure(ntile_max * 256) ||
 		    c->chunks.ensure(sizeof(EncChunks)) || c->info.ensure(sizeof(EncInfo)))
