@@ -1093,16 +1093,21 @@ __global__ void __launch_bounds__(1024) dec_tilescan_kernel(const __grid_constan
 	}
 }
 
+// also leaves the tile counts of the NEXT depth (members / refinement positions after this plane) in tile_sums,
+// so that dec_prep_kernel only runs for the top plane
 __global__ void __launch_bounds__(TG) dec_deposit_kernel(const __grid_constant__ Geom G, const __grid_constant__ DecBuffers B,
                                                           int nchunks, int depth)
 {
 	__shared__ u64 ws[32];
+	__shared__ u32 acc[2];
 	const int c = blockIdx.y, tile = blockIdx.x;
 	const int l = level_of_tile(G, tile);
 	int p;
 	const int j = chunk_at(B.sched, B.chunks, nchunks, c, l, depth, &p);
 	if (j < 0)
 		return;
+	if (threadIdx.x < 2)
+		acc[threadIdx.x] = 0;
 	const DecChunk ck = B.chunks[j];
 	const Sched *S = B.sched;
 	const int g = (tile - G.tbase[l]) * TG + threadIdx.x;
@@ -1113,44 +1118,55 @@ __global__ void __launch_bounds__(TG) dec_deposit_kernel(const __grid_constant__
 	const u32 member = vm & ~s;
 	const u32 nm = __popc(member), nr = __popc(s);
 	u64 tot;
-	const u64 ex = block_exscan_u64((u64)nm | ((u64)nr << 32), ws, &tot);
-	if (!vm)
-		return;
-	const u32 *tb = B.tile_base + 2 * ((size_t)c * G.tbase[G.levels] + tile);
-	u32 *plane_words = B.bs + S->bsbase[c] + (long long)p * G.GT;
-	u32 *sign_words = B.bs + S->bsbase[c] + (long long)S->planes[c] * G.GT;
+	const u64 ex = block_exscan_u64((u64)nm | ((u64)nr << 32), ws, &tot); // syncs: acc is initialised behind it
+	const size_t ti = 2 * ((size_t)c * G.tbase[G.levels] + tile);
 	u32 Bw = 0;
-	if (nm) {
-		const u64 off = ck.rank_base + tb[0] + (u32)ex;
-		u32 ob = bits_get32(B.ones_rank, off);
-		if (nm < 32)
-			ob &= (1u << nm) - 1u;
-		if (ob) {
-			Bw = bit_expand(ob, member);
-			const u32 sb = bits_get32(B.sign_rank, off) & ob;
-			if (sb)
-				sign_words[gi] |= bit_expand(sb, member);
+	if (vm) {
+		const u32 *tb = B.tile_base + ti;
+		u32 *plane_words = B.bs + S->bsbase[c] + (long long)p * G.GT;
+		u32 *sign_words = B.bs + S->bsbase[c] + (long long)S->planes[c] * G.GT;
+		if (nm) {
+			const u64 off = ck.rank_base + tb[0] + (u32)ex;
+			u32 ob = bits_get32(B.ones_rank, off);
+			if (nm < 32)
+				ob &= (1u << nm) - 1u;
+			if (ob) {
+				Bw = bit_expand(ob, member);
+				const u32 sb = bits_get32(B.sign_rank, off) & ob;
+				if (sb)
+					sign_words[gi] |= bit_expand(sb, member);
+			}
 		}
-	}
-	if (nr && ck.ref_valid) {
-		const u64 pos = ck.ref_bitpos + tb[1] + (u32)(ex >> 32);
-		const u64 end = B.end_bits;
-		if (pos < end) {
-			const u64 w = pos >> 5;
-			const int sh = (int)(pos & 31);
-			u32 rb = __funnelshift_r(__ldg(B.stream + w), __ldg(B.stream + w + 1), sh);
-			const u64 avail = end - pos;
-			u32 take = nr;
-			if (avail < take)
-				take = (u32)avail;
-			if (take < 32)
-				rb &= (1u << take) - 1u;
-			Bw |= bit_expand(rb, s);
+		if (nr && ck.ref_valid) {
+			const u64 pos = ck.ref_bitpos + tb[1] + (u32)(ex >> 32);
+			const u64 end = B.end_bits;
+			if (pos < end) {
+				const u64 w = pos >> 5;
+				const int sh = (int)(pos & 31);
+				u32 rb = __funnelshift_r(__ldg(B.stream + w), __ldg(B.stream + w + 1), sh);
+				const u64 avail = end - pos;
+				u32 take = nr;
+				if (avail < take)
+					take = (u32)avail;
+				if (take < 32)
+					rb &= (1u << take) - 1u;
+				Bw |= bit_expand(rb, s);
+			}
 		}
+		plane_words[gi] = Bw;
+		if (Bw)
+			sig[gi] = s | Bw;
 	}
-	plane_words[gi] = Bw;
-	if (Bw)
-		sig[gi] = s | Bw;
+	const u32 ns = s | Bw;
+	const u32 m2 = __reduce_add_sync(0xffffffffu, (u32)__popc(vm & ~ns));
+	const u32 r2 = __reduce_add_sync(0xffffffffu, (u32)__popc(ns));
+	if ((threadIdx.x & 31) == 0) {
+		atomicAdd(&acc[0], m2);
+		atomicAdd(&acc[1], r2);
+	}
+	__syncthreads();
+	if (threadIdx.x < 2)
+		B.tile_sums[ti + threadIdx.x] = acc[threadIdx.x];
 }
 
 } // namespace
@@ -1183,11 +1199,14 @@ int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b, int nchunks, cu
 			depth_max = hs.planes[c];
 	const dim3 tiles((unsigned)g.tbase[g.levels], (unsigned)g.channels);
 	const dim3 lv((unsigned)g.levels, (unsigned)g.channels);
+	if (depth_max > 0) {
+		dec_prep_kernel<<<tiles, TG, 0, st>>>(g, b, nchunks, 0);
+		++*launches;
+	}
 	for (int depth = 0; depth < depth_max; ++depth) {
-		dec_prep_kernel<<<tiles, TG, 0, st>>>(g, b, nchunks, depth);
 		dec_tilescan_kernel<<<lv, 1024, 0, st>>>(g, b, nchunks, depth);
-		dec_deposit_kernel<<<tiles, TG, 0, st>>>(g, b, nchunks, depth);
-		*launches += 3;
+		dec_deposit_kernel<<<tiles, TG, 0, st>>>(g, b, nchunks, depth); // leaves the tile counts of depth + 1
+		*launches += 2;
 	}
 	CUDA_OK(cudaGetLastError());
 	return 0;
