@@ -477,6 +477,19 @@ __global__ void __launch_bounds__(256) enc_scatter_kernel(const u32 *__restrict_
 	if (t0 >= ntok)
 		return;
 	int j = chunk_of_index(C->tok_start, J, t0);
+	// the codes of a thread's tokens are contiguous in the stream (except across a chunk's refinement block): they are
+	// gathered in a 64-bit window and sent with one atomic per 32-bit word instead of one or two per token
+	u64 acc = 0, acc_pos = 0;
+	int acc_len = 0;
+	auto flush = [&]() {
+		if (acc_len > 0 && acc_pos < limit_bits) {
+			bits_or(out, acc_pos, (u32)acc, acc_len < 32 ? acc_len : 32);
+			if (acc_len > 32)
+				bits_or(out, acc_pos + 32, (u32)(acc >> 32), acc_len - 32);
+		}
+		acc = 0;
+		acc_len = 0;
+	};
 #pragma unroll
 	for (int i = 0; i < TPT; ++i) {
 		const u32 t = t0 + i;
@@ -498,11 +511,12 @@ __global__ void __launch_bounds__(256) enc_scatter_kernel(const u32 *__restrict_
 				++len;
 			}
 			const u64 pos = off + C->ref_start[j];
-			if (pos < limit_bits) {
-				bits_or(out, pos, (u32)code, len < 32 ? len : 32);
-				if (len > 32)
-					bits_or(out, pos + 32, (u32)(code >> 32), len - 32);
+			if (acc_len == 0 || pos != acc_pos + (u64)acc_len || acc_len + len > 64) {
+				flush();
+				acc_pos = pos;
 			}
+			acc |= code << acc_len;
+			acc_len += len;
 			k = vli_next(e);
 		}
 		off += len;
@@ -511,6 +525,7 @@ __global__ void __launch_bounds__(256) enc_scatter_kernel(const u32 *__restrict_
 		if (kind == 2u)
 			info->total_bits = off + C->ref_start[j];
 	}
+	flush();
 }
 
 __global__ void __launch_bounds__(256) enc_refcopy_kernel(const u32 *__restrict__ refbuf, const EncChunks *__restrict__ C,

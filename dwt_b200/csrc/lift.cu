@@ -25,6 +25,11 @@ __device__ __forceinline__ int clampi(int x, int a, int b)
 	return min(max(x, a), b);
 }
 
+__device__ __forceinline__ int clamp_u8(int x) // clamp to 0..255 in one instruction (VIMNMX with relu)
+{
+	return __vimin_s32_relu(x, 255);
+}
+
 template <int MODE>
 struct FwdTraits {
 	static constexpr int NC = MODE == 0 ? 3 : 1;
@@ -105,9 +110,14 @@ __device__ __forceinline__ void fwd_expand(const Raw<MODE> &r, int (&v)[FwdTrait
 	if constexpr (MODE == 0) {
 #pragma unroll
 		for (int k = 0; k < 4; ++k) {
-			const int R = (int)((r.w[(3 * k) >> 2] >> (8 * ((3 * k) & 3))) & 255u);
-			const int G = (int)((r.w[(3 * k + 1) >> 2] >> (8 * ((3 * k + 1) & 3))) & 255u);
-			const int B = (int)((r.w[(3 * k + 2) >> 2] >> (8 * ((3 * k + 2) & 3))) & 255u);
+			int R = (int)((r.w[(3 * k) >> 2] >> (8 * ((3 * k) & 3))) & 255u);
+			int G = (int)((r.w[(3 * k + 1) >> 2] >> (8 * ((3 * k + 1) & 3))) & 255u);
+			int B = (int)((r.w[(3 * k + 2) >> 2] >> (8 * ((3 * k + 2) & 3))) & 255u);
+			// hide the 8-bit range from the compiler: it would narrow the whole transform to 16-bit arithmetic,
+			// which costs a mask and a sign extension per operation on this machine
+			asm("" : "+r"(R));
+			asm("" : "+r"(G));
+			asm("" : "+r"(B));
 			const int U = R - B, T = B + U / 2, V = G - T;
 			v[0][k] = T + V / 2;
 			v[1][k] = U;
@@ -115,8 +125,11 @@ __device__ __forceinline__ void fwd_expand(const Raw<MODE> &r, int (&v)[FwdTrait
 		}
 	} else if constexpr (MODE == 1) {
 #pragma unroll
-		for (int k = 0; k < 4; ++k)
-			v[0][k] = (int)((r.w[0] >> (8 * k)) & 255u);
+		for (int k = 0; k < 4; ++k) {
+			int t = (int)((r.w[0] >> (8 * k)) & 255u);
+			asm("" : "+r"(t));
+			v[0][k] = t;
+		}
 	} else {
 #pragma unroll
 		for (int k = 0; k < 4; ++k)
@@ -373,7 +386,7 @@ __device__ __forceinline__ void inv_store_row(const LiftLevel &p, int ch, int y,
 		u32 w = 0;
 #pragma unroll
 		for (int k = 0; k < 4; ++k)
-			w |= (u32)clampi(v[0][k], 0, 255) << (8 * k);
+			w |= (u32)clamp_u8(v[0][k]) << (8 * k);
 		if (full && vec) {
 			*reinterpret_cast<u32 *>(row + x) = w;
 		} else {
@@ -388,9 +401,12 @@ __device__ __forceinline__ void inv_store_row(const LiftLevel &p, int ch, int y,
 #pragma unroll
 		for (int k = 0; k < 4; ++k) {
 			// image.h:41-50 then pnm.h:108
-			const int Y = clampi(v[0][k], 0, 255), U = clampi(v[1][k], -255, 255), V = clampi(v[2][k], -255, 255);
+			int Y = clamp_u8(v[0][k]), U = clampi(v[1][k], -255, 255), V = clampi(v[2][k], -255, 255);
+			asm("" : "+r"(Y)); // keep the compiler from narrowing the transform to 16-bit arithmetic (see fwd_expand)
+			asm("" : "+r"(U));
+			asm("" : "+r"(V));
 			const int T = Y - V / 2, G = V + T, B = T - U / 2, R = B + U;
-			const u32 px[3] = {(u32)clampi(R, 0, 255), (u32)clampi(G, 0, 255), (u32)clampi(B, 0, 255)};
+			const u32 px[3] = {(u32)clamp_u8(R), (u32)clamp_u8(G), (u32)clamp_u8(B)};
 #pragma unroll
 			for (int b = 0; b < 3; ++b) {
 				const int n = 3 * k + b;
