@@ -14,6 +14,8 @@
 //   of a warp is one contiguous row segment.
 #include "lift.cuh"
 
+#include <type_traits>
+
 namespace {
 
 constexpr int STRIP_OUT = 120; // output columns per warp: 30 lanes x 4 columns (one halo lane on each side)
@@ -54,10 +56,10 @@ __device__ __forceinline__ void store2(int *q, int a, int b, bool vec)
 // ------------------------------------------------------------------------------------------------ forward
 
 // columns x .. x+3 of row y (clamped to the image); `fast`: all four exist and the row is 4-byte / 16-byte aligned
-template <int MODE>
+template <int MODE, bool ROW_INSIDE = false>
 __device__ __forceinline__ void fwd_load(const LiftLevel &p, int ch, int y, int x, bool fast, Raw<MODE> &r)
 {
-	const int cy = clampi(y, 0, p.H - 1);
+	const int cy = ROW_INSIDE ? y : clampi(y, 0, p.H - 1);
 	if constexpr (MODE == 0) {
 		const uint8_t *row = (const uint8_t *)p.in + (size_t)cy * p.in_pitch * 3;
 		if (fast) {
@@ -223,19 +225,21 @@ __device__ __forceinline__ void fwd_body(const LiftLevel &p, const int RS, const
 	Raw<MODE> no, ne; // prefetched raw rows r+1, r+2
 	fwd_load<MODE>(p, ch, y0 + 1, x, fast, no);
 	fwd_load<MODE>(p, ch, y0 + 2, x, fast, ne);
-#pragma unroll 1
-	for (int r = y0; r < y1; r += 2) {
+	// one row pair.  STEADY (interior strips only): not the first pair, rows r+3 / r+4 exist and are prefetched --
+	// no clamp, no boundary rule, no branch in the body; this is what almost every iteration runs
+	auto step = [&](const int r, auto steady_tag) {
+		constexpr bool STEADY = decltype(steady_tag)::value;
 		int o[NC][4], f[NC][4];
 		fwd_expand<MODE>(no, o);
 		fwd_expand<MODE>(ne, f);
-		if (r + 2 < y1) {
-			fwd_load<MODE>(p, ch, r + 3, x, fast, no);
-			fwd_load<MODE>(p, ch, r + 4, x, fast, ne);
+		if (STEADY || r + 2 < y1) {
+			fwd_load<MODE, STEADY>(p, ch, r + 3, x, fast, no);
+			fwd_load<MODE, STEADY>(p, ch, r + 4, x, fast, ne);
 		}
 		fwd_hlift<NC>(o, hp);
 		fwd_hlift<NC>(f, hp);
-		const bool has_odd = r + 1 < H;
-		const bool v_int = r > 0 && r + 1 < H - 1; // neither the first row pair nor the last odd row
+		const bool has_odd = STEADY || r + 1 < H;
+		const bool v_int = STEADY || (r > 0 && r + 1 < H - 1); // neither the first row pair nor the last odd row
 		const size_t lo_row = (size_t)(r >> 1), hi_row = (size_t)(h2 + (r >> 1));
 #pragma unroll
 		for (int c = 0; c < NC; ++c) {
@@ -296,6 +300,13 @@ __device__ __forceinline__ void fwd_body(const LiftLevel &p, const int RS, const
 				dp[c][k] = D[k];
 			}
 		}
+	};
+#pragma unroll 1
+	for (int r = y0; r < y1; r += 2) {
+		if (HI && r > 0 && r + 2 < y1 && r + 4 < H)
+			step(r, std::true_type());
+		else
+			step(r, std::false_type());
 	}
 #pragma unroll
 	for (int c = 0; c < NC; ++c) {
@@ -324,7 +335,7 @@ __device__ __forceinline__ bool next_item(const LiftLevel &p, int nstrip, int ns
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 6) lift_fwd_kernel(const __grid_constant__ LiftLevel p, int RS,
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 5) lift_fwd_kernel(const __grid_constant__ LiftLevel p, int RS,
                                                                             int nstrip, int nseg, int planes)
 {
 	const int lane = threadIdx.x & 31;

@@ -258,8 +258,8 @@ int ctx_forward_transform(dwt_ctx *c, const int *planar_in)
 	const int L = g.levels;
 	if (ensure_transform_buffers(c))
 		return -1;
-	CUDA_OK(cudaMemsetAsync(c->small.p, 0, 16, c->st));
-	CUDA_OK(cudaMemsetAsync(c->small.as<int>() + 64, 0, 32 * sizeof(int), c->st)); // work counters of the level launches
+	// maxabs[4] at ints 0..3 and the work counters of the level launches at 64..95 (16..63 belong to the decoder)
+	CUDA_OK(cudaMemsetAsync(c->small.p, 0, 96 * sizeof(int), c->st));
 	int cur = 0;
 	for (int lv = L; lv >= 1; --lv) {
 		if (lv < L && lift_tail_fits(g.w[lv], g.h[lv])) {
