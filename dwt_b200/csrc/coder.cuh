@@ -103,7 +103,7 @@ struct DecBuffers {
 	u32 *bs;              // bit-sliced store being filled
 	u32 *sig;             // significance words [c][GT]
 	const u32 *stream;    // stream words (zero padded by >= 64 bytes)
-	const u32 *toklut;    // order-0 token table (DWT_DEC_LUT_WORDS words, dec_token_table)
+	const u32 *toklut;    // order-0 token table: 4096 length words, then 4096 ones/sign mask words (dec_token_table)
 	u64 end_bits;
 	u32 nwin;             // scan windows covering the stream
 	u32 *E;               // per slice: canonical entry states of the two classes (e0 | e1 << 16)
@@ -123,7 +123,7 @@ struct DecBuffers {
 
 // whole significance/refinement decode of `nchunks` chunks of the schedule into b.bs (zero-initialised by the caller)
 int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b, int nchunks, cudaStream_t st, long long *launches);
-#define DWT_DEC_LUT_WORDS 4096
+#define DWT_DEC_LUT_WORDS 8192
 void dec_token_table(u32 *host_table); // fills DWT_DEC_LUT_WORDS words
 // bits of rank space needed for the first nchunks chunks
 u64 dec_rank_bits(const Geom &g, const Sched &hs, int nchunks);

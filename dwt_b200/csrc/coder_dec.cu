@@ -30,6 +30,8 @@ namespace {
 constexpr int TG = DWT_TILE_GROUPS;
 constexpr int WS = DWT_DEC_WS;
 constexpr u32 PDEAD = 0xffffu;    // a chain that cannot continue (EOF inside a token, impossible order)
+constexpr int LINK_CAP = DWT_DEC_WS; // exact slice steps the link pass spends on one (window, chain): the whole window
+constexpr u32 LINK_OPEN = 0xfffeu;  // link record: the chain had not joined after LINK_CAP slices
 constexpr u64 DEATH = 1ull << 48; // member count charged to a slice in which a canonical chain dies: more than any chunk holds
 
 enum { EV_NONE = 0, EV_COVERED = 1, EV_PENDING = 2, EV_STOP = 3 };
@@ -123,6 +125,29 @@ __host__ __device__ inline u32 toklut_entry(u32 bits)
 		pos += 2 * u + 2;
 	}
 	return (u32)pos | ((u32)last << 4) | ((u32)ntok << 8) | ((u32)mem << 11);
+}
+
+// second word of the table: which of the entry's members are ones (bit i = member i, 16 bits) and, on the same
+// positions, the sign bits of those ones (16 bits)
+__host__ __device__ inline u32 toklut_masks(u32 bits)
+{
+	int pos = 0, mem = 0;
+	u32 ones = 0, signs = 0;
+	for (;;) {
+		int u = 0;
+		while (u < 3 && pos + u < LUT_BITS && !((bits >> (pos + u)) & 1u))
+			++u;
+		if (u >= 3 || pos + 2 * u + 2 > LUT_BITS)
+			break;
+		const u32 payload = (bits >> (pos + u + 1)) & ((1u << u) - 1u);
+		const int n = (1 << u) - 1 + (int)payload;
+		ones |= 1u << (mem + n);
+		if ((bits >> (pos + 2 * u + 1)) & 1u)
+			signs |= 1u << (mem + n);
+		mem += n + 1;
+		pos += 2 * u + 2;
+	}
+	return ones | (signs << 16);
 }
 
 __device__ __forceinline__ u32 window32(u64 a, u64 b, int d) // 32 stream bits from offset d (0..63) of the pair
@@ -371,9 +396,22 @@ __global__ void __launch_bounds__(128) dec_link_kernel(const u32 *__restrict__ s
 		u32 stok = 0;
 		int i = 0, qm = -1;
 		if (st != PDEAD) {
-			for (; i < WS; ++i) {
+			// true chains join within a few slices, but where both canonical chains have fallen onto one bit parity
+			// (dense planes without long runs) a chain of the other parity can run through the whole window: such
+			// a window is walked to its end here, in parallel, rather than by the resolver (LINK_CAP = window).
+			// A lower cap is honoured by the resolver (LINK_OPEN records are stepped exactly).
+			// the loads do not depend on the state: the next slice is fetched while this one is walked
+			u64 na, nb;
+			u32 ne = E[(u64)w * WS];
+			load_slice(stream, end_bits, (u64)w * WS, na, nb);
+			for (; i < LINK_CAP; ++i) {
 				const u64 gs = (u64)w * WS + i;
-				const u32 e = E[gs];
+				const u32 e = ne;
+				const u64 a = na, b = nb;
+				if (i + 1 < LINK_CAP) {
+					ne = E[gs + 1];
+					load_slice(stream, end_bits, gs + 1, na, nb);
+				}
 				if (st == (e & 0xffffu)) {
 					qm = 0;
 					break;
@@ -382,9 +420,8 @@ __global__ void __launch_bounds__(128) dec_link_kernel(const u32 *__restrict__ s
 					qm = 1;
 					break;
 				}
-				u64 a, b, mm;
+				u64 mm;
 				u32 tt;
-				load_slice(stream, end_bits, gs, a, b);
 				st = slice_walk(a, b, clamp_avail(end_bits, gs << 6), st, mm, tt);
 				smem += mm;
 				stok += tt;
@@ -408,7 +445,7 @@ __global__ void __launch_bounds__(128) dec_link_kernel(const u32 *__restrict__ s
 			L.mem = smem;
 			L.tok = stok;
 			L.qn = st == PDEAD ? 3 : 2;
-			L.exit_state = (unsigned short)st;
+			L.exit_state = (unsigned short)(st == PDEAD ? PDEAD : (i >= WS ? st : LINK_OPEN));
 		}
 	}
 	uint4 r0, r1;
@@ -683,8 +720,9 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 					const u32 excl = __shfl_up_sync(FULL, inc, 1);
 					// class the chain enters my window with
 					const u32 cls = q >= 2u ? q : (lane == 0 ? q : (excl >> (2 * q)) & 3u);
-					const bool canon = cls < 2u && valid;
 					const DecLink &my = cls == 1u ? L1 : L0;
+					const bool open = my.qn == 2u && my.exit_state == LINK_OPEN; // not joined within LINK_CAP: step it exactly
+					const bool canon = cls < 2u && valid;
 					const u64 mymem = canon ? my.mem : 0ull;
 					const u32 mytok = canon ? my.tok : 0u;
 					u64 incm = mymem;
@@ -699,7 +737,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 						}
 					}
 					const u64 pre = incm - mymem;
-					const bool reached = canon && cum + incm >= T;
+					const bool reached = canon && (open || cum + incm >= T);
 					const u32 bal = __ballot_sync(FULL, reached || !canon);
 					const int f = bal ? __ffs((int)bal) - 1 : 32;
 					const u32 my_entry = (xprev >> (16 * (cls & 1u))) & 0xffffu;
@@ -925,11 +963,44 @@ __device__ __forceinline__ void acc_flush(RankAcc &A, u32 *ones_rank, u32 *sign_
 	A.ones = A.signs = 0;
 }
 
-// ones and signs of the tokens that start in one slice; false when the chain ends here
-__device__ __forceinline__ bool emit_slice(u64 a, u64 b, int avail, u64 T, u64 base, int &d, int &k, u64 &cum, RankAcc &A,
-                                           u32 *ones_rank, u32 *sign_rank)
+// OR a 16-bit member mask (ones / signs) into rank space at rank rk
+__device__ __forceinline__ void acc_mask(RankAcc &A, u64 rk, u32 ones, u32 signs, u32 *ones_rank, u32 *sign_rank)
 {
+	const u64 w = rk >> 5;
+	const int sh = (int)(rk & 31);
+	if (w != A.word) {
+		acc_flush(A, ones_rank, sign_rank);
+		A.word = w;
+	}
+	A.ones |= ones << sh;
+	A.signs |= signs << sh;
+	if (sh > 16 && (ones >> (32 - sh))) { // the mask runs over into the next word
+		acc_flush(A, ones_rank, sign_rank);
+		A.word = w + 1;
+		A.ones = ones >> (32 - sh);
+		A.signs = signs >> (32 - sh);
+	}
+}
+
+// ones and signs of the tokens that start in one slice; false when the chain ends here.
+// lut: the order-0 token table (both words) or nullptr
+__device__ __forceinline__ bool emit_slice(const u32 *lut, u64 a, u64 b, int avail, u64 T, u64 base, int &d, int &k, u64 &cum,
+                                           RankAcc &A, u32 *ones_rank, u32 *sign_rank)
+{
+	const bool lut_ok = lut != nullptr && avail >= 64 + LUT_BITS + 4;
 	while (d < 64) {
+		if (k == 0 && lut_ok) {
+			const u32 idx = window32(a, b, d) & ((1u << LUT_BITS) - 1u);
+			const u32 t = lut[idx];
+			const u32 mem = t >> 11;
+			if ((t & 15u) && d + (int)((t >> 4) & 15u) < 64 && cum + mem <= T) { // all of them ones of this chunk
+				const u32 mk = lut[(1 << LUT_BITS) + idx];
+				acc_mask(A, base + cum, mk & 0xffffu, mk >> 16, ones_rank, sign_rank);
+				cum += mem;
+				d += (int)(t & 15u);
+				continue;
+			}
+		}
 		const u64 w = bits_from(a, b, d);
 		const u32 lo = (u32)w;
 		const int u = lo ? __ffs((int)lo) - 1 : 32;
@@ -961,44 +1032,48 @@ __device__ __forceinline__ bool emit_slice(u64 a, u64 b, int avail, u64 T, u64 b
 
 __global__ void __launch_bounds__(WS) dec_emit_kernel(const __grid_constant__ DecBuffers B)
 {
-	if (blockIdx.x >= B.state->nseg)
-		return;
-	const DecSeg s = B.seg[blockIdx.x];
-	const DecChunk ck = B.chunks[s.j];
+	// (a table-driven walk like the scan's was measured here and lost: staging 32 KB per CTA and the divergence between
+	// table and generic steps cost more than the per-token work they save; emit_slice still takes a table pointer)
+	const u32 *lut = nullptr;
+	const u32 nseg = B.state->nseg;
 	const int i = threadIdx.x;
-	const int m = s.m;
-	const u64 T = ck.T;
-	const u64 base = ck.rank_base + ck.r0;
-	const u64 wbase = (u64)s.w * WS;
-	if (i == s.i0 && m > i) {
-		// exact steps through the slices in front of the join
-		int d = (int)(s.state & 63u), k = (int)(s.state >> 6);
-		u64 cum = s.cum0;
-		RankAcc A = {~0ull, 0u, 0u};
-		for (int ii = i; ii < m; ++ii) {
+	for (u32 sidx = blockIdx.x; sidx < nseg; sidx += gridDim.x) {
+		const DecSeg s = B.seg[sidx];
+		const DecChunk ck = B.chunks[s.j];
+		const int m = s.m;
+		const u64 T = ck.T;
+		const u64 base = ck.rank_base + ck.r0;
+		const u64 wbase = (u64)s.w * WS;
+		if (i == s.i0 && m > i) {
+			// exact steps through the slices in front of the join
+			int d = (int)(s.state & 63u), k = (int)(s.state >> 6);
+			u64 cum = s.cum0;
+			RankAcc A = {~0ull, 0u, 0u};
+			for (int ii = i; ii < m; ++ii) {
+				u64 a, b;
+				const u64 gs = wbase + ii;
+				load_slice(B.stream, B.end_bits, gs, a, b);
+				if (!emit_slice(lut, a, b, clamp_avail(B.end_bits, gs << 6), T, base, d, k, cum, A, B.ones_rank, B.sign_rank))
+					break;
+				d -= 64;
+			}
+			acc_flush(A, B.ones_rank, B.sign_rank);
+		} else if (i >= m) {
+			const u64 gs = wbase + i;
+			const u32 e = (B.E[gs] >> (16 * s.qm)) & 0xffffu;
+			if (e == PDEAD)
+				continue;
+			const ulonglong2 pi = B.P[gs], pm = B.P[wbase + m];
+			u64 cum = (u64)s.cum_m + (s.qm ? pi.y - pm.y : pi.x - pm.x);
+			if (cum >= T)
+				continue;
 			u64 a, b;
-			const u64 gs = wbase + ii;
 			load_slice(B.stream, B.end_bits, gs, a, b);
-			if (!emit_slice(a, b, clamp_avail(B.end_bits, gs << 6), T, base, d, k, cum, A, B.ones_rank, B.sign_rank))
-				break;
-			d -= 64;
+			int d = (int)(e & 63u), k = (int)(e >> 6);
+			RankAcc A = {~0ull, 0u, 0u};
+			emit_slice(lut, a, b, clamp_avail(B.end_bits, gs << 6), T, base, d, k, cum, A, B.ones_rank, B.sign_rank);
+			acc_flush(A, B.ones_rank, B.sign_rank);
 		}
-		acc_flush(A, B.ones_rank, B.sign_rank);
-	} else if (i >= m) {
-		const u64 gs = wbase + i;
-		const u32 e = (B.E[gs] >> (16 * s.qm)) & 0xffffu;
-		if (e == PDEAD)
-			return;
-		const ulonglong2 pi = B.P[gs], pm = B.P[wbase + m];
-		u64 cum = (u64)s.cum_m + (s.qm ? pi.y - pm.y : pi.x - pm.x);
-		if (cum >= T)
-			return;
-		u64 a, b;
-		load_slice(B.stream, B.end_bits, gs, a, b);
-		int d = (int)(e & 63u), k = (int)(e >> 6);
-		RankAcc A = {~0ull, 0u, 0u};
-		emit_slice(a, b, clamp_avail(B.end_bits, gs << 6), T, base, d, k, cum, A, B.ones_rank, B.sign_rank);
-		acc_flush(A, B.ones_rank, B.sign_rank);
 	}
 }
 
@@ -1181,8 +1256,10 @@ u64 dec_rank_bits(const Geom &g, const Sched &hs, int nchunks)
 
 void dec_token_table(u32 *host_table)
 {
-	for (u32 i = 0; i < (1u << LUT_BITS); ++i)
+	for (u32 i = 0; i < (1u << LUT_BITS); ++i) {
 		host_table[i] = toklut_entry(i);
+		host_table[(1u << LUT_BITS) + i] = toklut_masks(i);
+	}
 }
 
 int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b, int nchunks, cudaStream_t st, long long *launches)
@@ -1191,7 +1268,18 @@ int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b, int nchunks, cu
 	dec_link_kernel<<<(2 * b.nwin + 127) / 128, 128, 0, st>>>(b.stream, b.end_bits, b.nwin, b.E, b.P, b.TK, b.winX, b.winPT,
 	                                                           b.winTT, b.link);
 	dec_resolve_kernel<<<1, 32, 0, st>>>(g, nchunks, b);
-	dec_emit_kernel<<<b.nwin + (u32)nchunks, WS, 0, st>>>(b);
+	{
+		static int sms = 0;
+		if (!sms) {
+			int dev = 0;
+			cudaGetDevice(&dev);
+			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+			if (sms <= 0)
+				sms = 1;
+		}
+		const u32 want = b.nwin + (u32)nchunks, cap = (u32)sms * 64u;
+		dec_emit_kernel<<<want < cap ? want : cap, WS, 0, st>>>(b);
+	}
 	*launches += 4;
 	int depth_max = 0;
 	for (int c = 0; c < g.channels; ++c)

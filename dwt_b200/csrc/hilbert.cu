@@ -89,16 +89,25 @@ __device__ __forceinline__ void cell_xy(const unsigned short *lut, int dloc, u32
 	y = ly;
 }
 
-// ---- cells whose 1024 positions are all valid: one warp per cell, no shared staging.  The warp walks the cell's
-// groups of 32 ranks; lane i of iteration k holds the coefficient of rank 32 (g0 + k) + i, a ballot per bit-plane
-// gives the group's words, lane k keeps them, and at the end every plane row is written as one contiguous run.
+// ---- cells whose 1024 positions are all valid: one warp per cell.  The warp walks the cell's groups of 32 ranks;
+// lane i of iteration k holds the coefficient of rank 32 (g0 + k) + i of all channels, a ballot per bit-plane gives the
+// group's word, lane 0 parks it in the warp's shared-memory tile [plane][group], and at the end every plane row
+// leaves as one contiguous 128-byte run.
+constexpr int LIN_ROWS = 3 * (PMAX + 1); // plane rows of the three channels
+
+// NP = largest plane count of the channels: the ballots of planes 0 .. NP-1 are unrolled with immediate masks and
+// offsets for every channel (a channel with fewer planes parks zero words that are never flushed); signs use row PMAX
+template <int NP>
 __global__ void __launch_bounds__(256) linearize_full_kernel(const __grid_constant__ HParams P, const u32 *__restrict__ list,
                                                               int nlist, const int *__restrict__ pyr, long long chan_stride,
                                                               int pitch, u32 *bs)
 {
 	__shared__ unsigned short lut[1024];
+	__shared__ u32 tile[8][LIN_ROWS][32];
 	build_lut(lut);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	u32(*my)[32] = tile[wid];
+	const int C = P.channels;
 	for (int item = blockIdx.x * 8 + wid; item < nlist; item += gridDim.x * 8) {
 		const u32 ent = list[item];
 		const HLevel &L = P.lv[ent >> 28];
@@ -109,82 +118,99 @@ __global__ void __launch_bounds__(256) linearize_full_kernel(const __grid_consta
 		const u32 g0 = R0 >> 5;
 		const int s = (int)(R0 & 31u);
 		const int *base = pyr + (size_t)oy * pitch + ox;
-		for (int c = 0; c < P.channels; ++c) {
-			const int planes = P.lay.planes[c];
-			const int *src = base + (size_t)c * chan_stride;
-			u32 *dst = bs + P.lay.bsbase[c] + L.gbase + g0;
-			u32 keep[PMAX + 1];
+		const int niter = s ? 33 : 32; // the 33rd group holds the cell's last s positions
+		__syncwarp();
+		for (int k = 0; k < niter; ++k) {
+			const int dloc = 32 * k + lane - s;
+			u32 v[3] = {0u, 0u, 0u};
+			if (dloc >= 0 && dloc < 1024) {
+				int x, y;
+				cell_xy(lut, dloc, orient, x, y);
+				const int *src = base + (size_t)y * pitch + x;
 #pragma unroll
-			for (int p = 0; p <= PMAX; ++p)
-				keep[p] = 0;
-#pragma unroll 4
-			for (int k = 0; k < 32; ++k) {
-				const int dloc = 32 * k + lane - s;
-				u32 v = 0;
-				if (dloc >= 0) {
-					int x, y;
-					cell_xy(lut, dloc, orient, x, y);
-					const int t = __ldg(src + (size_t)y * pitch + x);
-					v = (t < 0 ? 0x80000000u : 0u) | (u32)abs(t); // encode.c:124-128
-				}
-				const bool mine = lane == k;
-#pragma unroll
-				for (int p = 0; p < PMAX; ++p) {
-					if (p < planes) {
-						const u32 w = __ballot_sync(0xffffffffu, (v >> p) & 1u);
-						if (mine)
-							keep[p] = w;
+				for (int c = 0; c < 3; ++c) {
+					if (c < C) {
+						const int t = __ldg(src + (size_t)c * chan_stride);
+						v[c] = (t < 0 ? 0x80000000u : 0u) | (u32)abs(t); // encode.c:124-128
 					}
 				}
-				const u32 w = __ballot_sync(0xffffffffu, v >> 31);
-				if (mine)
-					keep[PMAX] = w;
 			}
-			// group g0 + lane: whole unless it is the first one of a cell that does not start on a group boundary
-			const bool whole = lane > 0 || s == 0;
+			const int col = k & 31; // group 32 reuses column 0 after the first 32 columns are flushed
+			if (k == 32) {
+				// flush the 32 whole-or-first groups before the tail group overwrites column 0
+				__syncwarp();
+				for (int c = 0; c < C; ++c) {
+					const int planes = P.lay.planes[c];
+					u32 *dst = bs + P.lay.bsbase[c] + L.gbase + g0 + lane;
+					for (int p = 0; p <= planes; ++p) {
+						const u32 w = my[c * (PMAX + 1) + (p == planes ? PMAX : p)][lane];
+						u32 *d = dst + (long long)p * P.GT;
+						if (lane > 0)
+							*d = w; // whole group
+						else if (w)
+							atomicOr(d, w); // first group of a cell that does not start on a group boundary
+					}
+				}
+				__syncwarp();
+			}
 #pragma unroll
-			for (int p = 0; p <= PMAX; ++p) {
-				if (p < planes || p == PMAX) {
-					u32 *d = dst + (long long)(p == PMAX ? planes : p) * P.GT + lane;
-					if (whole)
-						*d = keep[p];
-					else if (keep[p])
-						atomicOr(d, keep[p]);
+			for (int c = 0; c < 3; ++c) {
+				if (c < C) {
+					u32(*rows)[32] = my + c * (PMAX + 1);
+#pragma unroll
+					for (int p = 0; p < NP; ++p) {
+						const u32 w = __ballot_sync(0xffffffffu, v[c] & (1u << p));
+						if (lane == 0)
+							rows[p][col] = w;
+					}
+					const u32 w = __ballot_sync(0xffffffffu, v[c] >> 31);
+					if (lane == 0)
+						rows[PMAX][col] = w; // sign row
 				}
 			}
-			if (s) { // the 33rd group holds the cell's last s positions
-				const int dloc = 1024 + lane - s;
-				u32 v = 0;
-				if (lane < s) {
-					int x, y;
-					cell_xy(lut, dloc, orient, x, y);
-					const int t = __ldg(src + (size_t)y * pitch + x);
-					v = (t < 0 ? 0x80000000u : 0u) | (u32)abs(t);
+		}
+		__syncwarp();
+		if (s == 0) {
+			for (int c = 0; c < C; ++c) {
+				const int planes = P.lay.planes[c];
+				u32 *dst = bs + P.lay.bsbase[c] + L.gbase + g0 + lane;
+				for (int p = 0; p <= planes; ++p)
+					dst[(long long)p * P.GT] = my[c * (PMAX + 1) + (p == planes ? PMAX : p)][lane];
+			}
+		} else if (lane == 0) {
+			// tail group (column 0 now): shared with the next cell on the curve
+			for (int c = 0; c < C; ++c) {
+				const int planes = P.lay.planes[c];
+				u32 *dst = bs + P.lay.bsbase[c] + L.gbase + g0 + 32;
+				for (int p = 0; p <= planes; ++p) {
+					const u32 w = my[c * (PMAX + 1) + (p == planes ? PMAX : p)][0];
+					if (w)
+						atomicOr(dst + (long long)p * P.GT, w);
 				}
-				u32 mine = 0;
-				for (int p = 0; p < planes; ++p) {
-					const u32 w = __ballot_sync(0xffffffffu, (v >> p) & 1u);
-					if (lane == p)
-						mine = w;
-				}
-				const u32 sb = __ballot_sync(0xffffffffu, v >> 31);
-				if (lane == planes)
-					mine = sb;
-				if (lane <= planes && mine)
-					atomicOr(dst + (long long)lane * P.GT + 32, mine);
 			}
 		}
 	}
 }
 
+// inverse: the plane rows of the cell's 33 groups are staged in the warp's shared-memory tile (128-byte loads), then
+// lane i of iteration k assembles the coefficient of rank 32 (g0 + k) + i: per plane one broadcast read, one rotate
+// that brings bit i to bit p, one merge
+template <int NP> // NP = largest plane count of the channels (rows a channel does not have are staged as zero)
 __global__ void __launch_bounds__(256) reconstruct_full_kernel(const __grid_constant__ HParams P,
                                                                 const u32 *__restrict__ list, int nlist,
                                                                 const u32 *__restrict__ bs, const int *__restrict__ missing,
                                                                 int levels_used, int *pyr, long long chan_stride, int pitch)
 {
 	__shared__ unsigned short lut[1024];
+	__shared__ u32 tile[8][LIN_ROWS][33];
 	build_lut(lut);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	u32(*my)[33] = tile[wid];
+	const int C = P.channels;
+	int rot[NP]; // rotate right by rot[p]: bit `lane` lands on bit p
+#pragma unroll
+	for (int p = 0; p < NP; ++p)
+		rot[p] = (lane - p) & 31;
 	for (int item = blockIdx.x * 8 + wid; item < nlist; item += gridDim.x * 8) {
 		const u32 ent = list[item];
 		const int level = (int)(ent >> 28);
@@ -198,43 +224,45 @@ __global__ void __launch_bounds__(256) reconstruct_full_kernel(const __grid_cons
 		const u32 g0 = R0 >> 5;
 		const int s = (int)(R0 & 31u);
 		int *base = pyr + (size_t)oy * pitch + ox;
-		for (int c = 0; c < P.channels; ++c) {
+		int bias[3];
+		__syncwarp();
+		for (int c = 0; c < C; ++c) {
 			const int planes = P.lay.planes[c];
-			int *dstp = base + (size_t)c * chan_stride;
 			const u32 *src = bs + P.lay.bsbase[c] + L.gbase + g0;
-			const int m = missing[c * 16 + level] - 2; // decode.c:51-58
-			const int bias = m >= 0 ? 1 << m : 0;
-			u32 keep[PMAX + 1], last[PMAX + 1];
-#pragma unroll
-			for (int p = 0; p <= PMAX; ++p) {
-				keep[p] = 0;
-				last[p] = 0;
-				if (p < planes || p == PMAX) {
-					const u32 *r = src + (long long)(p == PMAX ? planes : p) * P.GT;
-					keep[p] = __ldg(r + lane);
-					if (s)
-						last[p] = __ldg(r + 32);
-				}
+			for (int p = 0; p <= NP; ++p) { // p == NP stands for the sign row
+				const int row = c * (PMAX + 1) + (p == NP ? PMAX : p);
+				const bool have = p == NP || p < planes;
+				const u32 *r = src + (long long)(p == NP ? planes : p) * P.GT;
+				my[row][lane] = have ? __ldg(r + lane) : 0u;
+				if (s && lane == 0)
+					my[row][32] = have ? __ldg(r + 32) : 0u;
 			}
-			const int iters = s ? 33 : 32;
-			for (int k = 0; k < iters; ++k) {
-				const int dloc = 32 * k + lane - s;
-				int mag = 0;
+			const int m = missing[c * 16 + level] - 2; // decode.c:51-58
+			bias[c] = m >= 0 ? 1 << m : 0;
+		}
+		__syncwarp();
+		const int niter = s ? 33 : 32;
+		for (int k = 0; k < niter; ++k) {
+			const int dloc = 32 * k + lane - s;
+			const bool act = dloc >= 0 && dloc < 1024;
+			int x = 0, y = 0;
+			if (act)
+				cell_xy(lut, dloc, orient, x, y);
+			int *dstp = base + (size_t)y * pitch + x;
 #pragma unroll
-				for (int p = 0; p < PMAX; ++p) {
-					if (p < planes) {
-						const u32 w = k < 32 ? __shfl_sync(0xffffffffu, keep[p], k) : last[p];
-						mag |= (int)((w >> lane) & 1u) << p;
-					}
-				}
-				const u32 sw = k < 32 ? __shfl_sync(0xffffffffu, keep[PMAX], k) : last[PMAX];
-				if (dloc >= 0 && dloc < 1024) {
-					int v = (sw >> lane) & 1u ? -mag : mag;
+			for (int c = 0; c < 3; ++c) {
+				if (c < C) {
+					const u32(*rows)[33] = my + c * (PMAX + 1);
+					u32 mag = 0;
+#pragma unroll
+					for (int p = 0; p < NP; ++p)
+						mag |= __funnelshift_r(rows[p][k], rows[p][k], rot[p]) & (1u << p);
+					const u32 neg = (rows[PMAX][k] >> lane) & 1u;
+					int v = neg ? -(int)mag : (int)mag;
 					if (v != 0)
-						v += v < 0 ? -bias : bias;
-					int x, y;
-					cell_xy(lut, dloc, orient, x, y);
-					dstp[(size_t)y * pitch + x] = v;
+						v += v < 0 ? -bias[c] : bias[c];
+					if (act)
+						dstp[(size_t)c * chan_stride] = v;
 				}
 			}
 		}
@@ -545,7 +573,20 @@ int hilbert_linearize(const Geom &g, const HilbertPlan &plan, const Sched &s, co
 	// lists are ordered by level: the first levels_used levels are a prefix
 	const int nfull = plan.full_off[levels_used], npart = plan.part_off[levels_used];
 	if (fast && nfull > 0) {
-		linearize_full_kernel<<<full_grid(nfull), 256, 0, st>>>(P, plan.full_list, nfull, pyr, pyr_chan_stride, pyr_pitch, bs);
+		int np = 1;
+		for (int c = 0; c < g.channels; ++c)
+			if (s.planes[c] > np)
+				np = s.planes[c];
+		const int grid = full_grid(nfull);
+#define LIN_CASE(N)                                                                                                      \
+	case N:                                                                                                              \
+		linearize_full_kernel<N><<<grid, 256, 0, st>>>(P, plan.full_list, nfull, pyr, pyr_chan_stride, pyr_pitch, bs);    \
+		break;
+		switch (np) {
+			LIN_CASE(1) LIN_CASE(2) LIN_CASE(3) LIN_CASE(4) LIN_CASE(5) LIN_CASE(6) LIN_CASE(7) LIN_CASE(8) LIN_CASE(9)
+			LIN_CASE(10) LIN_CASE(11) LIN_CASE(12)
+		}
+#undef LIN_CASE
 		if (launches)
 			++*launches;
 	} else if (nfull > 0) {
@@ -570,8 +611,21 @@ int hilbert_reconstruct(const Geom &g, const HilbertPlan &plan, const Sched &s, 
 	const bool fast = planes_fit(g, s);
 	const int nfull = plan.full_off[levels_used], npart = plan.part_off[levels_used];
 	if (fast && nfull > 0) {
-		reconstruct_full_kernel<<<full_grid(nfull), 256, 0, st>>>(P, plan.full_list, nfull, bs, missing_dev, levels_used, pyr,
-		                                                         pyr_chan_stride, pyr_pitch);
+		int np = 1;
+		for (int c = 0; c < g.channels; ++c)
+			if (s.planes[c] > np)
+				np = s.planes[c];
+		const int grid = full_grid(nfull);
+#define REC_CASE(N)                                                                                                      \
+	case N:                                                                                                              \
+		reconstruct_full_kernel<N><<<grid, 256, 0, st>>>(P, plan.full_list, nfull, bs, missing_dev, levels_used, pyr,     \
+		                                                 pyr_chan_stride, pyr_pitch);                                    \
+		break;
+		switch (np) {
+			REC_CASE(1) REC_CASE(2) REC_CASE(3) REC_CASE(4) REC_CASE(5) REC_CASE(6) REC_CASE(7) REC_CASE(8) REC_CASE(9)
+			REC_CASE(10) REC_CASE(11) REC_CASE(12)
+		}
+#undef REC_CASE
 		if (launches)
 			++*launches;
 	} else if (nfull > 0) {
