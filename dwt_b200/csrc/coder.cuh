@@ -30,9 +30,9 @@ struct EncBuffers {
 	u32 *signbuf;         // 1 bit per token
 	u32 *specbuf;         // 1 bit per token: flush candidate / final token
 	u32 *refbuf;          // dense refinement bits, all chunks back to back
-	u32 *tile_lo, *tile_hi, *tile_start; // VLI order at tile end for entry order 0 / 31; resolved entry order
+	u32 *tile_flags;      // ticket + per token tile: order map ends, resolved end, bit prefix state (zeroed per encode)
+	size_t tile_flag_bytes;
 	unsigned char *thr_state;  // resolved order at the first token of every thread
-	u32 *tile_bits;
 	u64 *tile_bitbase;
 	EncChunks *chunks;
 	EncInfo *info;

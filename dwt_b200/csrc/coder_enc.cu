@@ -15,11 +15,13 @@
 //   orders   the Rice order is a serial recurrence k' = max(ilog2(v + 2^k) - 2, 0).  The maps are monotone
 //            in k, so a tile whose end order agrees for entry orders 0 and 31 is a constant map; tiles are
 //            solved by a block-local fixed-point iteration, the (rare) non-constant tiles are chained
-//            exactly                                                              [enc_vli_tile/resolve/len_kernel]
-//   offsets  exclusive scan of token bit lengths                                           [enc_bitscan_kernel]
+//            exactly                                                              [enc_vli_kernel]
+//   offsets  exclusive scan of token bit lengths (decoupled look-back inside enc_vli_kernel)
 //   scatter  tokens and refinement bits are OR-ed into the zero-initialised stream          [enc_scatter_kernel,
 //                                                                                            enc_refcopy_kernel]
 #include "coder.cuh"
+
+#include <stdlib.h>
 
 namespace {
 
@@ -327,117 +329,137 @@ __device__ __forceinline__ int solve_tile(const Tok &T, int first, unsigned char
 	return e;
 }
 
-__global__ void __launch_bounds__(256) enc_vli_tile_kernel(const u32 *__restrict__ Z, const u32 *__restrict__ specbuf,
-                                                            const EncInfo *__restrict__ info, u32 *tile_lo, u32 *tile_hi)
-{
-	__shared__ unsigned char ends[256];
-	const u32 ntok = info->ntok;
-	const u32 tile = blockIdx.x;
-	if ((u64)tile * TT >= ntok)
-		return;
-	Tok T;
-	load_tokens(Z, specbuf, nullptr, ntok, tile * TT + threadIdx.x * TPT, T);
-	int s;
-	int lo = solve_tile(T, 0, ends, &s);
-	__syncthreads();
-	int hi = solve_tile(T, 31, ends, &s);
-	if (threadIdx.x == 255) {
-		tile_lo[tile] = lo;
-		tile_hi[tile] = hi;
-	}
-}
+// One pass over the token tiles (2048 tokens each), tiles taken in launch order through a ticket so that a tile only
+// ever waits for tiles that are already running:
+//   1. end order of the tile for entry orders 0 and 31 (the order map is monotone: equal ends = constant map), published;
+//   2. the tile's entry order: the predecessor's end if its map is constant, else the predecessor's resolved end
+//      (a chain only through the rare non-constant tiles);
+//   3. exact orders of the tile's threads, published resolved end, bit lengths and the tile's bit total.
+// (A decoupled look-back for the bit prefix inside this kernel was measured and lost: every tile then holds its SM slot
+// until its 32 predecessors have their totals; the prefix is a separate two-pass scan.)
+#define VA_READY 0x80000000u
 
-__global__ void __launch_bounds__(256) enc_vli_resolve_kernel(const u32 *__restrict__ Z, const u32 *__restrict__ specbuf,
-                                                               EncInfo *info, const u32 *tile_lo, const u32 *tile_hi,
-                                                               u32 *tile_start, int k0)
+__global__ void __launch_bounds__(256) enc_vli_kernel(const u32 *__restrict__ Z, const u32 *__restrict__ specbuf, EncInfo *info,
+                                                       u32 *ticket, volatile u32 *tileA, volatile u32 *tileB,
+                                                       unsigned char *thr_state, u32 *tile_bits, int k0)
 {
 	__shared__ unsigned char ends[256];
-	__shared__ unsigned char flags[256];
-	const u32 ntok = info->ntok;
-	const int nt = (int)info->ntiles;
-	for (int i = threadIdx.x; i < nt; i += 256) {
-		if (i == 0)
-			tile_start[0] = (u32)k0;
-		if (i + 1 < nt && tile_lo[i] == tile_hi[i])
-			tile_start[i + 1] = tile_lo[i]; // constant map: the entry order does not matter
-	}
-	__syncthreads();
-	u32 nopaque = 0;
-	for (int base = 0; base < nt; base += 256) {
-		int i = base + threadIdx.x;
-		bool op = i + 1 < nt && tile_lo[i] != tile_hi[i];
-		if (!__syncthreads_or(op))
-			continue;
-		flags[threadIdx.x] = op;
-		__syncthreads();
-		for (int w = 0; w < 256; ++w) {
-			if (!flags[w])
-				continue;
-			int tile = base + w;
-			Tok T;
-			load_tokens(Z, specbuf, nullptr, ntok, (u32)tile * TT + threadIdx.x * TPT, T);
-			int first = (int)tile_start[tile], s;
-			int end = solve_tile(T, first, ends, &s);
-			if (threadIdx.x == 255)
-				tile_start[tile + 1] = (u32)end;
-			++nopaque;
-			__syncthreads();
-		}
-	}
-	if (threadIdx.x == 0)
-		info->opaque_tiles = nopaque;
-}
-
-__global__ void __launch_bounds__(256) enc_vli_len_kernel(const u32 *__restrict__ Z, const u32 *__restrict__ specbuf,
-                                                           EncInfo *info, const u32 *__restrict__ tile_start,
-                                                           unsigned char *thr_state, u32 *tile_bits)
-{
-	__shared__ unsigned char ends[256];
-	__shared__ u32 total;
-	const u32 ntok = info->ntok;
-	const u32 tile = blockIdx.x;
-	if ((u64)tile * TT >= ntok)
-		return;
-	if (threadIdx.x == 0)
+	__shared__ u32 s_tile, total;
+	__shared__ int s_start;
+	const int tid = threadIdx.x;
+	if (tid == 0) {
+		s_tile = atomicAdd(ticket, 1u);
 		total = 0;
+	}
+	__syncthreads();
+	const u32 tile = s_tile;
+	const u32 ntok = info->ntok;
+	if ((u64)tile * TT >= ntok)
+		return;
 	Tok T;
-	load_tokens(Z, specbuf, nullptr, ntok, tile * TT + threadIdx.x * TPT, T);
+	load_tokens(Z, specbuf, nullptr, ntok, tile * TT + tid * TPT, T);
 	bool big = false;
 #pragma unroll
 	for (int k = 0; k < TPT; ++k)
 		big |= T.v[k] >= (1u << 30);
 	if (big)
 		info->error = 4; // run length beyond the reference's int range
-	int s;
-	solve_tile(T, (int)tile_start[tile], ends, &s);
-	thr_state[(size_t)tile * 256 + threadIdx.x] = (unsigned char)s;
+	int s_lo, s_hi;
+	const int lo = solve_tile(T, 0, ends, &s_lo);
+	__syncthreads();
+	const int hi = solve_tile(T, 31, ends, &s_hi);
+	if (tid == 255)
+		tileA[tile] = VA_READY | (u32)lo | ((u32)hi << 8);
+	if (tid == 0) {
+		int start = k0;
+		if (tile > 0) {
+			u32 a;
+			while (!((a = tileA[tile - 1]) & VA_READY))
+				;
+			const int plo = (int)(a & 0xffu), phi = (int)((a >> 8) & 0xffu);
+			if (plo == phi) {
+				start = plo; // constant map: the predecessor's entry order does not matter
+			} else {
+				u32 bprev;
+				while (!((bprev = tileB[tile - 1]) & VA_READY))
+					;
+				start = (int)(bprev & 0xffu);
+				atomicAdd(&info->opaque_tiles, 1u);
+			}
+		}
+		s_start = start;
+	}
+	__syncthreads();
+	const int start = s_start;
+	int s, end;
+	if (start == 0) {
+		s = s_lo;
+		end = lo;
+	} else if (start == 31) {
+		s = s_hi;
+		end = hi;
+	} else {
+		__syncthreads();
+		end = solve_tile(T, start, ends, &s);
+	}
+	if (tid == 255)
+		tileB[tile] = VA_READY | (u32)end;
+	thr_state[(size_t)tile * 256 + tid] = (unsigned char)s;
 	u32 bits;
 	run_tokens(T, s, &bits);
 	bits = __reduce_add_sync(0xffffffffu, bits);
-	if ((threadIdx.x & 31) == 0)
+	if ((tid & 31) == 0)
 		atomicAdd(&total, bits);
 	__syncthreads();
-	if (threadIdx.x == 0)
+	if (tid == 0)
 		tile_bits[tile] = total;
 }
 
-__global__ void __launch_bounds__(1024) enc_bitscan_kernel(const u32 *tile_bits, u64 *tile_bitbase, EncInfo *info)
+// exclusive prefix (64-bit) of the tile bit totals, two passes over blocks of SCAN_TILE tiles
+__global__ void __launch_bounds__(1024) enc_bitscan_local_kernel(const u32 *__restrict__ tile_bits, u64 *tile_bitbase,
+                                                                 const EncInfo *__restrict__ info, u64 *bsum)
 {
 	__shared__ u64 ws[32];
-	const int n = (int)info->ntiles;
-	const int per = (n + 1023) / 1024;
-	const int b = threadIdx.x * per, e = min(b + per, n);
-	u64 s = 0;
-	for (int k = b; k < e; ++k)
-		s += tile_bits[k];
+	const int n = (int)((info->ntok + TT - 1) / TT);
+	const int base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+	u32 v[4];
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+		v[k] = base + k < n ? tile_bits[base + k] : 0u;
 	u64 tot;
-	u64 run = block_exscan_u64(s, ws, &tot);
-	for (int k = b; k < e; ++k) {
-		tile_bitbase[k] = run;
-		run += tile_bits[k];
+	u64 run = block_exscan_u64((u64)v[0] + v[1] + v[2] + v[3], ws, &tot);
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		if (base + k < n)
+			tile_bitbase[base + k] = run;
+		run += v[k];
 	}
 	if (threadIdx.x == 0)
-		info->tok_bits = tot;
+		bsum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) enc_bitscan_fix_kernel(u64 *tile_bitbase, EncInfo *info, const u64 *__restrict__ bsum)
+{
+	__shared__ u64 ws[32];
+	const int n = (int)((info->ntok + TT - 1) / TT);
+	const int nb = gridDim.x;
+	const int base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+	u64 before = 0, all = 0;
+	for (int i = threadIdx.x; i < nb; i += 1024) {
+		const u64 v = bsum[i];
+		all += v;
+		if (i < (int)blockIdx.x)
+			before += v;
+	}
+	u64 t0, t1;
+	block_exscan_u64(before, ws, &t0);
+	block_exscan_u64(all, ws, &t1);
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+		if (base + k < n)
+			tile_bitbase[base + k] += t0;
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		info->tok_bits = t1;
 }
 
 // ------------------------------------------------------------------------------------------------ scatter
@@ -593,12 +615,16 @@ int enc_emit(const Geom &g, const Sched &hs, const EncBuffers &b, cudaStream_t s
 int enc_vli_orders(const EncBuffers &b, int k0, cudaStream_t st, long long *launches)
 {
 	// the token count lives on the device: launch for the upper bound, surplus tiles exit at once
-	unsigned tiles = (b.max_tokens + TT - 1) / TT;
-	enc_vli_tile_kernel<<<tiles, 256, 0, st>>>(b.Z, b.specbuf, b.info, b.tile_lo, b.tile_hi);
-	enc_vli_resolve_kernel<<<1, 256, 0, st>>>(b.Z, b.specbuf, b.info, b.tile_lo, b.tile_hi, b.tile_start, k0);
-	enc_vli_len_kernel<<<tiles, 256, 0, st>>>(b.Z, b.specbuf, b.info, b.tile_start, b.thr_state, b.tile_bits);
-	enc_bitscan_kernel<<<1, 1024, 0, st>>>(b.tile_bits, b.tile_bitbase, b.info);
-	*launches += 4;
+	const unsigned tiles = (b.max_tokens + TT - 1) / TT;
+	CUDA_OK(cudaMemsetAsync(b.tile_flags, 0, b.tile_flag_bytes, st));
+	u32 *ticket = b.tile_flags;
+	u32 *tileA = ticket + 8, *tileB = tileA + (tiles + 4), *tile_bits = tileB + (tiles + 4);
+	u64 *bsum = reinterpret_cast<u64 *>((reinterpret_cast<uintptr_t>(tile_bits + (tiles + 4)) + 15) & ~(uintptr_t)15);
+	enc_vli_kernel<<<tiles, 256, 0, st>>>(b.Z, b.specbuf, b.info, ticket, tileA, tileB, b.thr_state, tile_bits, k0);
+	const unsigned nb = (tiles + SCAN_TILE - 1) / SCAN_TILE;
+	enc_bitscan_local_kernel<<<nb, 1024, 0, st>>>(tile_bits, b.tile_bitbase, b.info, bsum);
+	enc_bitscan_fix_kernel<<<nb, 1024, 0, st>>>(b.tile_bitbase, b.info, bsum);
+	*launches += 3;
 	CUDA_OK(cudaGetLastError());
 	return 0;
 }

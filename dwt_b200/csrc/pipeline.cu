@@ -486,7 +486,7 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 		if (c->ent.ensure((size_t)b.nent * 12 + 64 + (size_t)(b.nent / 4096 + 2) * 24) || // + block totals of the scan
 		    c->Z.ensure(tok_room * 4 + 64) ||
 		    c->signbuf.ensure(bit_words * 4) || c->specbuf.ensure(bit_words * 4) || c->refbuf.ensure(ref_words * 4) ||
-		    c->tiles.ensure(ntile_max * (4 * 4 + 8) + 256) || c->thr_state.ensure(ntile_max * 256) ||
+		    c->tiles.ensure(ntile_max * 8 + (ntile_max + 8) * 16 + 512) || c->thr_state.ensure(ntile_max * 256) ||
 		    c->chunks.ensure(sizeof(EncChunks)) || c->info.ensure(sizeof(EncInfo)))
 			return -1;
 		CUDA_OK(cudaMemsetAsync(c->signbuf.p, 0, bit_words * 4, st));
@@ -501,10 +501,8 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 		b.specbuf = c->specbuf.as<u32>();
 		b.refbuf = c->refbuf.as<u32>();
 		b.tile_bitbase = c->tiles.as<u64>();
-		b.tile_lo = (u32 *)(b.tile_bitbase + ntile_max);
-		b.tile_hi = b.tile_lo + ntile_max;
-		b.tile_start = b.tile_hi + ntile_max;
-		b.tile_bits = b.tile_start + ntile_max;
+		b.tile_flags = (u32 *)(b.tile_bitbase + ntile_max); // 16-byte aligned: ntile_max * 8 bytes in front
+		b.tile_flag_bytes = (ntile_max + 8) * 16 + 64;
 		b.thr_state = c->thr_state.as<unsigned char>();
 		b.chunks = c->chunks.as<EncChunks>();
 		b.info = c->info.as<EncInfo>();
