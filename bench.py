@@ -361,7 +361,8 @@ def our_bench(args, rank, world, local):
                            parallelism="one frame stream per GPU, no collective; the %d frames of a step are coded concurrently "
                                        "on %d contexts (one CUDA stream and one host thread each)" % (F, F)),
                e2e=dict(value=round(e2e_value, 2), unit="Mpixel/s", ms_per_step=round(e2e_total / args.steps, 3),
-                        h2d_bytes_per_step=int(F * (img.size + stream_bytes)), d2h_bytes_per_step=int(F * (stream_bytes + img.size)),
+                        h2d_bytes_per_step=int(world * F * (img.size + stream_bytes)),
+                        d2h_bytes_per_step=int(world * F * (stream_bytes + img.size)),
                         api="dwt_encode_into + dwt_decode_into on page-locked host buffers, %d frames in flight" % F),
                gpu_launches=int(launches), clocks=clocks, roofline=roofline, stages=stages,
                single_frame=dict(ms_per_frame=round(statistics.median(serial_ms), 3),
@@ -386,9 +387,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--frames", type=int, default=4, help="frames per step, coded concurrently (one context each)")
+    ap.add_argument("--frames", type=int, default=8, help="frames per step, coded concurrently (one context each)")
     args = ap.parse_args()
     rank, world, local = dist_env()
+    # the one JSON line goes to the real stdout; anything a library prints to fd 1 meanwhile (the NCCL version banner) is
+    # sent to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
     if args.impl == "reference":
         if rank != 0:
             return 0
@@ -399,13 +405,15 @@ def main():
                     config=dict(workload=WORKLOAD, sample=r["sample"]),
                     cpu_baseline=dict(value=round(r["value"], 3), unit="Mpixel/s", cores=r["cores"], kind="reference", sample=r["sample"]),
                     e2e=dict(value=round(r["value"], 3), unit="Mpixel/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
         return 0
     if args.warmup < 3:
         args.warmup = 3
     out = our_bench(args, rank, world, local)
     if out is not None:
-        print(json.dumps(out))
+        real_stdout.write(json.dumps(out) + "\n")
+        real_stdout.flush()
     return 0
 
 
