@@ -465,14 +465,26 @@ __global__ void __launch_bounds__(128) dec_link_kernel(const u32 *__restrict__ s
 
 // tokens that start in the slice (a, b) from offset d with order k, against the member budget T.
 // Returns EV_NONE when the slice is left (d >= 64 then), otherwise the event that ends the pass.
-__device__ __forceinline__ int walk_events(u64 a, u64 b, int avail, u64 T, int &d, int &k, u64 &cum, u32 &ones,
+// lut: order-0 token table in shared memory (the resolver runs in one warp, so table and generic steps never diverge)
+__device__ __forceinline__ int walk_events(const u32 *lut, u64 a, u64 b, int avail, u64 T, int &d, int &k, u64 &cum, u32 &ones,
                                            u32 &ev_pending)
 {
+	const bool lut_ok = avail >= 64 + LUT_BITS + 4;
 	for (;;) {
 		if (cum >= T)
 			return EV_COVERED; // every member has its symbol; the pass ends in front of the token at d
 		if (d >= 64)
 			return EV_NONE;
+		if (k == 0 && lut_ok) { // several short tokens at once, as long as the pass cannot end inside them
+			const u32 t = lut[window32(a, b, d) & ((1u << LUT_BITS) - 1u)];
+			const u32 mem = t >> 11;
+			if ((t & 15u) && d + (int)((t >> 4) & 15u) < 64 && cum + mem < T) {
+				d += (int)(t & 15u);
+				ones += (t >> 8) & 7u;
+				cum += mem;
+				continue;
+			}
+		}
 		const u64 w = bits_from(a, b, d);
 		const u32 lo = (u32)w;
 		const int u = lo ? __ffs((int)lo) - 1 : 32;
@@ -524,6 +536,8 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 {
 	__shared__ u32 sigcount[48];
 	__shared__ int missing[48];
+	__shared__ u32 lut[1 << LUT_BITS];
+	__shared__ unsigned char s_chan[DWT_MAX_CHUNKS], s_level[DWT_MAX_CHUNKS];
 	const int lane = threadIdx.x;
 	const u32 FULL = 0xffffffffu;
 	DecState *st = B.state;
@@ -534,6 +548,12 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 	for (int i = lane; i < 48; i += 32) {
 		sigcount[i] = 0;
 		missing[i] = st->missing[i];
+	}
+	for (int i = lane; i < (1 << LUT_BITS); i += 32)
+		lut[i] = __ldg(B.toklut + i);
+	for (int i = lane; i < nchunks; i += 32) {
+		s_chan[i] = (unsigned char)S->chan[i];
+		s_level[i] = (unsigned char)S->level[i];
 	}
 	__syncwarp();
 	u64 bitpos = st->bitpos;
@@ -547,7 +567,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 	const long long t_begin = clock64();
 
 	for (int j = 0; j < nchunks && !stopped; ++j) {
-		const int c = S->chan[j], l = S->level[j];
+		const int c = s_chan[j], l = s_level[j];
 		if (level < l)
 			level = l; // decode.c:203,219-220,236-237: the chunk is started
 		const u32 nsig = sigcount[c * 16 + l];
@@ -639,7 +659,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 							}
 							++dbg_stray;
 							const u64 sgs = (u64)cw * WS + i + t;
-							event = walk_events(a, b, clamp_avail(end_bits, sgs << 6), T, d, k, cum, ones, f_pending);
+							event = walk_events(lut, a, b, clamp_avail(end_bits, sgs << 6), T, d, k, cum, ones, f_pending);
 							if (event != EV_NONE) {
 								f_pos = (sgs << 6) + (u64)d;
 								f_k = k;
@@ -866,7 +886,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 					if (e == PDEAD) {
 						event = EV_STOP; // cannot happen: the prefixes say tokens start here
 					} else {
-						event = walk_events(a, b, clamp_avail(end_bits, egs << 6), T, d, k, cum, ones, f_pending);
+						event = walk_events(lut, a, b, clamp_avail(end_bits, egs << 6), T, d, k, cum, ones, f_pending);
 						if (event == EV_NONE && cum >= T)
 							event = EV_COVERED; // the pass ends exactly with the slice's last token
 						if (event == EV_NONE)
