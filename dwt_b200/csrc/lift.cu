@@ -167,14 +167,12 @@ __device__ __forceinline__ void fwd_hlift(int (&v)[NC][4], const HPred &hp)
 // HI: the whole strip is horizontally interior and every buffer is aligned for vector access, so the boundary
 // rules, clamps and alignment fall-backs are compiled out (all but the two edge strips of a level take this path)
 template <int MODE, bool HI>
-__device__ __forceinline__ void fwd_body(const LiftLevel &p, const int RS, const int strip, const int seg, const int ch,
+__device__ __forceinline__ void fwd_body(const LiftLevel &p, const int y0, const int y1, const int strip, const int ch,
                                          const int lane)
 {
 	constexpr int NC = FwdTraits<MODE>::NC;
 	const int W = p.W, H = p.H;
 	const int x = strip * STRIP_OUT - 4 + 4 * lane; // this lane's first column (a multiple of 4)
-	const int y0 = seg * RS;
-	const int y1 = min(y0 + RS, H);
 	const int w2 = (W + 1) / 2, h2 = (H + 1) / 2;
 	const bool vs = lane >= 1 && lane <= 30 && (HI || x < W); // this lane stores
 	const bool full = vs && (HI || x + 3 < W);                // ... all four columns
@@ -316,39 +314,56 @@ __device__ __forceinline__ void fwd_body(const LiftLevel &p, const int RS, const
 	}
 }
 
-// work items (strip, row segment, channel) are handed out through a counter, strips fastest: the grid is sized to
-// what is resident, every warp keeps taking items until they run out, and no partial last wave is left over
-__device__ __forceinline__ bool next_item(const LiftLevel &p, int nstrip, int nseg, int planes, int lane, int &strip, int &seg,
-                                          int &ch)
+// Work items (strip, row segment, channel) are handed out through a counter, strips fastest.  The grid is sized to
+// what is resident and every warp keeps taking items until they run out.  The schedule allows a second, smaller
+// segment height for the last rows (rss); equal heights measured best, so rss == rs.
+struct LiftSched {
+	int nstrip, planes;
+	int rs, nbig;    // segments of rs rows cover rows [0, nbig * rs)
+	int rss, nsmall; // then segments of rss rows
+};
+
+__device__ __forceinline__ bool next_item(const LiftLevel &p, const LiftSched &q, int lane, int &strip, int &y0, int &y1, int &ch)
 {
 	int item = 0;
 	if (lane == 0)
 		item = atomicAdd(p.work, 1);
 	item = __shfl_sync(FULLMASK, item, 0);
-	if (item >= nstrip * nseg * planes)
+	const int big = q.nstrip * q.nbig * q.planes;
+	if (item < big) {
+		strip = item % q.nstrip;
+		const int r = item / q.nstrip;
+		y0 = (r % q.nbig) * q.rs;
+		y1 = min(y0 + q.rs, min(q.nbig * q.rs, p.H));
+		ch = r / q.nbig;
+		return true;
+	}
+	item -= big;
+	if (item >= q.nstrip * q.nsmall * q.planes)
 		return false;
-	strip = item % nstrip;
-	const int r = item / nstrip;
-	seg = r % nseg;
-	ch = r / nseg;
+	strip = item % q.nstrip;
+	const int r = item / q.nstrip;
+	y0 = q.nbig * q.rs + (r % q.nsmall) * q.rss;
+	y1 = min(y0 + q.rss, p.H);
+	ch = r / q.nsmall;
 	return true;
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 5) lift_fwd_kernel(const __grid_constant__ LiftLevel p, int RS,
-                                                                            int nstrip, int nseg, int planes)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 5) lift_fwd_kernel(const __grid_constant__ LiftLevel p,
+                                                                            const __grid_constant__ LiftSched q)
 {
 	const int lane = threadIdx.x & 31;
 	const int W = p.W;
 	const int w2 = (W + 1) / 2;
 	const bool aligned = (MODE == 2 ? ((p.in_pitch | (int)p.in_chan_stride) & 3) == 0 : (p.in_pitch & 3) == 0) &&
 	                     ((p.out_pitch | (int)p.out_chan_stride | p.pyr_pitch | (int)p.pyr_chan_stride | w2) & 1) == 0;
-	int strip, seg, ch;
-	while (next_item(p, nstrip, nseg, planes, lane, strip, seg, ch)) {
+	int strip, y0, y1, ch;
+	while (next_item(p, q, lane, strip, y0, y1, ch)) {
 		if (aligned && strip > 0 && strip * STRIP_OUT + 124 < W)
-			fwd_body<MODE, true>(p, RS, strip, seg, ch, lane);
+			fwd_body<MODE, true>(p, y0, y1, strip, ch, lane);
 		else
-			fwd_body<MODE, false>(p, RS, strip, seg, ch, lane);
+			fwd_body<MODE, false>(p, y0, y1, strip, ch, lane);
 	}
 }
 
@@ -439,7 +454,7 @@ __device__ __forceinline__ void inv_store_row(const LiftLevel &p, int ch, int y,
 }
 
 template <int MODE, bool HI>
-__device__ __forceinline__ void inv_body(const LiftLevel &p, const int RS, const int strip, const int seg, const int chz,
+__device__ __forceinline__ void inv_body(const LiftLevel &p, const int y0, const int y1, const int strip, const int chz,
                                          const int lane)
 {
 	constexpr int NC = FwdTraits<MODE>::NC;
@@ -447,8 +462,6 @@ __device__ __forceinline__ void inv_body(const LiftLevel &p, const int RS, const
 	const int x = strip * STRIP_OUT - 4 + 4 * lane; // output columns x .. x+3 = column pairs j, j+1
 	const int j = x >> 1;
 	const int w2 = (W + 1) / 2, h2 = (H + 1) / 2, wd = W / 2, hd = H / 2;
-	const int y0 = seg * RS;
-	const int y1 = min(y0 + RS, H);
 	const bool vs = lane >= 1 && lane <= 30 && (HI || x < W);
 	const bool full = vs && (HI || x + 3 < W);
 	// clamped band columns: low-x pair and high-x pair (Mallat position)
@@ -580,20 +593,20 @@ __device__ __forceinline__ void inv_body(const LiftLevel &p, const int RS, const
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) lift_inv_kernel(const __grid_constant__ LiftLevel p, int RS,
-                                                                         int nstrip, int nseg, int planes)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) lift_inv_kernel(const __grid_constant__ LiftLevel p,
+                                                                         const __grid_constant__ LiftSched q)
 {
 	const int lane = threadIdx.x & 31;
 	const int W = p.W;
 	const int w2 = (W + 1) / 2;
 	const bool aligned = ((p.in_pitch | (int)p.in_chan_stride | p.pyr_pitch | (int)p.pyr_chan_stride | w2) & 1) == 0 &&
 	                     (MODE == 2 ? ((p.out_pitch | (int)p.out_chan_stride) & 3) == 0 : (p.out_pitch & 3) == 0);
-	int strip, seg, ch;
-	while (next_item(p, nstrip, nseg, planes, lane, strip, seg, ch)) {
+	int strip, y0, y1, ch;
+	while (next_item(p, q, lane, strip, y0, y1, ch)) {
 		if (aligned && strip > 0 && strip * STRIP_OUT + 124 < W)
-			inv_body<MODE, true>(p, RS, strip, seg, ch, lane);
+			inv_body<MODE, true>(p, y0, y1, strip, ch, lane);
 		else
-			inv_body<MODE, false>(p, RS, strip, seg, ch, lane);
+			inv_body<MODE, false>(p, y0, y1, strip, ch, lane);
 	}
 }
 
@@ -901,21 +914,35 @@ static int resident_blocks()
 	return n;
 }
 
+static LiftSched make_sched(const LiftLevel &lv, int planes, long long *items)
+{
+	LiftSched q;
+	q.nstrip = (lv.W + STRIP_OUT - 1) / STRIP_OUT;
+	q.planes = planes;
+	q.rs = pick_rows(lv.W, lv.H, planes);
+	q.rss = q.rs; // a finer last quarter (rs / 4) was measured and lost: the extra halo rows cost more than the idle tail
+	const int nseg = (lv.H + q.rs - 1) / q.rs;
+	q.nbig = q.rss < q.rs ? nseg * 3 / 4 : nseg; // small levels: one size
+	const int rest = lv.H - q.nbig * q.rs;
+	q.nsmall = rest > 0 ? (rest + q.rss - 1) / q.rss : 0;
+	*items = (long long)q.nstrip * planes * (q.nbig + q.nsmall);
+	return q;
+}
+
 // lv.work must point at a zeroed device counter (one per launch)
 int lift_forward_level(const LiftLevel &lv, int mode, cudaStream_t st, long long *launches)
 {
 	const int planes = mode == 2 ? lv.channels : 1;
-	const int RS = pick_rows(lv.W, lv.H, planes);
-	const int strips = (lv.W + STRIP_OUT - 1) / STRIP_OUT, nseg = (lv.H + RS - 1) / RS;
-	const long long items = (long long)strips * nseg * planes;
+	long long items;
+	const LiftSched q = make_sched(lv, planes, &items);
 	const int grid = (int)min((items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (long long)resident_blocks());
 	dim3 block(WARPS_PER_BLOCK * 32);
 	if (mode == 0)
-		lift_fwd_kernel<0><<<grid, block, 0, st>>>(lv, RS, strips, nseg, planes);
+		lift_fwd_kernel<0><<<grid, block, 0, st>>>(lv, q);
 	else if (mode == 1)
-		lift_fwd_kernel<1><<<grid, block, 0, st>>>(lv, RS, strips, nseg, planes);
+		lift_fwd_kernel<1><<<grid, block, 0, st>>>(lv, q);
 	else
-		lift_fwd_kernel<2><<<grid, block, 0, st>>>(lv, RS, strips, nseg, planes);
+		lift_fwd_kernel<2><<<grid, block, 0, st>>>(lv, q);
 	if (launches)
 		++*launches;
 	CUDA_OK(cudaGetLastError());
@@ -925,17 +952,16 @@ int lift_forward_level(const LiftLevel &lv, int mode, cudaStream_t st, long long
 int lift_inverse_level(const LiftLevel &lv, int mode, cudaStream_t st, long long *launches)
 {
 	const int planes = mode == 2 ? lv.channels : 1;
-	const int RS = pick_rows(lv.W, lv.H, planes);
-	const int strips = (lv.W + STRIP_OUT - 1) / STRIP_OUT, nseg = (lv.H + RS - 1) / RS;
-	const long long items = (long long)strips * nseg * planes;
+	long long items;
+	const LiftSched q = make_sched(lv, planes, &items);
 	const int grid = (int)min((items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (long long)resident_blocks());
 	dim3 block(WARPS_PER_BLOCK * 32);
 	if (mode == 0)
-		lift_inv_kernel<0><<<grid, block, 0, st>>>(lv, RS, strips, nseg, planes);
+		lift_inv_kernel<0><<<grid, block, 0, st>>>(lv, q);
 	else if (mode == 1)
-		lift_inv_kernel<1><<<grid, block, 0, st>>>(lv, RS, strips, nseg, planes);
+		lift_inv_kernel<1><<<grid, block, 0, st>>>(lv, q);
 	else
-		lift_inv_kernel<2><<<grid, block, 0, st>>>(lv, RS, strips, nseg, planes);
+		lift_inv_kernel<2><<<grid, block, 0, st>>>(lv, q);
 	if (launches)
 		++*launches;
 	CUDA_OK(cudaGetLastError());

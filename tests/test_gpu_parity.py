@@ -202,6 +202,59 @@ def test_batch_of_1080p_images(codec, oracle):
         assert np.array_equal(codec.decode(s), img)
 
 
+def test_adversarial_patterns(codec, oracle):
+    """checkerboards and stripes at several scales: largest coefficient growth through the levels, every token kind
+    (long runs, order excursions), streams that are mostly refinement bits"""
+    yy, xx = np.mgrid[0:256, 0:384]
+    pats = [((xx ^ yy) & 1) * 255, ((xx >> 1) ^ (yy >> 2)) % 2 * 255, (xx & 1) * 255, ((xx // 7 + yy // 5) % 2) * 255,
+            ((xx * yy) % 251)]
+    for k, p2 in enumerate(pats):
+        img = np.stack([p2, np.roll(p2, k + 1, axis=0), 255 - p2], axis=2).astype(np.uint8)
+        want, _ = oracle.encode(img)
+        assert codec.encode(img) == want, k
+        for cap in (len(want) // 3, len(want) - 1):
+            assert codec.encode(img, cap) == want[:cap]
+            a, b = codec.decode(want[:cap]), oracle.decode(want[:cap])
+            assert a.shape == b.shape and np.array_equal(a, b), (k, cap)
+        assert np.array_equal(codec.decode(want), img), k
+
+
+def test_concurrent_contexts(oracle):
+    """several contexts (one CUDA stream each) driven from their own host threads, as bench.py does: every thread's
+    streams and pixels must equal the oracle's"""
+    import threading
+    import dwt_b200 as D
+    imgs = [oracle.synth(640 + 64 * i, 360 + 24 * i, "photo" if i % 2 == 0 else "noise", 40 + i) for i in range(4)]
+    want = [oracle.encode(im)[0] for im in imgs]
+    cods = [D.Codec(0) for _ in imgs]
+    errors = []
+
+    def work(i):
+        try:
+            for _ in range(6):
+                s = cods[i].encode(imgs[i])
+                if s != want[i]:
+                    errors.append("stream %d" % i)
+                d = cods[i].decode(s)
+                if d is None or not np.array_equal(d, imgs[i]):
+                    errors.append("pixels %d" % i)
+                cap = len(want[i]) // 2
+                a, b = cods[i].decode(want[i][:cap]), oracle.decode(want[i][:cap])
+                if a.shape != b.shape or not np.array_equal(a, b):
+                    errors.append("truncated %d" % i)
+        except Exception as ex:  # noqa: BLE001
+            errors.append("%d: %r" % (i, ex))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(imgs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for c in cods:
+        c.close()
+    assert not errors, errors
+
+
 # ------------------------------------------------------------------ the drop-in programs
 
 def test_cli_roundtrip_matches_reference_behaviour(codec, oracle, tmp_path):
