@@ -220,9 +220,13 @@ __device__ __forceinline__ void fwd_body(const LiftLevel &p, const int y0, const
 		mx[c] = 0;
 
 	const int xl = x >> 1, xh = w2 + (x >> 1);
-	Raw<MODE> no, ne; // prefetched raw rows r+1, r+2
+	// raw rows are fetched two iterations ahead (r+1, r+2 in no / ne, r+3, r+4 in no2 / ne2): one iteration of
+	// distance left the first use of a row waiting on DRAM for half of all stall samples
+	Raw<MODE> no, ne, no2, ne2;
 	fwd_load<MODE>(p, ch, y0 + 1, x, fast, no);
 	fwd_load<MODE>(p, ch, y0 + 2, x, fast, ne);
+	fwd_load<MODE>(p, ch, y0 + 3, x, fast, no2);
+	fwd_load<MODE>(p, ch, y0 + 4, x, fast, ne2);
 	// one row pair.  STEADY (interior strips only): not the first pair, rows r+3 / r+4 exist and are prefetched --
 	// no clamp, no boundary rule, no branch in the body; this is what almost every iteration runs
 	auto step = [&](const int r, auto steady_tag) {
@@ -230,9 +234,11 @@ __device__ __forceinline__ void fwd_body(const LiftLevel &p, const int y0, const
 		int o[NC][4], f[NC][4];
 		fwd_expand<MODE>(no, o);
 		fwd_expand<MODE>(ne, f);
-		if (STEADY || r + 2 < y1) {
-			fwd_load<MODE, STEADY>(p, ch, r + 3, x, fast, no);
-			fwd_load<MODE, STEADY>(p, ch, r + 4, x, fast, ne);
+		no = no2;
+		ne = ne2;
+		if (STEADY || r + 4 < y1) {
+			fwd_load<MODE, STEADY>(p, ch, r + 5, x, fast, no2);
+			fwd_load<MODE, STEADY>(p, ch, r + 6, x, fast, ne2);
 		}
 		fwd_hlift<NC>(o, hp);
 		fwd_hlift<NC>(f, hp);
@@ -301,7 +307,7 @@ __device__ __forceinline__ void fwd_body(const LiftLevel &p, const int y0, const
 	};
 #pragma unroll 1
 	for (int r = y0; r < y1; r += 2) {
-		if (HI && r > 0 && r + 2 < y1 && r + 4 < H)
+		if (HI && r > 0 && r + 6 < H)
 			step(r, std::true_type());
 		else
 			step(r, std::false_type());
