@@ -19,6 +19,7 @@ ABI_SYMBOLS = [
     "dwt_ctx_decode_resident", "dwt_ctx_download_image", "dwt_ctx_launch_count", "dwt_ctx_sync",
     "dwt_host_alloc", "dwt_host_free", "dwt_encode_into", "dwt_decode_into", "dwt_ctx_flush_l2",
     "dwt_ctx_event_record", "dwt_ctx_event_elapsed_ms", "dwt_ctx_wait_for",
+    "dwt_pool_create", "dwt_pool_destroy", "dwt_pool_workers", "dwt_pool_encode", "dwt_pool_decode", "dwt_pool_run",
     "cdf53", "icdf53", "dwt_forward", "dwt_inverse", "dwt_ycocg_from_rgb", "dwt_rgb_from_ycocg",
     "compute_lengths", "ilog2", "dwt_debug_front_end",
     "bytes_reader", "bytes_writer", "bytes_count", "close_bytes_reader", "close_bytes_writer", "put_byte",
@@ -38,6 +39,16 @@ class Stats(C.Structure):
                 ("ms_h2d", C.c_float), ("ms_lift", C.c_float), ("ms_linearize", C.c_float), ("ms_coder", C.c_float),
                 ("ms_d2h", C.c_float), ("ms_total", C.c_float), ("level_reached", C.c_int),
                 ("parse_windows", C.c_longlong), ("parse_jumps", C.c_longlong), ("parse_exact", C.c_longlong)]
+
+
+class EncodeItem(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("capacity", C.c_int),
+                ("out", C.c_void_p), ("out_room", C.c_size_t), ("out_len", C.c_size_t), ("status", C.c_int)]
+
+
+class DecodeItem(C.Structure):
+    _fields_ = [("stream", C.c_void_p), ("len", C.c_size_t), ("pixels_max", C.c_int), ("pixels", C.c_void_p),
+                ("pixels_room", C.c_size_t), ("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("status", C.c_int)]
 
 
 class DwtError(RuntimeError):
@@ -86,6 +97,14 @@ def lib():
     L.dwt_ctx_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int]
     L.dwt_ctx_event_elapsed_ms.restype = C.c_float
     L.dwt_ctx_wait_for.argtypes = [vp, vp]
+    L.dwt_pool_create.argtypes = [C.c_int, C.c_int]
+    L.dwt_pool_create.restype = vp
+    L.dwt_pool_destroy.argtypes = [vp]
+    L.dwt_pool_destroy.restype = None
+    L.dwt_pool_workers.argtypes = [vp]
+    L.dwt_pool_encode.argtypes = [vp, C.POINTER(EncodeItem), C.c_int]
+    L.dwt_pool_decode.argtypes = [vp, C.POINTER(DecodeItem), C.c_int]
+    L.dwt_pool_run.argtypes = [vp, C.POINTER(EncodeItem), C.c_int, C.POINTER(DecodeItem), C.c_int]
     L.cdf53.argtypes = [ip, ip, C.c_int, C.c_int, C.c_int, C.c_int]
     L.cdf53.restype = None
     L.icdf53.argtypes = [ip, ip, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -259,6 +278,71 @@ class Codec:
         if lib().dwt_debug_front_end(self._h, _u8p(img), w, h, ch, _ip(pyr), _ip(lin), planes):
             raise DwtError("dwt_debug_front_end failed: " + last_error())
         return pyr, lin, list(planes)[:ch]
+
+
+class Pool:
+    """dwt_pool: `workers` contexts on one device coding the items of a batch concurrently (one host thread each)"""
+
+    def __init__(self, device=0, workers=4):
+        self._h = lib().dwt_pool_create(int(device), int(workers))
+        if not self._h:
+            raise DwtError("dwt_pool_create failed: " + last_error())
+
+    def close(self):
+        if self._h:
+            lib().dwt_pool_destroy(self._h)
+            self._h = None
+
+    def encode_items(self, items, n):
+        """items: ctypes array of EncodeItem (buffers owned by the caller); returns the number of failed items"""
+        return lib().dwt_pool_encode(self._h, items, n)
+
+    def decode_items(self, items, n):
+        return lib().dwt_pool_decode(self._h, items, n)
+
+    def run_items(self, enc_items, n_enc, dec_items, n_dec):
+        """encode and decode items in one call, interleaved on the workers"""
+        return lib().dwt_pool_run(self._h, enc_items, n_enc, dec_items, n_dec)
+
+    def encode_batch(self, images, capacity=0):
+        """list of uint8 images -> list of .dwt byte strings"""
+        n = len(images)
+        items = (EncodeItem * n)()
+        keep = []
+        for i, img in enumerate(images):
+            img = np.ascontiguousarray(img, dtype=np.uint8)
+            w, h, ch = _shape(img)
+            src, o1 = pinned_array(img.size)
+            src[:] = img.reshape(-1)
+            dst, o2 = pinned_array(img.size * 2 + 4096)
+            keep.append((src, dst, o1, o2))
+            items[i] = EncodeItem(src.ctypes.data, w, h, ch, int(capacity), dst.ctypes.data, dst.size, 0, 0)
+        bad = self.encode_items(items, n)
+        if bad:
+            raise DwtError("dwt_pool_encode: %d items failed" % bad)
+        return [bytes(keep[i][1][:items[i].out_len]) for i in range(n)]
+
+    def decode_batch(self, streams, shapes, pixels_max=-1):
+        """list of streams + upper bounds (h, w, ch) of their decoded sizes -> list of uint8 arrays"""
+        n = len(streams)
+        items = (DecodeItem * n)()
+        keep = []
+        for i, s in enumerate(streams):
+            src, o1 = pinned_array(max(1, len(s)))
+            src[:len(s)] = np.frombuffer(s, dtype=np.uint8)
+            h, w, ch = shapes[i]
+            dst, o2 = pinned_array(h * w * ch)
+            keep.append((src, dst, o1, o2))
+            items[i] = DecodeItem(src.ctypes.data, len(s), int(pixels_max), dst.ctypes.data, dst.size, 0, 0, 0, 0)
+        bad = self.decode_items(items, n)
+        if bad:
+            raise DwtError("dwt_pool_decode: %d items failed" % bad)
+        out = []
+        for i in range(n):
+            it = items[i]
+            shape = (it.height, it.width, it.channels) if it.channels > 1 else (it.height, it.width)
+            out.append(np.array(keep[i][1][:it.height * it.width * it.channels]).reshape(shape))
+        return out
 
 
 def pinned_array(nbytes):

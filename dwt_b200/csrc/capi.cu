@@ -5,6 +5,10 @@
 
 #include "dwt_b200.h"
 
+#include <atomic>
+#include <thread>
+#include <vector>
+
 #include <string.h>
 
 
@@ -345,6 +349,131 @@ extern "C" int dwt_decode_into(dwt_ctx *c, const uint8_t *stream, size_t len, in
 	CUDA_OK(cudaMemcpyAsync(pixels, c->img.p, n, cudaMemcpyDeviceToHost, c->st));
 	CUDA_OK(cudaStreamSynchronize(c->st));
 	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ batches
+//
+// Images are independent: a pool owns `workers` contexts on one device (one CUDA stream each) and codes
+// the items of a batch on as many host threads, so the copies of one item overlap the kernels of the others and the
+// single-warp stages of one frame hide behind the wide kernels of its neighbours.  One pool per GPU; no collective.
+
+struct dwt_pool {
+	int device = 0;
+	std::vector<dwt_ctx *> ctx;
+};
+
+extern "C" dwt_pool *dwt_pool_create(int device, int workers)
+{
+	if (workers < 1)
+		workers = 1;
+	dwt_pool *p = new dwt_pool();
+	for (int i = 0; i < workers; ++i) {
+		dwt_ctx *c = dwt_ctx_create(device);
+		if (!c) {
+			for (dwt_ctx *d : p->ctx)
+				dwt_ctx_destroy(d);
+			delete p;
+			return nullptr;
+		}
+		p->ctx.push_back(c);
+		p->device = c->device;
+	}
+	return p;
+}
+
+extern "C" void dwt_pool_destroy(dwt_pool *p)
+{
+	if (!p)
+		return;
+	for (dwt_ctx *c : p->ctx)
+		dwt_ctx_destroy(c);
+	delete p;
+}
+
+extern "C" int dwt_pool_workers(const dwt_pool *p)
+{
+	return p ? (int)p->ctx.size() : 0;
+}
+
+template <typename F>
+static int pool_run(dwt_pool *p, int n, F &&one)
+{
+	if (!p || n < 0) {
+		dwt_set_error("bad batch arguments");
+		return -1;
+	}
+	std::atomic<int> next(0), failed(0);
+	auto work = [&](int w) {
+		for (;;) {
+			const int i = next.fetch_add(1);
+			if (i >= n)
+				break;
+			if (one(p->ctx[(size_t)w], i))
+				failed.fetch_add(1);
+		}
+	};
+	const int nw = (int)p->ctx.size() < n ? (int)p->ctx.size() : n;
+	std::vector<std::thread> th;
+	for (int w = 1; w < nw; ++w)
+		th.emplace_back(work, w);
+	if (nw > 0)
+		work(0);
+	for (auto &t : th)
+		t.join();
+	return failed.load();
+}
+
+extern "C" int dwt_pool_encode(dwt_pool *p, struct dwt_encode_item *items, int n)
+{
+	return pool_run(p, n, [&](dwt_ctx *c, int i) {
+		dwt_encode_item &it = items[i];
+		it.status = dwt_encode_into(c, it.pixels, it.width, it.height, it.channels, it.capacity, it.out, it.out_room, &it.out_len,
+		                            nullptr);
+		return it.status != 0;
+	});
+}
+
+extern "C" int dwt_pool_decode(dwt_pool *p, struct dwt_decode_item *items, int n)
+{
+	return pool_run(p, n, [&](dwt_ctx *c, int i) {
+		dwt_decode_item &it = items[i];
+		it.status = dwt_decode_into(c, it.stream, it.len, it.pixels_max, it.pixels, it.pixels_room, &it.width, &it.height,
+		                            &it.channels, nullptr);
+		return it.status != 0;
+	});
+}
+
+// encode and decode items of one batch in one go, interleaved on the workers (a transcoding front end has both kinds
+// of job in flight: uploads of pixels overlap downloads of pixels, streams flow the other way)
+extern "C" int dwt_pool_run(dwt_pool *p, struct dwt_encode_item *enc, int n_enc, struct dwt_decode_item *dec, int n_dec)
+{
+	if (n_enc < 0 || n_dec < 0 || (n_enc && !enc) || (n_dec && !dec)) {
+		dwt_set_error("bad batch arguments");
+		return -1;
+	}
+	const int lo = n_enc < n_dec ? n_enc : n_dec;
+	return pool_run(p, n_enc + n_dec, [&](dwt_ctx *c, int i) {
+		// jobs 0 .. 2*lo-1 alternate encode / decode, the rest is whatever kind is left
+		bool is_enc;
+		int k;
+		if (i < 2 * lo) {
+			is_enc = (i & 1) == 0;
+			k = i >> 1;
+		} else {
+			is_enc = n_enc > n_dec;
+			k = lo + (i - 2 * lo);
+		}
+		if (is_enc) {
+			dwt_encode_item &it = enc[k];
+			it.status = dwt_encode_into(c, it.pixels, it.width, it.height, it.channels, it.capacity, it.out, it.out_room,
+			                            &it.out_len, nullptr);
+			return it.status != 0;
+		}
+		dwt_decode_item &it = dec[k];
+		it.status = dwt_decode_into(c, it.stream, it.len, it.pixels_max, it.pixels, it.pixels_room, &it.width, &it.height,
+		                            &it.channels, nullptr);
+		return it.status != 0;
+	});
 }
 
 // write a buffer larger than L2 (126 MB) so the next timed step starts from HBM

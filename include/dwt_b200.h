@@ -86,6 +86,35 @@ int dwt_encode_into(dwt_ctx *ctx, const uint8_t *pixels, int width, int height, 
                     uint8_t *out, size_t out_room, size_t *out_len, struct dwt_stats *stats);
 int dwt_decode_into(dwt_ctx *ctx, const uint8_t *stream, size_t len, int pixels_max, uint8_t *pixels,
                     size_t pixels_room, int *width, int *height, int *channels, struct dwt_stats *stats);
+/* Batches of independent images (the reference codes one image per process): a pool owns `workers`
+ * contexts on one device and codes the items on as many host threads, so host<->device copies and kernels of different
+ * items overlap.  Buffers should come from dwt_host_alloc().  status per item: the value dwt_encode_into /
+ * dwt_decode_into would have returned.  Return value: number of items whose status is non-zero, -1 on bad arguments. */
+struct dwt_encode_item {
+	const uint8_t *pixels;
+	int width, height, channels, capacity;
+	uint8_t *out;
+	size_t out_room, out_len;
+	int status;
+};
+struct dwt_decode_item {
+	const uint8_t *stream;
+	size_t len;
+	int pixels_max; /* < 0: none */
+	uint8_t *pixels;
+	size_t pixels_room;
+	int width, height, channels;
+	int status;
+};
+typedef struct dwt_pool dwt_pool;
+dwt_pool *dwt_pool_create(int device, int workers);
+void dwt_pool_destroy(dwt_pool *pool);
+int dwt_pool_workers(const dwt_pool *pool);
+int dwt_pool_encode(dwt_pool *pool, struct dwt_encode_item *items, int n);
+int dwt_pool_decode(dwt_pool *pool, struct dwt_decode_item *items, int n);
+/* both kinds of item in one call, interleaved on the workers (pixel uploads overlap pixel downloads) */
+int dwt_pool_run(dwt_pool *pool, struct dwt_encode_item *enc, int n_enc, struct dwt_decode_item *dec, int n_dec);
+
 /* benchmark helpers: evict L2 (writes 256 MB), CUDA events on the context's stream (slots 0..3) */
 int dwt_ctx_flush_l2(dwt_ctx *ctx);
 int dwt_ctx_event_record(dwt_ctx *ctx, int slot);

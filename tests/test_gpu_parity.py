@@ -255,6 +255,30 @@ def test_concurrent_contexts(oracle):
     assert not errors, errors
 
 
+def test_pool_batch_matches_oracle(oracle):
+    """dwt_pool: a batch of independent images of different sizes through 3 workers; streams, truncated streams
+    and decoded pixels must equal the oracle's, item by item"""
+    import dwt_b200 as D
+    imgs = [oracle.synth(200 + 37 * i, 120 + 29 * i, "photo" if i % 3 else "noise", 60 + i) for i in range(7)]
+    imgs.append(oracle.synth(133, 100, "photo", 5)[:, :, 1].copy())  # gray
+    want = [oracle.encode(im)[0] for im in imgs]
+    pool = D.Pool(0, 3)
+    try:
+        assert pool.encode_batch(imgs) == want
+        cut = pool.encode_batch(imgs, 777)
+        assert cut == [w[:777] for w in want]
+        shapes = [im.shape if im.ndim == 3 else im.shape + (1,) for im in imgs]
+        dec = pool.decode_batch(want, shapes)
+        for a, b in zip(dec, imgs):
+            assert a.shape == b.shape and np.array_equal(a, b)
+        part = pool.decode_batch(cut, shapes)
+        for a, s in zip(part, cut):
+            b = oracle.decode(s)
+            assert a.shape == b.shape and np.array_equal(a, b)
+    finally:
+        pool.close()
+
+
 # ------------------------------------------------------------------ the drop-in programs
 
 def test_cli_roundtrip_matches_reference_behaviour(codec, oracle, tmp_path):
