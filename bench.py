@@ -34,7 +34,8 @@ sys.path.insert(0, ROOT)
 W, H, CH = 7680, 4320, 3
 WORKLOAD = "synthetic 7680x4320 RGB 'photo' frame (SURVEY App. E.2, seed = rank+1), lossless encode + decode round trip"
 LIFT_BYTES_PER_PIXEL = 23.0   # u8 in (colour fused), int32 between levels, RGB
-L2_NOTE = "L2 flushed (256 MB write) between timed steps; per-step working set ~1.5 GB >> 126 MB L2"
+L2_NOTE = ("inputs larger than L2: a step touches ~1.5 GB per frame (126 MB L2); L2 flushed (256 MB write) before the timed "
+           "region and between the frames of the single-frame pass")
 
 
 def peaks():
@@ -267,71 +268,82 @@ def our_bench(args, rank, world, local):
     serial_ms = [serial_step(True) for _ in range(args.steps)]
     barrier()
 
-    # ---- pass 2, the measured throughput: F frames per step, device resident, one region of CUDA events
-    def resident_frame(i):
-        cods[i].encode_resident(0)
-        cods[i].decode_resident(-1)
+    # ---- pass 2, the measured throughput: K steps of F frames, device resident, ONE region of CUDA events around the K
+    # steps (barrier + synchronize on both sides).  Context i codes its K frames back to back; the contexts run freely
+    # next to each other, so there is no idle tail between steps.  No L2 flush inside the region: a step touches
+    # F x ~1.5 GB, far more than the 126 MB L2.
+    def resident_frames(i, k):
+        for _ in range(k):
+            cods[i].encode_resident(0)
+            cods[i].decode_resident(-1)
 
-    def resident_step():
+    def resident_region(k):
         cod.flush_l2()
         sync_all()
         cod.event_record(0)
-        list(pool.map(resident_frame, range(F)))
+        list(pool.map(lambda i: resident_frames(i, k), range(F)))
         for cd in cods[1:]:
             cod.wait_for(cd)
         cod.event_record(1)
         return cod.event_elapsed_ms(0, 1)
 
-    for _ in range(args.warmup):
-        resident_step()
+    resident_region(args.warmup)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = sum(cd.launch_count() for cd in cods)
     t_wall0 = time.perf_counter()
-    dev_ms = [resident_step() for _ in range(args.steps)]
+    total_ms = resident_region(args.steps)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = sum(cd.launch_count() for cd in cods) - l0
-    total_ms = sum(dev_ms)
 
     # ---- pass 3, end to end through the library's batch call (dwt_pool_run): host buffers in, host buffers out, copies
-    # inside the timed region.  A step encodes its F frames and decodes the F streams the previous step produced (the
-    # first one: the parity gate's), both kinds of job interleaved on the pool's F contexts, so pixel uploads overlap pixel
-    # downloads; every step does the full work of F encodes + F decodes
-    dpool = D.Pool(local, 2 * F)   # one context per job of a step
-    alt_out = []
-    for _ in range(F):
-        b2, o4 = D.pinned_array(img.size * 2 + 4096)
-        keep.append(o4)
-        alt_out.append(b2)
-    sets = [pin_out, alt_out]
-    enc_items = (D.EncodeItem * F)()
-    dec_items = (D.DecodeItem * F)()
-    state = dict(cur=1, lens=[stream_bytes] * F)   # pin_out holds valid streams from the parity gate
+    # inside the timed region.  The K steps are one call: K x F encode items (frames) + K x F decode items (the streams of
+    # the parity gate), interleaved on the pool's contexts so that pixel uploads overlap pixel downloads.  Every job has
+    # its own output buffer.
+    dpool = D.Pool(local, 2 * F)
+    out_room = stream_bytes + stream_bytes // 4 + 4096
 
-    def e2e_step():
+    def make_jobs(k):
+        n_jobs = k * F
+        enc_items = (D.EncodeItem * n_jobs)()
+        dec_items = (D.DecodeItem * n_jobs)()
+        outs, decs = [], []
+        for jb in range(n_jobs):
+            o, own_o = D.pinned_array(out_room)
+            dd, own_d = D.pinned_array(img.size)
+            keep.extend([own_o, own_d])
+            outs.append(o)
+            decs.append(dd)
+            i = jb % F
+            enc_items[jb] = D.EncodeItem(pin_img[i].ctypes.data, W, H, CH, 0, o.ctypes.data, o.size, 0, 0)
+            dec_items[jb] = D.DecodeItem(pin_out[i].ctypes.data, stream_bytes, -1, dd.ctypes.data, dd.size, 0, 0, 0, 0)
+        return n_jobs, enc_items, dec_items, outs, decs
+
+    def e2e_region(jobs):
+        n_jobs, enc_items, dec_items, outs, decs = jobs
         cod.flush_l2()
         sync_all()
-        wr, rd = sets[state["cur"]], sets[state["cur"] ^ 1]
-        for i in range(F):
-            enc_items[i] = D.EncodeItem(pin_img[i].ctypes.data, W, H, CH, 0, wr[i].ctypes.data, wr[i].size, 0, 0)
-            dec_items[i] = D.DecodeItem(rd[i].ctypes.data, state["lens"][i], -1, pin_dec[i].ctypes.data, pin_dec[i].size, 0, 0, 0, 0)
         t0 = time.perf_counter()
-        if dpool.run_items(enc_items, F, dec_items, F):
+        if dpool.run_items(enc_items, n_jobs, dec_items, n_jobs):
             raise RuntimeError("dwt_pool_run failed")
         dt = (time.perf_counter() - t0) * 1e3
-        state["lens"] = [enc_items[i].out_len for i in range(F)]
-        state["cur"] ^= 1
+        assert all(enc_items[jb].out_len == stream_bytes for jb in range(n_jobs)), "stream length changed"
         return dt
 
+    # warm-up: every context of the pool must have coded in both directions (buffers are allocated on first use):
+    # one call per direction with exactly one job per context, then mixed calls
+    warm_jobs = make_jobs(2)
+    assert dpool.encode_items(warm_jobs[1], 2 * F) == 0 and dpool.decode_items(warm_jobs[2], 2 * F) == 0
     for _ in range(max(1, args.warmup // 2)):
-        e2e_step()
+        e2e_region(warm_jobs)
+    jobs = make_jobs(args.steps)
     barrier()
-    e2e_ms = [e2e_step() for _ in range(args.steps)]
+    e2e_total = e2e_region(jobs)
     barrier()
     clocks = sampler.stop() if sampler else None
-    e2e_total = sum(e2e_ms)
-    assert np.array_equal(pin_dec[F - 1], pin_img[F - 1].reshape(-1)), "end-to-end round trip is not lossless"
+    assert np.array_equal(jobs[4][-1], pin_img[(jobs[0] - 1) % F].reshape(-1)), "end-to-end round trip is not lossless"
+    assert bytes(jobs[3][0][:stream_bytes]) == bytes(pin_out[0][:stream_bytes]), "end-to-end stream differs from the gate's"
     dpool.close()
 
     # ---- max over ranks
@@ -382,8 +394,8 @@ def our_bench(args, rank, world, local):
                e2e=dict(value=round(e2e_value, 2), unit="Mpixel/s", ms_per_step=round(e2e_total / args.steps, 3),
                         h2d_bytes_per_step=int(world * F * (img.size + stream_bytes)),
                         d2h_bytes_per_step=int(world * F * (stream_bytes + img.size)),
-                        api="dwt_pool_run: dwt_encode_into of %d frames + dwt_decode_into of the %d streams of the previous step, interleaved "
-                            "on %d contexts, page-locked host buffers" % (F, F, 2 * F)),
+                        api="dwt_pool_run: dwt_encode_into of %d frames + dwt_decode_into of %d streams per step, interleaved on %d contexts, "
+                            "page-locked host buffers, the K steps in one call" % (F, F, 2 * F)),
                gpu_launches=int(launches), clocks=clocks, roofline=roofline, stages=stages,
                single_frame=dict(ms_per_frame=round(statistics.median(serial_ms), 3),
                                  mpixel_s=round(npx / (statistics.median(serial_ms) / 1e3) / 1e6, 1),
