@@ -496,9 +496,20 @@ __global__ void __launch_bounds__(256) enc_scatter_kernel(const u32 *__restrict_
 	run_tokens(T, k, &mybits);
 	u64 tot;
 	u64 off = prefix_bits + tile_bitbase[tile] + block_exscan_u64(mybits, ws, &tot);
+	// chunk of the tile's first token: one binary search per block, the threads only walk forward from it
+	__shared__ int s_j0;
+	if (threadIdx.x == 0)
+		s_j0 = chunk_of_index(C->tok_start, J, tile * TT);
+	__syncthreads();
 	if (t0 >= ntok)
 		return;
-	int j = chunk_of_index(C->tok_start, J, t0);
+	int j = s_j0;
+	u32 next_start = j < J ? C->tok_start[j + 1] : 0xffffffffu; // first token of the next chunk
+	while (j < J && t0 >= next_start) {
+		++j;
+		next_start = j < J ? C->tok_start[j + 1] : 0xffffffffu;
+	}
+	u64 ref_start = C->ref_start[j];
 	// the codes of a thread's tokens are contiguous in the stream (except across a chunk's refinement block): they are
 	// gathered in a 64-bit window and sent with one atomic per 32-bit word instead of one or two per token
 	u64 acc = 0, acc_pos = 0;
@@ -518,8 +529,11 @@ __global__ void __launch_bounds__(256) enc_scatter_kernel(const u32 *__restrict_
 		const u32 kind = (T.kinds >> (2 * i)) & 3u;
 		if (kind == 3u)
 			break;
-		while (j < J && t >= C->tok_start[j + 1])
+		while (j < J && t >= next_start) {
 			++j;
+			next_start = j < J ? C->tok_start[j + 1] : 0xffffffffu;
+			ref_start = C->ref_start[j];
+		}
 		const u32 v = T.v[i];
 		int len = 0;
 		if (!(kind == 1u && v == 0)) {
@@ -532,7 +546,7 @@ __global__ void __launch_bounds__(256) enc_scatter_kernel(const u32 *__restrict_
 				code |= (u64)((T.signs >> i) & 1u) << len;
 				++len;
 			}
-			const u64 pos = off + C->ref_start[j];
+			const u64 pos = off + ref_start;
 			if (acc_len == 0 || pos != acc_pos + (u64)acc_len || acc_len + len > 64) {
 				flush();
 				acc_pos = pos;
@@ -543,9 +557,9 @@ __global__ void __launch_bounds__(256) enc_scatter_kernel(const u32 *__restrict_
 		}
 		off += len;
 		if (kind == 1u)
-			C->ref_pos[j] = off + C->ref_start[j]; // the chunk's refinement block starts right after the phantom one
+			C->ref_pos[j] = off + ref_start; // the chunk's refinement block starts right after the phantom one
 		if (kind == 2u)
-			info->total_bits = off + C->ref_start[j];
+			info->total_bits = off + ref_start;
 	}
 	flush();
 }
