@@ -287,6 +287,8 @@ def our_bench(args, rank, world, local):
         cod.event_record(1)
         return cod.event_elapsed_ms(0, 1)
 
+    for cd in cods:
+        cd.set_in_flight(F)   # F contexts are busy from here on (pass 1 ran with the default: one frame at a time)
     resident_region(args.warmup)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None

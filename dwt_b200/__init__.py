@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libdwt_b200.so")
 ABI_SYMBOLS = [
     "dwt_ctx_create", "dwt_ctx_destroy", "dwt_last_error", "dwt_encode", "dwt_decode", "dwt_free",
     "dwt_ctx_upload_image", "dwt_ctx_encode_resident", "dwt_ctx_download_stream", "dwt_ctx_upload_stream",
-    "dwt_ctx_decode_resident", "dwt_ctx_download_image", "dwt_ctx_launch_count", "dwt_ctx_sync",
+    "dwt_ctx_decode_resident", "dwt_ctx_download_image", "dwt_ctx_launch_count", "dwt_ctx_sync", "dwt_ctx_set_in_flight",
     "dwt_host_alloc", "dwt_host_free", "dwt_encode_into", "dwt_decode_into", "dwt_ctx_flush_l2",
     "dwt_ctx_event_record", "dwt_ctx_event_elapsed_ms", "dwt_ctx_wait_for",
     "dwt_pool_create", "dwt_pool_destroy", "dwt_pool_workers", "dwt_pool_encode", "dwt_pool_decode", "dwt_pool_run",
@@ -97,6 +97,7 @@ def lib():
     L.dwt_ctx_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int]
     L.dwt_ctx_event_elapsed_ms.restype = C.c_float
     L.dwt_ctx_wait_for.argtypes = [vp, vp]
+    L.dwt_ctx_set_in_flight.argtypes = [vp, C.c_int]
     L.dwt_pool_create.argtypes = [C.c_int, C.c_int]
     L.dwt_pool_create.restype = vp
     L.dwt_pool_destroy.argtypes = [vp]
@@ -261,6 +262,11 @@ class Codec:
 
     def event_elapsed_ms(self, a, b):
         return float(lib().dwt_ctx_event_elapsed_ms(self._h, a, b))
+
+    def set_in_flight(self, contexts):
+        """how many contexts the caller keeps busy on this device at once (throughput- vs latency-oriented kernels)"""
+        if lib().dwt_ctx_set_in_flight(self._h, int(contexts)):
+            raise DwtError("set_in_flight failed")
 
     def wait_for(self, other):
         """this context's stream waits for the work queued so far on `other`'s stream"""

@@ -362,6 +362,16 @@ struct dwt_pool {
 	std::vector<dwt_ctx *> ctx;
 };
 
+// How many contexts the caller keeps busy on this device at the same time (default 1).  With several frames in flight the
+// library prefers kernels that do less total work over kernels that finish one frame sooner (decoder scan).
+extern "C" int dwt_ctx_set_in_flight(dwt_ctx *c, int contexts)
+{
+	if (!c || contexts < 1)
+		return -1;
+	c->in_flight = contexts;
+	return 0;
+}
+
 extern "C" dwt_pool *dwt_pool_create(int device, int workers)
 {
 	if (workers < 1)
@@ -375,6 +385,7 @@ extern "C" dwt_pool *dwt_pool_create(int device, int workers)
 			delete p;
 			return nullptr;
 		}
+		c->in_flight = workers;
 		p->ctx.push_back(c);
 		p->device = c->device;
 	}

@@ -369,6 +369,104 @@ __global__ void __launch_bounds__(WS) dec_scan_kernel(const u32 *__restrict__ st
 	}
 }
 
+// The same tables, computed the other way round: ONE thread per (window, chain) walks its 512 slices serially from
+// the seed, so every token is decoded once per chain (the kernel above decodes it ~4.5 times: seeds, evaluation,
+// repairs, at 13 of 32 lanes).  A stream of a few MB has thousands of windows, which is all the parallelism a
+// latency-bound walk needs: the kernel takes ~512 x the latency of one slice (1.8 ms) whatever the stream size, uses a
+// third of the instructions and leaves the machine's issue slots to the kernels of other frames.  It is the scan of
+// choice when several frames are in flight (8K: +19 % frames per second with 8 contexts); alone on the GPU the parallel
+// kernel above is faster (1.1 ms).  Used when the caller announced >= DEC_SERIAL_MIN_IN_FLIGHT busy contexts
+// (dwt_ctx_set_in_flight; dwt_pool does) and the stream has >= DEC_SERIAL_MIN_WINDOWS windows.
+constexpr u32 DEC_SERIAL_MIN_WINDOWS = 2048;
+constexpr int DEC_SERIAL_MIN_IN_FLIGHT = 4;
+
+__global__ void __launch_bounds__(128) dec_scan_serial_kernel(const u32 *__restrict__ stream, u64 end_bits,
+                                                               const u32 *__restrict__ toklut, u32 nwin, u32 *E, ulonglong2 *P,
+                                                               u32 *TK, u32 *winX, ulonglong2 *winPT, u32 *winTT)
+{
+	__shared__ u32 lut[1 << LUT_BITS];
+	for (int i = threadIdx.x; i < (1 << LUT_BITS); i += 128)
+		lut[i] = __ldg(toklut + i);
+	__syncthreads();
+	const u32 t = blockIdx.x * 128 + threadIdx.x;
+	const u32 w = t >> 1, q = t & 1u;
+	if (w >= nwin)
+		return;
+	unsigned short *E16 = reinterpret_cast<unsigned short *>(E), *TK16 = reinterpret_cast<unsigned short *>(TK);
+	u64 *P64 = reinterpret_cast<u64 *>(P);
+	const u64 gs0 = (u64)w * WS;
+	auto word = [&](u64 slice) { return (slice << 6) < end_bits + 128 ? __ldg((const u64 *)stream + slice) : 0ull; };
+	u64 a = word(gs0), b = word(gs0 + 1), c = word(gs0 + 2), dnext = word(gs0 + 3); // two slices of look-ahead
+	// One flat loop over the token steps of the whole window: the lanes of a warp (different windows) do not wait for
+	// each other at slice boundaries, a lane that crosses one closes the slice and opens the next on the side.
+	int i = 0, d = (int)q, k = 0;
+	int avail = clamp_avail(end_bits, gs0 << 6);
+	bool lut_ok = avail >= 64 + LUT_BITS + 4;
+	u32 x = q;
+	u64 pm = 0, m = 0;  // members before the slice / inside it so far
+	u32 ptok = 0, n = 0;
+	E16[2 * gs0 + q] = (unsigned short)q;
+	P64[2 * gs0 + q] = 0;
+	TK16[2 * gs0 + q] = 0;
+	for (;;) {
+		bool dead = false;
+		const u32 bits = window32(a, b, d);
+		bool stepped = false;
+		if (k == 0 && lut_ok) {
+			const u32 t = lut[bits & ((1u << LUT_BITS) - 1u)];
+			if ((t & 15u) && d + (int)((t >> 4) & 15u) < 64) { // every token of the entry starts in this slice
+				d += (int)(t & 15u);
+				n += (t >> 8) & 7u;
+				m += t >> 11;
+				stepped = true;
+			}
+		}
+		if (!stepped) {
+			const int u = bits ? __ffs((int)bits) - 1 : 32;
+			const int e = k + u;
+			const int L = u + 1 + e;
+			if (e > 31 || d + L > avail) {
+				dead = true;
+			} else {
+				const u64 wv = bits_from(a, b, d);
+				const u32 payload = (u32)(wv >> (u + 1)) & ((1u << e) - 1u);
+				m += (u64)((1u << e) - (1u << k)) + payload + 1ull;
+				++n;
+				k = e >= 2 ? e - 2 : 0;
+				d += L + 1;
+			}
+		}
+		if (dead || d >= 64) { // the slice is finished
+			x = dead ? PDEAD : ((u32)(d - 64) | ((u32)k << 6));
+			pm += m + (dead ? DEATH : 0ull); // see dec_scan_kernel: a dead chain restarts at its seed offset
+			ptok += n;
+			m = 0;
+			n = 0;
+			if (++i == WS)
+				break;
+			if (dead) {
+				d = (int)q;
+				k = 0;
+			} else {
+				d -= 64;
+			}
+			const u64 gs = gs0 + i;
+			E16[2 * gs + q] = (unsigned short)((u32)d | ((u32)k << 6));
+			P64[2 * gs + q] = pm;
+			TK16[2 * gs + q] = (unsigned short)ptok;
+			a = b;
+			b = c;
+			c = dnext;
+			dnext = word(gs + 3);
+			avail = clamp_avail(end_bits, gs << 6);
+			lut_ok = avail >= 64 + LUT_BITS + 4;
+		}
+	}
+	reinterpret_cast<unsigned short *>(winX)[2 * w + q] = (unsigned short)x;
+	reinterpret_cast<u64 *>(winPT)[2 * w + q] = pm;
+	reinterpret_cast<unsigned short *>(winTT)[2 * w + q] = (unsigned short)ptok;
+}
+
 // ---------------------------------------------------------------------------------------------- link
 
 __global__ void __launch_bounds__(128) dec_link_kernel(const u32 *__restrict__ stream, u64 end_bits, u32 nwin,
@@ -1284,7 +1382,11 @@ void dec_token_table(u32 *host_table)
 
 int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b, int nchunks, cudaStream_t st, long long *launches)
 {
-	dec_scan_kernel<<<b.nwin, WS, 0, st>>>(b.stream, b.end_bits, b.toklut, b.E, b.P, b.TK, b.winX, b.winPT, b.winTT);
+	if (b.nwin >= DEC_SERIAL_MIN_WINDOWS && b.in_flight >= DEC_SERIAL_MIN_IN_FLIGHT)
+		dec_scan_serial_kernel<<<(2 * b.nwin + 127) / 128, 128, 0, st>>>(b.stream, b.end_bits, b.toklut, b.nwin, b.E, b.P, b.TK,
+		                                                                  b.winX, b.winPT, b.winTT);
+	else
+		dec_scan_kernel<<<b.nwin, WS, 0, st>>>(b.stream, b.end_bits, b.toklut, b.E, b.P, b.TK, b.winX, b.winPT, b.winTT);
 	dec_link_kernel<<<(2 * b.nwin + 127) / 128, 128, 0, st>>>(b.stream, b.end_bits, b.nwin, b.E, b.P, b.TK, b.winX, b.winPT,
 	                                                           b.winTT, b.link);
 	dec_resolve_kernel<<<1, 32, 0, st>>>(g, nchunks, b);

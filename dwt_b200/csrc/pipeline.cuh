@@ -52,6 +52,7 @@ struct dwt_ctx {
 	DevBuf dec_lut;    // decoder: order-0 token table
 	bool dec_lut_ready = false;
 	int sm_count = 1;
+	int in_flight = 1;   // contexts the caller keeps busy on this device (throughput- vs latency-oriented kernels)
 	PinBuf pin_small, pin_io, pin_stream;
 
 	// last encode result (device resident)

@@ -238,6 +238,7 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		b.toklut = c->dec_lut.as<u32>();
 		b.end_bits = end_bits;
 		b.nwin = (u32)nwin;
+		b.in_flight = c->in_flight;
 		char *sp = c->dec_scan.as<char>();
 		b.P = (ulonglong2 *)sp;
 		sp += nslice * 16;

@@ -76,6 +76,9 @@ int dwt_ctx_download_image(dwt_ctx *ctx, uint8_t **pixels, int *width, int *heig
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 long long dwt_ctx_launch_count(const dwt_ctx *ctx);
 int dwt_ctx_sync(dwt_ctx *ctx);
+/* number of contexts the caller keeps busy on this device at the same time (default 1; dwt_pool sets its worker count):
+ * with several frames in flight the library prefers kernels that do less total work over lower single-frame latency */
+int dwt_ctx_set_in_flight(dwt_ctx *ctx, int contexts);
 
 /* Caller-owned buffer variants of dwt_encode / dwt_decode (same semantics and return values; -1 with
  * *out_len = needed size when the buffer is too small).  With buffers from dwt_host_alloc() (page-locked

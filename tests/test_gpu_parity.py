@@ -255,6 +255,28 @@ def test_concurrent_contexts(oracle):
     assert not errors, errors
 
 
+def test_throughput_scan_matches_latency_scan(codec, oracle):
+    """the decoder has two scan kernels (parallel per window / one thread per window and chain, chosen by the in-flight
+    hint for streams of >= 2048 windows): both must give the same pixels, lossless and truncated"""
+    import dwt_b200 as D
+    img = oracle.synth(3840, 2160, "photo", 1)
+    s = codec.encode(img)
+    assert len(s) == 12216090  # 4K pin (SURVEY App. E.1): 2 983 scan windows
+    other = D.Codec(0)
+    other.set_in_flight(8)
+    try:
+        for cap in (len(s), len(s) - 1, len(s) // 2, 9_000_001, 70_000):
+            a, b = other.decode(s[:cap]), codec.decode(s[:cap])
+            assert a.shape == b.shape and np.array_equal(a, b), cap
+        assert np.array_equal(other.decode(s), img)
+        noise = oracle.synth(2048, 2048, "noise", 3)
+        sn = codec.encode(noise)
+        assert np.array_equal(other.decode(sn), noise)
+        assert np.array_equal(other.decode(sn[:len(sn) // 3]), codec.decode(sn[:len(sn) // 3]))
+    finally:
+        other.close()
+
+
 def test_pool_batch_matches_oracle(oracle):
     """dwt_pool: a batch of independent images of different sizes through 3 workers; streams, truncated streams
     and decoded pixels must equal the oracle's, item by item"""
