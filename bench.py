@@ -19,6 +19,10 @@ cores, on bands of the same frame (one process per band).
 import argparse
 import json
 import os
+
+# 8 + 16 codec contexts share the device: give every CUDA stream its own hardware queue (the default is 8 connections,
+# more streams than that get false dependencies).  Has to be set before CUDA is initialised.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import shutil
 import statistics
 import subprocess
@@ -303,7 +307,7 @@ def our_bench(args, rank, world, local):
     # inside the timed region.  The K steps are one call: K x F encode items (frames) + K x F decode items (the streams of
     # the parity gate), interleaved on the pool's contexts so that pixel uploads overlap pixel downloads.  Every job has
     # its own output buffer.
-    dpool = D.Pool(local, 2 * F)
+    dpool = D.Pool(local, args.pool_workers if args.pool_workers > 0 else 2 * F)
     out_room = stream_bytes + stream_bytes // 4 + 4096
 
     def make_jobs(k):
@@ -335,8 +339,9 @@ def our_bench(args, rank, world, local):
 
     # warm-up: every context of the pool must have coded in both directions (buffers are allocated on first use):
     # one call per direction with exactly one job per context, then mixed calls
-    warm_jobs = make_jobs(2)
-    assert dpool.encode_items(warm_jobs[1], 2 * F) == 0 and dpool.decode_items(warm_jobs[2], 2 * F) == 0
+    nwk = args.pool_workers if args.pool_workers > 0 else 2 * F
+    warm_jobs = make_jobs((nwk + F - 1) // F)
+    assert dpool.encode_items(warm_jobs[1], nwk) == 0 and dpool.decode_items(warm_jobs[2], nwk) == 0
     for _ in range(max(1, args.warmup // 2)):
         e2e_region(warm_jobs)
     jobs = make_jobs(args.steps)
@@ -421,6 +426,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pool-workers", type=int, default=0, help="contexts of the end-to-end pool (default 2 x frames)")
     ap.add_argument("--frames", type=int, default=8, help="frames per step, coded concurrently (one context each)")
     args = ap.parse_args()
     rank, world, local = dist_env()
