@@ -22,14 +22,15 @@ static dwt_ctx *default_ctx()
 }
 
 // root LL in ll[0] (planar, pitch w[0]) + details in pyr -> image
-int ctx_inverse_transform(dwt_ctx *c, int levels_used, bool to_u8, int *planar_out)
+int ctx_inverse_transform(dwt_ctx *c, int levels_used, bool to_u8, int *planar_out, bool counters_zeroed)
 {
 	const Geom &g = c->geom;
 	cudaStream_t st = c->st;
 	const int top = levels_used > 0 ? levels_used : 0;
 	const long long pyr_stride = g.pix[top];
 	const int pyr_pitch = g.w[top];
-	CUDA_OK(cudaMemsetAsync(c->small.as<int>() + 64, 0, 32 * sizeof(int), st)); // work counters of the level launches
+	if (!counters_zeroed && ctx_zero_transform_counters(c, false)) // work counters of the level launches
+		return -1;
 	if (levels_used == 0) {
 		// decode.c:258 with levels == 0 still runs one inverse level on the w0 x h0 root, reading the root
 		// itself as a one-level Mallat pyramid
@@ -97,6 +98,7 @@ int ctx_inverse_transform(dwt_ctx *c, int levels_used, bool to_u8, int *planar_o
 		p.pyr_pitch = pyr_pitch;
 		p.maxabs = nullptr;
 		p.work = c->small.as<int>() + 64 + lv;
+		p.chained = !(lv == first && cur == 0); // all but the first launch of the chain
 		int mode = 2;
 		if (lv == levels_used && to_u8) {
 			p.out = c->img.p;

@@ -21,6 +21,8 @@ struct LiftLevel {
 	int channels;
 	int *maxabs;               // forward only: per-channel max |detail| (atomicMax)
 	int *work;                 // zeroed device counter: work items are handed out dynamically
+	int chained = 0;           // 1 = the previous launch on the stream produced this level's input: launch as a
+	                           // programmatic dependent (its prologue overlaps the producer's drain)
 };
 
 // mode: 0 = u8 interleaved RGB with the colour transform fused (image.h:53-65 / 34-51),
@@ -42,6 +44,7 @@ struct LiftTail {
 	int pyr_pitch;
 	int W, H, nlev, channels;
 	int *maxabs;               // forward only
+	int chained = 0;           // as LiftLevel::chained
 };
 bool lift_tail_fits(int W, int H); // shared memory and lane budget of the fused kernel
 int lift_tail(const LiftTail &t, bool inverse, cudaStream_t st, long long *launches);

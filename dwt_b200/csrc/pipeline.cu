@@ -252,14 +252,26 @@ int ensure_transform_buffers(dwt_ctx *c)
 	return 0;
 }
 
-int ctx_forward_transform(dwt_ctx *c, const int *planar_in)
+int ctx_zero_transform_counters(dwt_ctx *c, bool forward)
+{
+	if (ensure_transform_buffers(c))
+		return -1;
+	// maxabs[4] at ints 0..3 and the work counters of the level launches at 64..95 (16..63 belong to the decoder)
+	if (forward)
+		CUDA_OK(cudaMemsetAsync(c->small.p, 0, 96 * sizeof(int), c->st));
+	else
+		CUDA_OK(cudaMemsetAsync(c->small.as<int>() + 64, 0, 32 * sizeof(int), c->st));
+	return 0;
+}
+
+int ctx_forward_transform(dwt_ctx *c, const int *planar_in, bool counters_zeroed)
 {
 	const Geom &g = c->geom;
 	const int L = g.levels;
 	if (ensure_transform_buffers(c))
 		return -1;
-	// maxabs[4] at ints 0..3 and the work counters of the level launches at 64..95 (16..63 belong to the decoder)
-	CUDA_OK(cudaMemsetAsync(c->small.p, 0, 96 * sizeof(int), c->st));
+	if (!counters_zeroed && ctx_zero_transform_counters(c, true))
+		return -1;
 	int cur = 0;
 	for (int lv = L; lv >= 1; --lv) {
 		if (lv < L && lift_tail_fits(g.w[lv], g.h[lv])) {
@@ -279,6 +291,7 @@ int ctx_forward_transform(dwt_ctx *c, const int *planar_in)
 			t.nlev = lv;
 			t.channels = g.channels;
 			t.maxabs = c->small.as<int>();
+			t.chained = 1; // behind the level kernel that wrote ll_in
 			if (lift_tail(t, false, c->st, &c->launches))
 				return -1;
 			c->root_buf = cur;
@@ -313,6 +326,7 @@ int ctx_forward_transform(dwt_ctx *c, const int *planar_in)
 		p.pyr_pitch = g.w[L];
 		p.maxabs = c->small.as<int>();
 		p.work = c->small.as<int>() + 64 + (L - lv);
+		p.chained = lv != L;
 		if (lift_forward_level(p, mode, c->st, &c->launches))
 			return -1;
 		c->root_buf = cur;
@@ -379,8 +393,10 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 	const Geom &g = c->geom;
 	const int C = g.channels, L = g.levels;
 	cudaStream_t st = c->st;
+	if (ctx_zero_transform_counters(c, true))
+		return -1;
 	CUDA_OK(cudaEventRecord(c->ev[0], st));
-	if (ctx_forward_transform(c, nullptr))
+	if (ctx_forward_transform(c, nullptr, true))
 		return -1;
 
 	// ---- plane counts and root image come back to the host (a few hundred bytes)

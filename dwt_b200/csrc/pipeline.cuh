@@ -66,8 +66,11 @@ struct dwt_ctx {
 int ctx_set_geometry(dwt_ctx *c, int w, int h, int ch);
 void build_schedule(const Geom &g, const int *planes, Sched *s);
 // img (or a planar int32 image when planar_in != NULL) -> pyr (+ root LL in an ll buffer), maxabs in small
-int ctx_forward_transform(dwt_ctx *c, const int *planar_in);
+// counters_zeroed: the caller already issued ctx_zero_transform_counters on the stream (keeps the small memset out of a
+// timed lifting region)
+int ctx_zero_transform_counters(dwt_ctx *c, bool forward);
+int ctx_forward_transform(dwt_ctx *c, const int *planar_in, bool counters_zeroed = false);
 // root LL in ll[0] + details in pyr (pitch w[levels_used]) -> u8 image in img (to_u8) or planar int32
-int ctx_inverse_transform(dwt_ctx *c, int levels_used, bool to_u8, int *planar_out);
+int ctx_inverse_transform(dwt_ctx *c, int levels_used, bool to_u8, int *planar_out, bool counters_zeroed = false);
 int ensure_transform_buffers(dwt_ctx *c);
 const int *ctx_root_ll(dwt_ctx *c);      // device pointer to the planar root LL after ctx_forward_transform

@@ -279,6 +279,8 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 	if (c->img.ensure((size_t)ow * oh * C + 16))
 		return -1;
 	CUDA_OK(cudaMemcpyAsync(c->ll[0].p, h_root, sizeof(int) * (size_t)nroot * C, cudaMemcpyHostToDevice, st));
+	if (ctx_zero_transform_counters(c, false))
+		return -1;
 	if (levels_used > 0) {
 		int *d_missing = c->small.as<int>() + 16;
 		CUDA_OK(cudaMemcpyAsync(d_missing, h_state->missing, sizeof(int) * 48, cudaMemcpyHostToDevice, st));
@@ -291,7 +293,7 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		}
 	}
 	CUDA_OK(cudaEventRecord(c->ev[2], st));
-	if (ctx_inverse_transform(c, levels_used, true, nullptr))
+	if (ctx_inverse_transform(c, levels_used, true, nullptr, true))
 		return -1;
 	CUDA_OK(cudaEventRecord(c->ev[3], st));
 	CUDA_OK(cudaStreamSynchronize(st));
