@@ -15,8 +15,6 @@
 #include "lift.cuh"
 
 #include <type_traits>
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -675,7 +673,7 @@ __device__ __forceinline__ int inv_o_at(FS S, FD D, int j, int N) // x[2j+1] (cd
 }
 
 constexpr int TAIL_THREADS = 1024;
-constexpr int TAIL_MAX_W = 128;      // wider levels have enough rows and strips to fill the machine
+constexpr int TAIL_MAX_W = 64;       // wider levels are faster as strip launches (short walks, dependent launches)
 constexpr int TAIL_MAX_INTS = 56000; // shared memory budget (both buffers), in ints
 
 __global__ void __launch_bounds__(TAIL_THREADS) lift_tail_fwd_kernel(LiftTail t)
@@ -842,235 +840,16 @@ __global__ void __launch_bounds__(TAIL_THREADS) lift_tail_inv_kernel(LiftTail t)
 	}
 }
 
-// ------------------------------------------------------------------------------------------------ cluster tail
-//
-// Levels between ~1000 and 128 columns are still latency bound as strip kernels (a warp walks its rows one after
-// the other, 7-10 us a level for microseconds of traffic).  A thread-block cluster per channel keeps such a level
-// resident in the DISTRIBUTED shared memory of its CTAs, split by rows: CTA r owns rows [r * rp, (r + 1) * rp) of
-// the current level (rp even, so row pairs never straddle CTAs).  Rows are lifted by their owner; the column step
-// of a CTA produces the rows it owns on the next level and reads the two or three halo rows it needs from its
-// neighbours' shared memory.  One cluster barrier per level.  Same arithmetic and order as the per-level kernels.
-
-constexpr int CT_QMAX = 8; // in-place rows: a lane keeps CT_QMAX pairs -> rows up to 512 samples
-
-__host__ __device__ __forceinline__ int ct_rows(int h, int nc) // rows per CTA of a level with h rows
+int resident_blocks()
 {
-	return 2 * ((h + 2 * nc - 1) / (2 * nc));
-}
-
-__global__ void __launch_bounds__(TAIL_THREADS) lift_ctail_fwd_kernel(LiftTail t, int big_ints)
-{
-	pdl_launch_dependents();
-	pdl_wait();
-	extern __shared__ int sm[];
-	__shared__ int smax;
-	cg::cluster_group cl = cg::this_cluster();
-	const int nc = (int)cl.num_blocks(), r = (int)cl.block_rank();
-	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	const int ch = blockIdx.x / nc;
-	int w = t.W, h = t.H;
-	int *src = sm, *dst = sm + big_ints;
-	int rp = ct_rows(h, nc);
-	if (tid == 0)
-		smax = 0;
-	{ // own rows of the finest level: lifted while they are loaded
-		const int *in = t.ll_in + (size_t)ch * t.in_chan_stride;
-		const int y0 = min(h, r * rp), y1 = min(h, y0 + rp), w2 = (w + 1) / 2;
-		for (int i = tid; i < (y1 - y0) * w2; i += TAIL_THREADS) {
-			const int yl = i / w2, k = i - yl * w2;
-			const int *row = in + (size_t)(y0 + yl) * t.in_pitch;
-			auto X = [&](int x) { return __ldg(row + x); };
-			src[yl * w + k] = fwd_s_at(X, 2 * k, w);
-			if (2 * k + 1 < w)
-				src[yl * w + w2 + k] = fwd_d_at(X, 2 * k + 1, w);
-		}
+	static int n = 0;
+	if (!n) {
+		int dev = 0, sms = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		n = (sms > 0 ? sms : 1) * 8;
 	}
-	cl.sync();
-	int *pyr = t.pyr + (size_t)ch * t.pyr_chan_stride;
-	int mx = 0;
-	for (int lev = 0;; ++lev) {
-		const int w2 = (w + 1) / 2, h2 = (h + 1) / 2;
-		const int rp2 = ct_rows(h2, nc);
-		const int j0 = min(h2, r * rp2), j1 = min(h2, j0 + rp2);
-		for (int i = tid; i < (j1 - j0) * w; i += TAIL_THREADS) { // columns: own LL rows -> dst, the rest -> pyramid
-			const int jl = i / w, x = i - jl * w, j = j0 + jl, yb = 2 * j - 2;
-			int v[5];
-#pragma unroll
-			for (int k = 0; k < 5; ++k) {
-				const int y = yb + k;
-				v[k] = 0;
-				if (y >= 0 && y < h) {
-					const int o = y / rp;
-					const int *base = o == r ? src : cl.map_shared_rank(src, o);
-					v[k] = base[(y - o * rp) * w + x];
-				}
-			}
-			auto X = [&](int y) {
-				const int k = y - yb;
-				return k == 0 ? v[0] : k == 1 ? v[1] : k == 2 ? v[2] : k == 3 ? v[3] : v[4];
-			};
-			const int S = fwd_s_at(X, 2 * j, h);
-			if (x < w2) {
-				dst[jl * w2 + x] = S;
-			} else {
-				pyr[(size_t)j * t.pyr_pitch + x] = S;
-				mx = max(mx, abs(S));
-			}
-			if (2 * j + 1 < h) {
-				const int D = fwd_d_at(X, 2 * j + 1, h);
-				pyr[(size_t)(h2 + j) * t.pyr_pitch + x] = D;
-				mx = max(mx, abs(D));
-			}
-		}
-		int *tmp = src;
-		src = dst;
-		dst = tmp;
-		w = w2;
-		h = h2;
-		rp = rp2;
-		if (lev == t.nlev - 1)
-			break;
-		__syncthreads();
-		{ // rows of the new level, in place (the CTA wrote them itself)
-			const int y0 = min(h, r * rp), y1 = min(h, y0 + rp), wh = (w + 1) / 2;
-			for (int yl = wid; yl < y1 - y0; yl += TAIL_THREADS / 32) {
-				int *row = src + yl * w;
-				auto X = [&](int i) { return row[i]; };
-				int sv[CT_QMAX], dv[CT_QMAX];
-#pragma unroll
-				for (int q = 0; q < CT_QMAX; ++q) {
-					const int i = lane + 32 * q;
-					sv[q] = 2 * i < w ? fwd_s_at(X, 2 * i, w) : 0;
-					dv[q] = 2 * i + 1 < w ? fwd_d_at(X, 2 * i + 1, w) : 0;
-				}
-				__syncwarp();
-#pragma unroll
-				for (int q = 0; q < CT_QMAX; ++q) {
-					const int i = lane + 32 * q;
-					if (2 * i < w)
-						row[i] = sv[q];
-					if (2 * i + 1 < w)
-						row[wh + i] = dv[q];
-				}
-			}
-		}
-		cl.sync();
-	}
-	__syncthreads();
-	{ // root: own rows
-		int *out = t.ll_out + (size_t)ch * t.out_chan_stride;
-		const int y0 = min(h, r * rp), y1 = min(h, y0 + rp);
-		for (int i = tid; i < (y1 - y0) * w; i += TAIL_THREADS) {
-			const int yl = i / w, x = i - yl * w;
-			out[(size_t)(y0 + yl) * t.out_pitch + x] = src[yl * w + x];
-		}
-	}
-	mx = __reduce_max_sync(FULLMASK, mx);
-	if (lane == 0 && mx > 0)
-		atomicMax(&smax, mx);
-	__syncthreads();
-	if (tid == 0 && smax > 0)
-		atomicMax(t.maxabs + ch, smax);
-	cl.sync(); // nobody leaves while a neighbour may still read its rows
-}
-
-__global__ void __launch_bounds__(TAIL_THREADS) lift_ctail_inv_kernel(LiftTail t, int big_ints)
-{
-	pdl_launch_dependents();
-	pdl_wait();
-	extern __shared__ int sm[];
-	cg::cluster_group cl = cg::this_cluster();
-	const int nc = (int)cl.num_blocks(), r = (int)cl.block_rank();
-	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	const int ch = blockIdx.x / nc;
-	int ws[DWT_MAX_LEVELS + 1], hs[DWT_MAX_LEVELS + 1];
-	ws[t.nlev] = t.W;
-	hs[t.nlev] = t.H;
-	for (int l = t.nlev; l > 0; --l) {
-		ws[l - 1] = (ws[l] + 1) / 2;
-		hs[l - 1] = (hs[l] + 1) / 2;
-	}
-	int *big = sm, *small = sm + big_ints;
-	int *cur = (t.nlev & 1) ? small : big; // buffers alternate so that the finest level lands in `big`
-	int pc = ws[0];
-	int rpc = ct_rows(hs[0], nc);
-	{ // root: own rows
-		const int *in = t.ll_in + (size_t)ch * t.in_chan_stride;
-		const int w = ws[0], h = hs[0];
-		const int y0 = min(h, r * rpc), y1 = min(h, y0 + rpc);
-		for (int i = tid; i < (y1 - y0) * w; i += TAIL_THREADS) {
-			const int yl = i / w, x = i - yl * w;
-			cur[yl * pc + x] = in[(size_t)(y0 + yl) * t.in_pitch + x];
-		}
-	}
-	cl.sync();
-	const int *pyr = t.pyr + (size_t)ch * t.pyr_chan_stride;
-	for (int lev = 1; lev <= t.nlev; ++lev) {
-		const int w = ws[lev], h = hs[lev], w2 = ws[lev - 1], h2 = hs[lev - 1];
-		int *nxt = cur == big ? small : big;
-		const int rp = ct_rows(h, nc), pn = w;
-		const int y0 = min(h, r * rp), y1 = min(h, y0 + rp);
-		const int j0 = y0 / 2, j1 = y0 < h ? (y1 + 1) / 2 : j0;
-		for (int i = tid; i < (j1 - j0) * w; i += TAIL_THREADS) { // columns (decode.c:21): the row pairs this CTA owns
-			const int jl = i / w, x = i - jl * w, j = j0 + jl;
-			auto ldS = [&](int m) {
-				if (x < w2) {
-					const int o = m / rpc;
-					const int *base = o == r ? cur : cl.map_shared_rank(cur, o);
-					return base[(m - o * rpc) * pc + x];
-				}
-				return __ldg(pyr + (size_t)m * t.pyr_pitch + x);
-			};
-			auto ldD = [&](int m) { return __ldg(pyr + (size_t)(h2 + m) * t.pyr_pitch + x); };
-			const int s0 = ldS(j), s1 = j + 1 < h2 ? ldS(j + 1) : 0;
-			const int dm = j >= 1 ? ldD(j - 1) : 0, d0 = 2 * j + 1 < h ? ldD(j) : 0, d1 = 2 * j + 3 < h ? ldD(j + 1) : 0;
-			auto S = [&](int m) { return m == j ? s0 : s1; };
-			auto D = [&](int m) { return m == j - 1 ? dm : m == j ? d0 : d1; };
-			nxt[(2 * jl) * pn + x] = inv_e_at(S, D, j, h);
-			if (2 * j + 1 < h)
-				nxt[(2 * jl + 1) * pn + x] = inv_o_at(S, D, j, h);
-		}
-		__syncthreads();
-		if (lev < t.nlev) { // rows, in place (decode.c:25-29)
-			for (int yl = wid; yl < y1 - y0; yl += TAIL_THREADS / 32) {
-				int *row = nxt + yl * pn;
-				auto S = [&](int m) { return row[m]; };
-				auto D = [&](int m) { return row[w2 + m]; };
-				int ev[CT_QMAX], ov[CT_QMAX];
-#pragma unroll
-				for (int q = 0; q < CT_QMAX; ++q) {
-					const int jj = lane + 32 * q;
-					ev[q] = 2 * jj < w ? inv_e_at(S, D, jj, w) : 0;
-					ov[q] = 2 * jj + 1 < w ? inv_o_at(S, D, jj, w) : 0;
-				}
-				__syncwarp();
-#pragma unroll
-				for (int q = 0; q < CT_QMAX; ++q) {
-					const int jj = lane + 32 * q;
-					if (2 * jj < w)
-						row[2 * jj] = ev[q];
-					if (2 * jj + 1 < w)
-						row[2 * jj + 1] = ov[q];
-				}
-			}
-		} else { // the finest level leaves shared memory row-lifted
-			int *out = t.ll_out + (size_t)ch * t.out_chan_stride;
-			for (int i = tid; i < (y1 - y0) * w2; i += TAIL_THREADS) {
-				const int yl = i / w2, jj = i - yl * w2;
-				const int *row = nxt + yl * pn;
-				auto S = [&](int m) { return row[m]; };
-				auto D = [&](int m) { return row[w2 + m]; };
-				int *o = out + (size_t)(y0 + yl) * t.out_pitch + 2 * jj;
-				o[0] = inv_e_at(S, D, jj, w);
-				if (2 * jj + 1 < w)
-					o[1] = inv_o_at(S, D, jj, w);
-			}
-		}
-		cl.sync();
-		cur = nxt;
-		pc = pn;
-		rpc = rp;
-	}
+	return n;
 }
 
 int pick_rows(int W, int H, int planes)
@@ -1079,6 +858,11 @@ int pick_rows(int W, int H, int planes)
 	long long strips = (W + STRIP_OUT - 1) / STRIP_OUT;
 	int rs = 64;
 	while (rs > 8 && strips * planes * ((H + rs - 1) / rs) < 8192)
+		rs >>= 1;
+	// a level small enough to give every item a resident warp is latency bound (a launch plus the dependent L2 round
+	// trips of one warp's walk): the shortest walk wins there, the extra halo rows cost nothing that matters
+	const long long cap = (long long)resident_blocks() * WARPS_PER_BLOCK;
+	while (rs <= 8 && rs > 2 && strips * planes * ((H + rs / 2 - 1) / (rs / 2)) <= cap)
 		rs >>= 1;
 	return rs;
 }
@@ -1178,17 +962,6 @@ static cudaError_t launch_chained(void (*k)(P...), dim3 grid, dim3 block, size_t
 	return cudaLaunchKernelEx(&cfg, k, a...);
 }
 
-static int resident_blocks()
-{
-	static int n = 0;
-	if (!n) {
-		int dev = 0, sms = 0;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		n = (sms > 0 ? sms : 1) * 8;
-	}
-	return n;
-}
 
 static LiftSched make_sched(const LiftLevel &lv, int planes, long long *items)
 {
@@ -1243,113 +1016,14 @@ int lift_inverse_level(const LiftLevel &lv, int mode, cudaStream_t st, long long
 	return 0;
 }
 
-namespace {
-
-constexpr size_t CT_SMEM_MAX = 200 * 1024;
-
-struct CtailCfg {
-	int nc = 0; // CTAs per cluster (one cluster per channel); 0 = no cluster kernel
-};
-
-// shared memory of one CTA: its rows of the finest level + its rows of the level below
-size_t ctail_smem(int W, int H, int nc, int *big_ints)
-{
-	const int w1 = (W + 1) / 2, h1 = (H + 1) / 2;
-	const size_t big = (size_t)ct_rows(H, nc) * W, small = (size_t)ct_rows(h1, nc) * w1;
-	if (big_ints)
-		*big_ints = (int)big;
-	return (big + small) * sizeof(int);
-}
-
-int ctail_launch(const LiftTail &t, bool inverse, int nc, cudaStream_t st, bool probe_only, int *max_clusters)
-{
-	int big = 0;
-	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3(t.channels * nc);
-	cfg.blockDim = dim3(TAIL_THREADS);
-	cfg.dynamicSmemBytes = probe_only ? CT_SMEM_MAX : ctail_smem(t.W, t.H, nc, &big);
-	cfg.stream = st;
-	cudaLaunchAttribute at[2];
-	at[0].id = cudaLaunchAttributeClusterDimension;
-	at[0].val.clusterDim.x = nc;
-	at[0].val.clusterDim.y = 1;
-	at[0].val.clusterDim.z = 1;
-	at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-	at[1].val.programmaticStreamSerializationAllowed = 1;
-	cfg.attrs = at;
-	cfg.numAttrs = !probe_only && t.chained ? 2 : 1;
-	if (probe_only)
-		return cudaOccupancyMaxActiveClusters(max_clusters, inverse ? lift_ctail_inv_kernel : lift_ctail_fwd_kernel, &cfg) ==
-		               cudaSuccess
-		           ? 0
-		           : -1;
-	CUDA_OK(cudaLaunchKernelEx(&cfg, inverse ? lift_ctail_inv_kernel : lift_ctail_fwd_kernel, t, big));
-	return 0;
-}
-
-// the largest cluster this device schedules with the full shared-memory budget (16 needs the non-portable opt-in)
-const CtailCfg &ctail_cfg()
-{
-	static CtailCfg cfg = [] {
-		CtailCfg c;
-		const char *env = getenv("DWT_CTAIL");
-		const int want = env ? atoi(env) : 0; // off unless asked for: slower than the strip kernels so far
-		if (want <= 0)
-			return c;
-		for (auto k : {lift_ctail_fwd_kernel, lift_ctail_inv_kernel}) {
-			if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM_MAX) != cudaSuccess ||
-			    cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-				cudaGetLastError();
-				return c;
-			}
-		}
-		LiftTail t = {};
-		t.channels = 3;
-		for (int nc : {16, 8, 4}) {
-			if (nc > want)
-				continue;
-			int n = 0;
-			if (ctail_launch(t, false, nc, 0, true, &n) == 0 && n >= 3 && ctail_launch(t, true, nc, 0, true, &n) == 0 &&
-			    n >= 3) {
-				c.nc = nc;
-				break;
-			}
-			cudaGetLastError();
-		}
-		return c;
-	}();
-	return cfg;
-}
-
-bool small_tail_fits(int W, int H)
+bool lift_tail_fits(int W, int H)
 {
 	const long long ints = (long long)W * H + (long long)((W + 1) / 2) * ((H + 1) / 2);
 	return W <= TAIL_MAX_W && ints <= TAIL_MAX_INTS;
 }
 
-bool ctail_fits(int W, int H)
-{
-	const int nc = ctail_cfg().nc;
-	return nc > 0 && (W + 1) / 2 <= 64 * CT_QMAX && // rows are lifted in place from the second level on
-	        ctail_smem(W, H, nc, nullptr) <= CT_SMEM_MAX;
-}
-
-} // namespace
-
-bool lift_tail_fits(int W, int H)
-{
-	return small_tail_fits(W, H) || ctail_fits(W, H);
-}
-
 int lift_tail(const LiftTail &t, bool inverse, cudaStream_t st, long long *launches)
 {
-	if (!small_tail_fits(t.W, t.H)) {
-		if (ctail_launch(t, inverse, ctail_cfg().nc, st, false, nullptr))
-			return -1;
-		if (launches)
-			++*launches;
-		return 0;
-	}
 	static bool configured = false;
 	const size_t smem = sizeof(int) * ((size_t)t.W * t.H + (size_t)((t.W + 1) / 2) * ((t.H + 1) / 2));
 	if (!configured) {
