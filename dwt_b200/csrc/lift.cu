@@ -854,10 +854,10 @@ int resident_blocks()
 
 int pick_rows(int W, int H, int planes)
 {
-	// aim for >= ~4k warps in flight; rows per segment even, 8..64
+	// aim for >= ~12k items (four per resident warp: measured best with dependent launches); rows per segment even
 	long long strips = (W + STRIP_OUT - 1) / STRIP_OUT;
 	int rs = 64;
-	while (rs > 8 && strips * planes * ((H + rs - 1) / rs) < 8192)
+	while (rs > 8 && strips * planes * ((H + rs - 1) / rs) < 12000)
 		rs >>= 1;
 	// a level small enough to give every item a resident warp is latency bound (a launch plus the dependent L2 round
 	// trips of one warp's walk): the shortest walk wins there, the extra halo rows cost nothing that matters
