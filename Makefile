@@ -11,7 +11,7 @@ CU      := $(CSRC)/lift.cu $(CSRC)/hilbert.cu $(CSRC)/coder_enc.cu $(CSRC)/coder
 OBJ     := $(CU:.cu=.o) dwt_b200/host/streamio.o
 HDR     := $(wildcard $(CSRC)/*.cuh) include/dwt_b200.h dwt_b200/host/streamio_internal.h
 
-all: $(LIB) encode decode oracle
+all: $(LIB) encode decode dwtbatch oracle
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(HDR)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; false)
@@ -27,12 +27,15 @@ encode: dwt_b200/host/encode.c dwt_b200/host/pnm.c $(LIB)
 	$(CC) $(CFLAGS) dwt_b200/host/encode.c dwt_b200/host/pnm.c -o $@ -Ldwt_b200 -ldwt_b200 -Wl,-rpath,'$$ORIGIN/dwt_b200'
 decode: dwt_b200/host/decode.c dwt_b200/host/pnm.c $(LIB)
 	$(CC) $(CFLAGS) dwt_b200/host/decode.c dwt_b200/host/pnm.c -o $@ -Ldwt_b200 -ldwt_b200 -Wl,-rpath,'$$ORIGIN/dwt_b200'
+# many images per process on a pool of contexts (no reference counterpart: SURVEY.md 8f-3)
+dwtbatch: dwt_b200/host/batch.c dwt_b200/host/pnm.c $(LIB)
+	$(CC) $(CFLAGS) dwt_b200/host/batch.c dwt_b200/host/pnm.c -o $@ -Ldwt_b200 -ldwt_b200 -Wl,-rpath,'$$ORIGIN/dwt_b200'
 
 oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -f $(OBJ) $(CSRC)/*.ptxas.log $(LIB) encode decode
+	rm -f $(OBJ) $(CSRC)/*.ptxas.log $(LIB) encode decode dwtbatch
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

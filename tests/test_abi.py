@@ -171,3 +171,11 @@ def test_cli_usage_and_rejections(built, tmp_path):
     bad.write_bytes(b"hello")
     r = subprocess.run([enc, str(bad), str(out)], capture_output=True)
     assert r.returncode == 1 and not out.exists()
+
+
+def test_batch_cli_usage(built):
+    tool = os.path.join(ROOT, "dwtbatch")
+    assert os.path.exists(tool)
+    for argv in ([tool], [tool, "transcode", "out"], [tool, "encode"], [tool, "encode", "-j", "0", "out"]):
+        r = subprocess.run(argv, capture_output=True)
+        assert r.returncode == 1 and b"usage:" in r.stderr and b"OUTDIR" in r.stderr

@@ -337,3 +337,50 @@ def test_cli_roundtrip_matches_reference_behaviour(codec, oracle, tmp_path):
     gone = tmp_path / "none.pnm"
     r = subprocess.run([dec, str(tmp_path / "short.dwt"), str(gone)], capture_output=True)
     assert r.returncode == 1 and not gone.exists()
+
+
+def test_batch_cli_matches_per_file_programs(oracle, tmp_path):
+    """dwtbatch codes every file exactly as encode / decode would"""
+    tool = os.path.join(ROOT, "dwtbatch")
+    src, enc_dir, dec_dir = tmp_path / "src", tmp_path / "enc", tmp_path / "dec"
+    for d in (src, enc_dir, dec_dir):
+        d.mkdir()
+    imgs = {}
+    for i, (w, h, kind) in enumerate([(320, 240, "photo"), (133, 100, "noise"), (640, 360, "photo"), (64, 48, "photo"),
+                                      (257, 255, "noise"), (1920, 1080, "photo"), (96, 96, "gray")]):
+        if kind == "gray":
+            img = oracle.synth(w, h, "photo", 40 + i)[:, :, 1].copy()
+            hdr = b"P5\n%d %d\n255\n" % (w, h)
+        else:
+            img = oracle.synth(w, h, kind, 40 + i)
+            hdr = b"P6\n%d %d\n255\n" % (w, h)
+        imgs["im%d" % i] = img
+        (src / ("im%d.pnm" % i)).write_bytes(hdr + img.tobytes())
+    (src / "bad.pnm").write_bytes(b"P6\n4 4\n255\n" + bytes(48))  # rejected: smaller than 8x8 (encode.c:144-146)
+    names = sorted(str(p) for p in src.iterdir())
+    r = subprocess.run([tool, "encode", "-j", "3", str(enc_dir)] + names, capture_output=True)
+    assert r.returncode == 1 and b"1 of %d files failed" % len(names) in r.stderr, r.stderr
+    assert not (enc_dir / "bad.dwt").exists()
+    for k, img in imgs.items():
+        assert (enc_dir / (k + ".dwt")).read_bytes() == oracle.encode(img)[0], k
+    # capacity for every file, paths on stdin
+    cap_dir = tmp_path / "cap"
+    cap_dir.mkdir()
+    good = [n for n in names if not n.endswith("bad.pnm")]
+    r = subprocess.run([tool, "encode", "-c", "3000", str(cap_dir)], input="\n".join(good).encode(), capture_output=True)
+    assert r.returncode == 0, r.stderr
+    for k, img in imgs.items():
+        assert (cap_dir / (k + ".dwt")).read_bytes() == oracle.encode(img, 3000)[0], k
+    # decode: full streams, then truncated streams with a PIXELS bound
+    r = subprocess.run([tool, "decode", str(dec_dir)] + sorted(str(p) for p in enc_dir.iterdir()), capture_output=True)
+    assert r.returncode == 0, r.stderr
+    for k, img in imgs.items():
+        assert (dec_dir / (k + ".pnm")).read_bytes() == oracle.pnm_bytes(img), k
+    low_dir = tmp_path / "low"
+    low_dir.mkdir()
+    r = subprocess.run([tool, "decode", "-p", "20000", "-j", "2", str(low_dir)] + sorted(str(p) for p in cap_dir.iterdir()),
+                       capture_output=True)
+    assert r.returncode == 0, r.stderr
+    for k, img in imgs.items():
+        want = oracle.pnm_bytes(oracle.decode(oracle.encode(img, 3000)[0], 20000))
+        assert (low_dir / (k + ".pnm")).read_bytes() == want, k
