@@ -322,7 +322,7 @@ extern "C" int dwt_encode_into(dwt_ctx *c, const uint8_t *pixels, int width, int
 	}
 	if (c->out_bytes) {
 		CUDA_OK(cudaMemcpyAsync(out, c->out.p, c->out_bytes, cudaMemcpyDeviceToHost, c->st));
-		CUDA_OK(cudaStreamSynchronize(c->st));
+		CUDA_OK(ctx_stream_sync(c));
 	}
 	*out_len = c->out_bytes;
 	return 0;
@@ -349,7 +349,7 @@ extern "C" int dwt_decode_into(dwt_ctx *c, const uint8_t *stream, size_t len, in
 		return -1;
 	}
 	CUDA_OK(cudaMemcpyAsync(pixels, c->img.p, n, cudaMemcpyDeviceToHost, c->st));
-	CUDA_OK(cudaStreamSynchronize(c->st));
+	CUDA_OK(ctx_stream_sync(c));
 	return 0;
 }
 

@@ -10,6 +10,7 @@
 #include "../host/streamio_internal.h"
 #include "dwt_b200.h"
 
+#include <sched.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -105,8 +106,28 @@ extern "C" dwt_ctx *dwt_ctx_create(int device)
 	}
 	for (auto &e : c->ev)
 		cudaEventCreate(&e);
+	cudaEventCreateWithFlags(&c->sync_ev, cudaEventDisableTiming);
 	c->plan.cell_base = nullptr;
 	return c;
+}
+
+cudaError_t ctx_stream_sync(dwt_ctx *c)
+{
+	// DWT_SYNC=spin: plain cudaStreamSynchronize; default: poll an event and give the core away between polls once the
+	// wait is longer than a short spin
+	static const bool plain = getenv("DWT_SYNC") && !strcmp(getenv("DWT_SYNC"), "spin");
+	if (plain || !c->sync_ev)
+		return cudaStreamSynchronize(c->st);
+	cudaError_t e = cudaEventRecord(c->sync_ev, c->st);
+	if (e != cudaSuccess)
+		return e;
+	for (int polls = 0;; ++polls) {
+		e = cudaEventQuery(c->sync_ev);
+		if (e != cudaErrorNotReady)
+			return e;
+		if (polls >= 64)
+			sched_yield();
+	}
 }
 
 extern "C" void dwt_ctx_destroy(dwt_ctx *c)
@@ -407,7 +428,7 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 	CUDA_OK(cudaEventRecord(c->ev[1], st)); // ev0..ev1 = the lifting kernels only
 	CUDA_OK(cudaMemcpyAsync(h_small, c->small.p, 16, cudaMemcpyDeviceToHost, st));
 	CUDA_OK(cudaMemcpyAsync(h_small + 4, ctx_root_ll(c), sizeof(int) * nroot, cudaMemcpyDeviceToHost, st));
-	CUDA_OK(cudaStreamSynchronize(st));
+	CUDA_OK(ctx_stream_sync(c));
 	int planes[3] = {0, 0, 0}, planes_max = 0;
 	for (int ch = 0; ch < C; ++ch) {
 		planes[ch] = 1 + ilog2(h_small[ch]); // encode.c:130
@@ -529,7 +550,7 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 		EncInfo *h_info = (EncInfo *)(h_small + 4 + nroot + 2);
 		h_info = (EncInfo *)(((uintptr_t)h_info + 15) & ~(uintptr_t)15);
 		CUDA_OK(cudaMemcpyAsync(h_info, b.info, sizeof(EncInfo), cudaMemcpyDeviceToHost, st));
-		CUDA_OK(cudaStreamSynchronize(st));
+		CUDA_OK(ctx_stream_sync(c));
 		if (h_info->error) {
 			dwt_set_error("coder: input outside the supported range (code %d)", h_info->error);
 			return -1;
@@ -565,7 +586,7 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 		c->out_bytes = out_bytes;
 	}
 	CUDA_OK(cudaEventRecord(c->ev[3], st));
-	CUDA_OK(cudaStreamSynchronize(st));
+	CUDA_OK(ctx_stream_sync(c));
 	close_bytes_writer(bw);
 
 	if (stt) {
@@ -602,7 +623,7 @@ extern "C" int dwt_ctx_download_stream(dwt_ctx *c, uint8_t **out, size_t *out_le
 	}
 	if (c->out_bytes) {
 		CUDA_OK(cudaMemcpyAsync(buf, c->out.p, c->out_bytes, cudaMemcpyDeviceToHost, c->st));
-		CUDA_OK(cudaStreamSynchronize(c->st));
+		CUDA_OK(ctx_stream_sync(c));
 	}
 	*out = buf;
 	*out_len = c->out_bytes;
@@ -639,7 +660,7 @@ extern "C" int dwt_debug_front_end(dwt_ctx *c, const uint8_t *pixels, int width,
 		return -1;
 	int h_max[4];
 	CUDA_OK(cudaMemcpyAsync(h_max, c->small.p, 16, cudaMemcpyDeviceToHost, st));
-	CUDA_OK(cudaStreamSynchronize(st));
+	CUDA_OK(ctx_stream_sync(c));
 	int planes[3] = {0, 0, 0};
 	for (int ch = 0; ch < C; ++ch)
 		planes[ch] = 1 + ilog2(h_max[ch]);
@@ -653,7 +674,7 @@ extern "C" int dwt_debug_front_end(dwt_ctx *c, const uint8_t *pixels, int width,
 		export_pyramid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->pyr.as<int>(), ctx_root_ll(c), tmp, g.w[L],
 		                                                                   g.h[L], C, g.w[0], g.h[0]);
 		CUDA_OK(cudaMemcpyAsync(pyramid, tmp, n * sizeof(int), cudaMemcpyDeviceToHost, st));
-		CUDA_OK(cudaStreamSynchronize(st));
+		CUDA_OK(ctx_stream_sync(c));
 	}
 	if (planar) {
 		build_schedule(g, planes, &c->sched);
@@ -675,7 +696,7 @@ extern "C" int dwt_debug_front_end(dwt_ctx *c, const uint8_t *pixels, int width,
 			CUDA_OK(cudaMemcpyAsync(tmp + (size_t)ch * npix, ctx_root_ll(c) + (size_t)ch * g.pix[0],
 			                        sizeof(int) * g.pix[0], cudaMemcpyDeviceToDevice, st));
 		CUDA_OK(cudaMemcpyAsync(planar, tmp, n * sizeof(int), cudaMemcpyDeviceToHost, st));
-		CUDA_OK(cudaStreamSynchronize(st));
+		CUDA_OK(ctx_stream_sync(c));
 	}
 	cudaFree(tmp);
 	return 0;

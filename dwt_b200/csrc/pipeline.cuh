@@ -29,6 +29,7 @@ struct dwt_ctx {
 	cudaStream_t st = nullptr;
 	long long launches = 0;
 	cudaEvent_t ev[9] = {};   // 0..3 stage timers, 4..7 caller slots, 8 cross-context waits
+	cudaEvent_t sync_ev = nullptr; // polled by ctx_stream_sync
 
 	// geometry cache
 	bool have_geom = false;
@@ -73,4 +74,7 @@ int ctx_forward_transform(dwt_ctx *c, const int *planar_in, bool counters_zeroed
 // root LL in ll[0] + details in pyr (pitch w[levels_used]) -> u8 image in img (to_u8) or planar int32
 int ctx_inverse_transform(dwt_ctx *c, int levels_used, bool to_u8, int *planar_out, bool counters_zeroed = false);
 int ensure_transform_buffers(dwt_ctx *c);
+// wait for the context's stream by polling an event and yielding the core between polls: a pool's threads (and the ranks of
+// a multi-GPU job) outnumber the cores, and a waiter that spins inside the driver takes the core a launching thread needs
+cudaError_t ctx_stream_sync(dwt_ctx *c);
 const int *ctx_root_ll(dwt_ctx *c);      // device pointer to the planar root LL after ctx_forward_transform

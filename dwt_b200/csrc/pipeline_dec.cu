@@ -45,7 +45,7 @@ extern "C" int dwt_ctx_upload_stream(dwt_ctx *c, const uint8_t *stream, size_t l
 	if (len) {
 		memcpy(c->pin_stream.p, stream, head);
 		CUDA_OK(cudaMemcpyAsync(c->stream.p, stream, len, cudaMemcpyHostToDevice, c->st));
-		CUDA_OK(cudaStreamSynchronize(c->st)); // the caller's buffer is free again when this returns
+		CUDA_OK(ctx_stream_sync(c)); // the caller's buffer is free again when this returns
 	}
 	c->stream_head = head;
 	c->stream_len = len;
@@ -222,7 +222,7 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 			if (c->dec_lut.ensure(sizeof(table)))
 				return -1;
 			CUDA_OK(cudaMemcpyAsync(c->dec_lut.p, table, sizeof(table), cudaMemcpyHostToDevice, st));
-			CUDA_OK(cudaStreamSynchronize(st));
+			CUDA_OK(ctx_stream_sync(c));
 			c->dec_lut_ready = true;
 		}
 		CUDA_OK(cudaMemsetAsync(c->bs.p, 0, bs_words * 4, st));
@@ -265,7 +265,7 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 			return -1;
 		CUDA_OK(cudaMemcpyAsync(h_state, c->dstate.p, sizeof(DecState), cudaMemcpyDeviceToHost, st));
 		CUDA_OK(cudaEventRecord(c->ev[1], st));
-		CUDA_OK(cudaStreamSynchronize(st));
+		CUDA_OK(ctx_stream_sync(c));
 		level = h_state->level;
 	}
 	if (planes_max == 0 || nchunks == 0)
@@ -296,7 +296,7 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 	if (ctx_inverse_transform(c, levels_used, true, nullptr, true))
 		return -1;
 	CUDA_OK(cudaEventRecord(c->ev[3], st));
-	CUDA_OK(cudaStreamSynchronize(st));
+	CUDA_OK(ctx_stream_sync(c));
 	c->dec_w = ow;
 	c->dec_h = oh;
 	c->dec_ch = C;
@@ -336,7 +336,7 @@ extern "C" int dwt_ctx_download_image(dwt_ctx *c, uint8_t **pixels, int *width, 
 		return -1;
 	}
 	CUDA_OK(cudaMemcpyAsync(buf, c->img.p, n, cudaMemcpyDeviceToHost, c->st));
-	CUDA_OK(cudaStreamSynchronize(c->st));
+	CUDA_OK(ctx_stream_sync(c));
 	*pixels = buf;
 	*width = c->dec_w;
 	*height = c->dec_h;
