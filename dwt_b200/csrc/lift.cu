@@ -14,6 +14,7 @@
 //   of a warp is one contiguous row segment.
 #include "lift.cuh"
 
+#include <atomic>
 #include <type_traits>
 
 namespace {
@@ -1024,14 +1025,17 @@ bool lift_tail_fits(int W, int H)
 
 int lift_tail(const LiftTail &t, bool inverse, cudaStream_t st, long long *launches)
 {
-	static bool configured = false;
+	static std::atomic<unsigned long long> configured{0}; // one bit per device: the attribute is per device
 	const size_t smem = sizeof(int) * ((size_t)t.W * t.H + (size_t)((t.W + 1) / 2) * ((t.H + 1) / 2));
-	if (!configured) {
+	int dev = 0;
+	CUDA_OK(cudaGetDevice(&dev));
+	const unsigned long long bit = 1ull << (dev & 63);
+	if (!(configured.load(std::memory_order_acquire) & bit)) {
 		CUDA_OK(cudaFuncSetAttribute(lift_tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                             (int)(TAIL_MAX_INTS * sizeof(int))));
 		CUDA_OK(cudaFuncSetAttribute(lift_tail_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                             (int)(TAIL_MAX_INTS * sizeof(int))));
-		configured = true;
+		configured.fetch_or(bit, std::memory_order_release);
 	}
 	CUDA_OK(launch_chained(inverse ? lift_tail_inv_kernel : lift_tail_fwd_kernel, t.channels, TAIL_THREADS, smem, st, t.chained, t));
 	if (launches)
