@@ -384,3 +384,21 @@ def test_batch_cli_matches_per_file_programs(oracle, tmp_path):
     for k, img in imgs.items():
         want = oracle.pnm_bytes(oracle.decode(oracle.encode(img, 3000)[0], 20000))
         assert (low_dir / (k + ".pnm")).read_bytes() == want, k
+
+
+@pytest.mark.parametrize("shape", [(4096, 8), (8, 4096), (4096, 17), (2500, 9)])
+def test_thin_strips(codec, oracle, shape):
+    """one dimension at the minimum: a single level whose Hilbert square is mostly empty (the reference walks all of it,
+    which is why this stays at 4096: its time grows with the square of the longer side, and 65536 overflows its int counters)"""
+    w, h = shape
+    img = oracle.synth(w, h, "photo", 7)
+    want, st = oracle.encode(img)
+    assert codec.encode(img) == want
+    assert np.array_equal(codec.decode(want), img)
+    cap = len(want) // 3
+    assert codec.encode(img, cap) == want[:cap]
+    for cut, pm in [(cap, -1), (len(want) - 5, -1), (len(want), 10000)]:
+        a, b = codec.decode(want[:cut], pm), oracle.decode(want[:cut], pm)
+        assert (a is None) == (b is None)  # the root image of a strip is large: a cut inside it is "exit 1, no output"
+        if a is not None:
+            assert a.shape == b.shape and np.array_equal(a, b)
