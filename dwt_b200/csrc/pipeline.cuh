@@ -74,7 +74,6 @@ int ctx_forward_transform(dwt_ctx *c, const int *planar_in, bool counters_zeroed
 // root LL in ll[0] + details in pyr (pitch w[levels_used]) -> u8 image in img (to_u8) or planar int32
 int ctx_inverse_transform(dwt_ctx *c, int levels_used, bool to_u8, int *planar_out, bool counters_zeroed = false);
 int ensure_transform_buffers(dwt_ctx *c);
-// wait for the context's stream by polling an event and yielding the core between polls: a pool's threads (and the ranks of
-// a multi-GPU job) outnumber the cores, and a waiter that spins inside the driver takes the core a launching thread needs
+// wait for the context's stream (cudaStreamSynchronize; with DWT_SYNC=poll an event poll that yields the core between polls)
 cudaError_t ctx_stream_sync(dwt_ctx *c);
 const int *ctx_root_ll(dwt_ctx *c);      // device pointer to the planar root LL after ctx_forward_transform
