@@ -310,8 +310,7 @@ def our_bench(args, rank, world, local):
     dpool = D.Pool(local, args.pool_workers if args.pool_workers > 0 else 2 * F)
     out_room = stream_bytes + stream_bytes // 4 + 4096
 
-    def make_jobs(k):
-        n_jobs = k * F
+    def make_jobs(n_jobs):
         enc_items = (D.EncodeItem * n_jobs)()
         dec_items = (D.DecodeItem * n_jobs)()
         outs, decs = [], []
@@ -326,8 +325,9 @@ def our_bench(args, rank, world, local):
             dec_items[jb] = D.DecodeItem(pin_out[i].ctypes.data, stream_bytes, -1, dd.ctypes.data, dd.size, 0, 0, 0, 0)
         return n_jobs, enc_items, dec_items, outs, decs
 
-    def e2e_region(jobs):
-        n_jobs, enc_items, dec_items, outs, decs = jobs
+    def e2e_region(jobs, n_jobs=None):
+        n_all, enc_items, dec_items, outs, decs = jobs
+        n_jobs = n_all if n_jobs is None else n_jobs
         cod.flush_l2()
         sync_all()
         t0 = time.perf_counter()
@@ -340,13 +340,20 @@ def our_bench(args, rank, world, local):
     # warm-up: every context of the pool must have coded in both directions (buffers are allocated on first use):
     # one call per direction with exactly one job per context, then mixed calls
     nwk = args.pool_workers if args.pool_workers > 0 else 2 * F
-    warm_jobs = make_jobs((nwk + F - 1) // F)
+    warm_jobs = make_jobs((nwk + F - 1) // F * F)
     assert dpool.encode_items(warm_jobs[1], nwk) == 0 and dpool.decode_items(warm_jobs[2], nwk) == 0
     for _ in range(max(1, args.warmup // 2)):
         e2e_region(warm_jobs)
-    jobs = make_jobs(args.steps)
+    # one call for the K steps; a long run (large --steps) is cut into calls of <= ~8 GB of page-locked job buffers, which are
+    # reused from call to call (every call still carries all of its copies; only the drain between calls is extra)
+    total_jobs = args.steps * F
+    jobs = make_jobs(min(total_jobs, max(2 * nwk, int(8e9) // (out_room + img.size))))
     barrier()
-    e2e_total = e2e_region(jobs)
+    e2e_total, done = 0.0, 0
+    while done < total_jobs:
+        n = min(jobs[0], total_jobs - done)
+        e2e_total += e2e_region(jobs, n)
+        done += n
     barrier()
     clocks = sampler.stop() if sampler else None
     assert np.array_equal(jobs[4][-1], pin_img[(jobs[0] - 1) % F].reshape(-1)), "end-to-end round trip is not lossless"
