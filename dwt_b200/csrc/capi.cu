@@ -321,8 +321,7 @@ extern "C" int dwt_encode_into(dwt_ctx *c, const uint8_t *pixels, int width, int
 		return -1;
 	}
 	if (c->out_bytes) {
-		CUDA_OK(cudaMemcpyAsync(out, c->out.p, c->out_bytes, cudaMemcpyDeviceToHost, c->st));
-		CUDA_OK(ctx_stream_sync(c));
+		CUDA_OK(ctx_copy(c, out, c->out.p, c->out_bytes, cudaMemcpyDeviceToHost, true));
 	}
 	*out_len = c->out_bytes;
 	return 0;
@@ -348,8 +347,7 @@ extern "C" int dwt_decode_into(dwt_ctx *c, const uint8_t *stream, size_t len, in
 		dwt_set_error("pixel buffer too small: need %zu bytes", n);
 		return -1;
 	}
-	CUDA_OK(cudaMemcpyAsync(pixels, c->img.p, n, cudaMemcpyDeviceToHost, c->st));
-	CUDA_OK(ctx_stream_sync(c));
+	CUDA_OK(ctx_copy(c, pixels, c->img.p, n, cudaMemcpyDeviceToHost, true));
 	return 0;
 }
 
@@ -362,6 +360,7 @@ extern "C" int dwt_decode_into(dwt_ctx *c, const uint8_t *stream, size_t len, in
 struct dwt_pool {
 	int device = 0;
 	std::vector<dwt_ctx *> ctx;
+	XferGate gate; // shared by the contexts: one large copy per direction at a time
 };
 
 // How many contexts the caller keeps busy on this device at the same time (default 1).  With several frames in flight the
@@ -388,6 +387,7 @@ extern "C" dwt_pool *dwt_pool_create(int device, int workers)
 			return nullptr;
 		}
 		c->in_flight = workers;
+		c->gate = workers > 1 ? &p->gate : nullptr;
 		p->ctx.push_back(c);
 		p->device = c->device;
 	}

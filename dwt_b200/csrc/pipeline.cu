@@ -131,6 +131,24 @@ cudaError_t ctx_stream_sync(dwt_ctx *c)
 	}
 }
 
+cudaError_t ctx_copy(dwt_ctx *c, void *dst, const void *src, size_t n, cudaMemcpyKind kind, bool wait)
+{
+	static const bool ungated = getenv("DWT_XFER_GATE") && !strcmp(getenv("DWT_XFER_GATE"), "0");
+	if (!c->gate || ungated || n < (1u << 20)) {
+		cudaError_t e = cudaMemcpyAsync(dst, src, n, kind, c->st);
+		return e == cudaSuccess && wait ? ctx_stream_sync(c) : e;
+	}
+	const bool down = kind == cudaMemcpyDeviceToHost;
+	if (down) {
+		cudaError_t e = ctx_stream_sync(c);
+		if (e != cudaSuccess)
+			return e;
+	}
+	std::lock_guard<std::mutex> hold(c->gate->dir[down ? 1 : 0]);
+	cudaError_t e = cudaMemcpyAsync(dst, src, n, kind, c->st);
+	return e == cudaSuccess ? ctx_stream_sync(c) : e;
+}
+
 extern "C" void dwt_ctx_destroy(dwt_ctx *c)
 {
 	if (!c)
@@ -380,7 +398,7 @@ extern "C" int dwt_ctx_upload_image(dwt_ctx *c, const uint8_t *pixels, int width
 	size_t n = (size_t)width * height * channels;
 	if (c->img.ensure(n + 16))
 		return -1;
-	CUDA_OK(cudaMemcpyAsync(c->img.p, pixels, n, cudaMemcpyHostToDevice, c->st));
+	CUDA_OK(ctx_copy(c, c->img.p, pixels, n, cudaMemcpyHostToDevice, false));
 	c->img_w = width;
 	c->img_h = height;
 	c->img_ch = channels;

@@ -1,5 +1,6 @@
 // pipeline.cuh -- the per-device codec context (host orchestration of the kernels)
 #pragma once
+#include <mutex>
 #include "coder.cuh"
 #include "hilbert.cuh"
 #include "lift.cuh"
@@ -29,6 +30,7 @@ struct dwt_ctx {
 	cudaStream_t st = nullptr;
 	long long launches = 0;
 	cudaEvent_t ev[9] = {};   // 0..3 stage timers, 4..7 caller slots, 8 cross-context waits
+	struct XferGate *gate = nullptr; // set by a pool: see ctx_copy
 	cudaEvent_t sync_ev = nullptr; // polled by ctx_stream_sync
 
 	// geometry cache
@@ -74,6 +76,15 @@ int ctx_forward_transform(dwt_ctx *c, const int *planar_in, bool counters_zeroed
 // root LL in ll[0] + details in pyr (pitch w[levels_used]) -> u8 image in img (to_u8) or planar int32
 int ctx_inverse_transform(dwt_ctx *c, int levels_used, bool to_u8, int *planar_out, bool counters_zeroed = false);
 int ensure_transform_buffers(dwt_ctx *c);
+// One large host<->device copy per direction at a time among the contexts of a pool: copies issued together share the link,
+// so every job of a batch would get its data only when all of them have it (an idle GPU for the first ~20 ms of a batch
+// of 8K frames); one after the other, the first job computes after one copy time.
+struct XferGate {
+	std::mutex dir[2]; // [0] host -> device, [1] device -> host
+};
+// copy on the context's stream and, if `wait` or gated, wait for it.  Gated device -> host copies first wait for the
+// stream's kernels, so that the gate is only held for the copy itself.
+cudaError_t ctx_copy(dwt_ctx *c, void *dst, const void *src, size_t n, cudaMemcpyKind kind, bool wait);
 // wait for the context's stream (cudaStreamSynchronize; with DWT_SYNC=poll an event poll that yields the core between polls)
 cudaError_t ctx_stream_sync(dwt_ctx *c);
 const int *ctx_root_ll(dwt_ctx *c);      // device pointer to the planar root LL after ctx_forward_transform

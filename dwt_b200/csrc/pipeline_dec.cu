@@ -44,8 +44,7 @@ extern "C" int dwt_ctx_upload_stream(dwt_ctx *c, const uint8_t *stream, size_t l
 	CUDA_OK(cudaMemsetAsync((char *)c->stream.p + (len / 4) * 4, 0, room - (len / 4) * 4, c->st));
 	if (len) {
 		memcpy(c->pin_stream.p, stream, head);
-		CUDA_OK(cudaMemcpyAsync(c->stream.p, stream, len, cudaMemcpyHostToDevice, c->st));
-		CUDA_OK(ctx_stream_sync(c)); // the caller's buffer is free again when this returns
+		CUDA_OK(ctx_copy(c, c->stream.p, stream, len, cudaMemcpyHostToDevice, true)); // the caller's buffer is free again
 	}
 	c->stream_head = head;
 	c->stream_len = len;
