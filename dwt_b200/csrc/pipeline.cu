@@ -134,7 +134,8 @@ cudaError_t ctx_stream_sync(dwt_ctx *c)
 cudaError_t ctx_copy(dwt_ctx *c, void *dst, const void *src, size_t n, cudaMemcpyKind kind, bool wait)
 {
 	static const bool ungated = getenv("DWT_XFER_GATE") && !strcmp(getenv("DWT_XFER_GATE"), "0");
-	if (!c->gate || ungated || n < (1u << 20)) {
+	// below 16 MB a copy is over before the others notice (1080p frames measured 2-3 % slower gated: the extra wait costs more)
+	if (!c->gate || ungated || n < (16u << 20)) {
 		cudaError_t e = cudaMemcpyAsync(dst, src, n, kind, c->st);
 		return e == cudaSuccess && wait ? ctx_stream_sync(c) : e;
 	}
