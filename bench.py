@@ -376,6 +376,7 @@ def our_bench(args, rank, world, local):
     def roof(ms, nbytes):
         gbs = nbytes / (ms / 1e3) / 1e9
         return dict(bound="hbm", achieved=round(gbs, 1), peak=peak, unit="GB/s", frac=round(gbs / peak, 4),
+                    frac_of_datasheet_8000=round(gbs / 8000.0, 4),  # also against the 8 TB/s datasheet figure
                     ms=round(ms, 4), bytes=int(nbytes))
 
     nsamples = npx * CH

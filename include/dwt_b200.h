@@ -92,7 +92,10 @@ int dwt_decode_into(dwt_ctx *ctx, const uint8_t *stream, size_t len, int pixels_
 /* Batches of independent images (the reference codes one image per process): a pool owns `workers`
  * contexts on one device and codes the items on as many host threads, so host<->device copies and kernels of different
  * items overlap.  Buffers should come from dwt_host_alloc().  status per item: the value dwt_encode_into /
- * dwt_decode_into would have returned.  Return value: number of items whose status is non-zero, -1 on bad arguments. */
+ * dwt_decode_into would have returned.  Return value: number of items whose status is non-zero, -1 on bad arguments.
+ * The contexts of a pool take turns for host<->device copies of 16 MB and more (one per direction at a time), so the
+ * first items of a batch start computing after one copy time.  Environment (debugging aids): DWT_XFER_GATE=0 switches
+ * the turn-taking off, DWT_SYNC=poll makes waiting host threads poll and yield instead of spinning in the driver. */
 struct dwt_encode_item {
 	const uint8_t *pixels;
 	int width, height, channels, capacity;
