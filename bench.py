@@ -410,7 +410,7 @@ def our_bench(args, rank, world, local):
                         h2d_bytes_per_step=int(world * F * (img.size + stream_bytes)),
                         d2h_bytes_per_step=int(world * F * (stream_bytes + img.size)),
                         api="dwt_pool_run: dwt_encode_into of %d frames + dwt_decode_into of %d streams per step, interleaved on %d contexts, "
-                            "page-locked host buffers, the K steps in one call" % (F, F, 2 * F)),
+                            "page-locked host buffers, the K steps in one call (runs of more than ~50 jobs: several calls on the same buffers)" % (F, F, 2 * F)),
                gpu_launches=int(launches), clocks=clocks, roofline=roofline, stages=stages,
                single_frame=dict(ms_per_frame=round(statistics.median(serial_ms), 3),
                                  mpixel_s=round(npx / (statistics.median(serial_ms) / 1e3) / 1e6, 1),
