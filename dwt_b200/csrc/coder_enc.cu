@@ -236,14 +236,17 @@ __global__ void __launch_bounds__(TG) enc_emit_kernel(const __grid_constant__ Ge
 		if (n1) {
 			u32 zb = ez[e] + (u32)(ex & 0x1fffffu);
 			u32 tb = e1[e] + C->tok_adj[j] + (u32)((ex >> 21) & 0x1fffffu);
-			bits_or(signbuf, tb, bit_compress(sgn, ones), (int)n1);
-			u32 o = ones, t = tb;
+			// the signs of the ones, in token order: gathered in the walk over the ones (cheaper than a parallel-suffix
+			// compress of the sign word for the two or three ones a group has per plane)
+			u32 o = ones, t = tb, sb = 0;
 			while (o) {
 				int b = __ffs(o) - 1;
 				Z[t + 1] = zb + __popc(zeros & ((1u << b) - 1u));
+				sb |= ((sgn >> b) & 1u) << (t - tb);
 				++t;
 				o &= o - 1;
 			}
+			bits_or(signbuf, tb, sb, (int)n1);
 		}
 		if (nr) {
 			u32 rb = er[e] + (u32)(ex >> 42);
