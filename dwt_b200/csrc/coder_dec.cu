@@ -1324,10 +1324,11 @@ __global__ void __launch_bounds__(TG) dec_deposit_kernel(const __grid_constant__
 			if (nm < 32)
 				ob &= (1u << nm) - 1u;
 			if (ob) {
-				Bw = bit_expand(ob, member);
+				const ExpandPlan pl = bit_expand_plan(member); // ones and their signs go through the same mask
+				Bw = bit_expand_apply(ob, pl);
 				const u32 sb = bits_get32(B.sign_rank, off) & ob;
 				if (sb)
-					sign_words[gi] |= bit_expand(sb, member);
+					sign_words[gi] |= bit_expand_apply(sb, pl);
 			}
 		}
 		if (nr && ck.ref_valid) {

@@ -107,6 +107,40 @@ __device__ __forceinline__ u32 bit_expand(u32 x, u32 m)
 	return x & m0;
 }
 
+// bit_expand split in two for several words that go through the same mask: the mask-only part (the five move masks) ...
+struct ExpandPlan {
+	u32 mv[5], m0;
+};
+__device__ __forceinline__ ExpandPlan bit_expand_plan(u32 m)
+{
+	ExpandPlan pl;
+	pl.m0 = m;
+	u32 mk = ~m << 1;
+#pragma unroll
+	for (int i = 0; i < 5; ++i) {
+		u32 mp = mk ^ (mk << 1);
+		mp ^= mp << 2;
+		mp ^= mp << 4;
+		mp ^= mp << 8;
+		mp ^= mp << 16;
+		const u32 mv = mp & m;
+		pl.mv[i] = mv;
+		m = (m ^ mv) | (mv >> (1 << i));
+		mk &= ~mp;
+	}
+	return pl;
+}
+// ... and the five conditional moves of one word
+__device__ __forceinline__ u32 bit_expand_apply(u32 x, const ExpandPlan &pl)
+{
+#pragma unroll
+	for (int i = 4; i >= 0; --i) {
+		const u32 t = x << (1 << i);
+		x = (x & ~pl.mv[i]) | (t & pl.mv[i]);
+	}
+	return x & pl.m0;
+}
+
 // OR `n` (0..32) bits into an LSB-first bit array of zero-initialised 32-bit words at bit offset `off`.
 __device__ __forceinline__ void bits_or(u32 *buf, u64 off, u32 bits, int n)
 {
