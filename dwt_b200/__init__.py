@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "dwt_ctx_decode_resident", "dwt_ctx_download_image", "dwt_ctx_launch_count", "dwt_ctx_sync", "dwt_ctx_set_in_flight",
     "dwt_host_alloc", "dwt_host_free", "dwt_encode_into", "dwt_decode_into", "dwt_ctx_flush_l2",
     "dwt_ctx_event_record", "dwt_ctx_event_elapsed_ms", "dwt_ctx_wait_for",
-    "dwt_pool_create", "dwt_pool_destroy", "dwt_pool_workers", "dwt_pool_encode", "dwt_pool_decode", "dwt_pool_run",
+    "dwt_pool_create", "dwt_pool_destroy", "dwt_pool_workers", "dwt_pool_last_error", "dwt_pool_encode", "dwt_pool_decode", "dwt_pool_run",
     "cdf53", "icdf53", "dwt_forward", "dwt_inverse", "dwt_ycocg_from_rgb", "dwt_rgb_from_ycocg",
     "compute_lengths", "ilog2", "dwt_debug_front_end",
     "bytes_reader", "bytes_writer", "bytes_count", "close_bytes_reader", "close_bytes_writer", "put_byte",
@@ -103,6 +103,8 @@ def lib():
     L.dwt_pool_destroy.argtypes = [vp]
     L.dwt_pool_destroy.restype = None
     L.dwt_pool_workers.argtypes = [vp]
+    L.dwt_pool_last_error.argtypes = [vp]
+    L.dwt_pool_last_error.restype = C.c_char_p
     L.dwt_pool_encode.argtypes = [vp, C.POINTER(EncodeItem), C.c_int]
     L.dwt_pool_decode.argtypes = [vp, C.POINTER(DecodeItem), C.c_int]
     L.dwt_pool_run.argtypes = [vp, C.POINTER(EncodeItem), C.c_int, C.POINTER(DecodeItem), C.c_int]
@@ -181,7 +183,8 @@ class Codec:
         pix, w, h, ch = C.POINTER(C.c_uint8)(), C.c_int(), C.c_int(), C.c_int()
         r = lib().dwt_decode(self._h, _u8p(buf), n, int(pixels_max), C.byref(pix), C.byref(w), C.byref(h), C.byref(ch),
                              C.byref(self.stats))
-        if r == 1:
+        if r > 0:  # 1: stream ends inside the prefix, 2: bad magic / size -- the reference exits 1 without output
+            self.reject_code = r
             return None
         if r:
             raise DwtError("dwt_decode failed: " + last_error())

@@ -6,6 +6,7 @@
 #include "dwt_b200.h"
 
 #include <atomic>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -13,6 +14,17 @@
 
 
 static thread_local dwt_ctx *g_default_ctx = nullptr;
+
+// a temporary device allocation that is released on every return path
+struct DevTmp {
+	int *p = nullptr;
+	cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+	~DevTmp()
+	{
+		if (p)
+			cudaFree(p);
+	}
+};
 
 static dwt_ctx *default_ctx()
 {
@@ -131,24 +143,34 @@ static void run_1d(int *out, int *in, int N, int SO, int SI, int CH, bool invers
 			fprintf(stderr, "libdwt_b200: %s\n", dwt_last_error());
 		return; // the reference signature has no error path
 	}
-	cudaSetDevice(c->device);
 	cudaStream_t st = c->st;
-	size_t span_in = (size_t)(N - 1) * SI + CH, span_out = (size_t)(N - 1) * SO + CH;
-	int *d_in = nullptr, *d_out = nullptr;
-	if (cudaMalloc(&d_in, span_in * sizeof(int)) != cudaSuccess || cudaMalloc(&d_out, span_out * sizeof(int)) != cudaSuccess) {
-		fprintf(stderr, "libdwt_b200: out of device memory\n");
-		return;
-	}
-	cudaMemcpyAsync(d_in, in, span_in * sizeof(int), cudaMemcpyHostToDevice, st);
-	cudaMemcpyAsync(d_out, out, span_out * sizeof(int), cudaMemcpyHostToDevice, st); // untouched gaps survive
-	lift_cdf53_1d(d_out, d_in, N, SO, SI, CH, inverse, st);
+	const size_t span_in = (size_t)(N - 1) * SI + CH, span_out = (size_t)(N - 1) * SO + CH;
+	DevTmp d_in, d_out;
+	// the reference signature returns nothing: a CUDA failure is reported on stderr and leaves `out` untouched
+	cudaError_t e = cudaSetDevice(c->device);
+	if (e == cudaSuccess)
+		e = d_in.alloc(span_in * sizeof(int));
+	if (e == cudaSuccess)
+		e = d_out.alloc(span_out * sizeof(int));
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(d_in.p, in, span_in * sizeof(int), cudaMemcpyHostToDevice, st);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(d_out.p, out, span_out * sizeof(int), cudaMemcpyHostToDevice, st); // untouched gaps survive
+	if (e == cudaSuccess && lift_cdf53_1d(d_out.p, d_in.p, N, SO, SI, CH, inverse, st))
+		e = cudaErrorUnknown;
 	c->launches += 1;
-	cudaMemcpyAsync(out, d_out, span_out * sizeof(int), cudaMemcpyDeviceToHost, st);
-	if (!inverse) // cdf53.h:12-23 lifts in place: the caller sees the lifted samples in `in`
-		cudaMemcpyAsync(in, d_in, span_in * sizeof(int), cudaMemcpyDeviceToHost, st);
-	cudaStreamSynchronize(st);
-	cudaFree(d_in);
-	cudaFree(d_out);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(out, d_out.p, span_out * sizeof(int), cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess && !inverse) // cdf53.h:12-23 lifts in place: the caller sees the lifted samples in `in`
+		e = cudaMemcpyAsync(in, d_in.p, span_in * sizeof(int), cudaMemcpyDeviceToHost, st);
+	const cudaError_t e2 = cudaStreamSynchronize(st);
+	if (e == cudaSuccess)
+		e = e2;
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		fprintf(stderr, "libdwt_b200: %s failed: %s\n", inverse ? "icdf53" : "cdf53",
+		        e == cudaErrorUnknown ? dwt_last_error() : cudaGetErrorString(e));
+	}
 }
 
 extern "C" void cdf53(int *out, int *in, int N, int SO, int SI, int CH)
@@ -180,9 +202,10 @@ extern "C" int dwt_forward(int *out, const int *in, int W, int H, int CH)
 	cudaStream_t st = c->st;
 	const long long npix = (long long)W * H;
 	const size_t n = (size_t)npix * CH;
-	int *d_a = nullptr, *d_b = nullptr;
-	CUDA_OK(cudaMalloc(&d_a, n * sizeof(int)));
-	CUDA_OK(cudaMalloc(&d_b, n * sizeof(int)));
+	DevTmp ta, tb;
+	CUDA_OK(ta.alloc(n * sizeof(int)));
+	CUDA_OK(tb.alloc(n * sizeof(int)));
+	int *d_a = ta.p, *d_b = tb.p;
 	CUDA_OK(cudaMemcpyAsync(d_a, in, n * sizeof(int), cudaMemcpyHostToDevice, st));
 	deinterleave_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_a, d_b, npix, CH);
 	int r = ctx_forward_transform(c, d_b);
@@ -193,8 +216,6 @@ extern "C" int dwt_forward(int *out, const int *in, int W, int H, int CH)
 		cudaMemcpyAsync(out, d_a, n * sizeof(int), cudaMemcpyDeviceToHost, st);
 	}
 	cudaError_t e = cudaStreamSynchronize(st);
-	cudaFree(d_a);
-	cudaFree(d_b);
 	(void)L;
 	if (r || e != cudaSuccess) {
 		if (!r)
@@ -223,9 +244,10 @@ extern "C" int dwt_inverse(int *out, const int *in, int W, int H, int CH)
 		return -1;
 	const long long npix = (long long)W * H;
 	const size_t n = (size_t)npix * CH;
-	int *d_a = nullptr, *d_b = nullptr;
-	CUDA_OK(cudaMalloc(&d_a, n * sizeof(int)));
-	CUDA_OK(cudaMalloc(&d_b, n * sizeof(int)));
+	DevTmp ta, tb;
+	CUDA_OK(ta.alloc(n * sizeof(int)));
+	CUDA_OK(tb.alloc(n * sizeof(int)));
+	int *d_a = ta.p, *d_b = tb.p;
 	CUDA_OK(cudaMemcpyAsync(d_a, in, n * sizeof(int), cudaMemcpyHostToDevice, st));
 	// planar pyramid; the root rectangle is copied to ll[0] with its own pitch
 	deinterleave_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_a, c->pyr.as<int>(), npix, CH);
@@ -240,8 +262,6 @@ extern "C" int dwt_inverse(int *out, const int *in, int W, int H, int CH)
 		cudaMemcpyAsync(out, d_a, n * sizeof(int), cudaMemcpyDeviceToHost, st);
 	}
 	cudaError_t e = cudaStreamSynchronize(st);
-	cudaFree(d_a);
-	cudaFree(d_b);
 	if (r || e != cudaSuccess) {
 		if (!r)
 			dwt_set_error("dwt_inverse: %s", cudaGetErrorString(e));
@@ -258,15 +278,16 @@ static int colour_host(int *buffer, int total, bool inverse)
 	if (total <= 0)
 		return 0;
 	CUDA_OK(cudaSetDevice(c->device));
-	int *d = nullptr;
+	DevTmp td;
 	size_t bytes = (size_t)total * 3 * sizeof(int);
-	CUDA_OK(cudaMalloc(&d, bytes));
-	cudaMemcpyAsync(d, buffer, bytes, cudaMemcpyHostToDevice, c->st);
+	CUDA_OK(td.alloc(bytes));
+	int *d = td.p;
+	CUDA_OK(cudaMemcpyAsync(d, buffer, bytes, cudaMemcpyHostToDevice, c->st));
 	int r = lift_colour(d, total, inverse, c->st);
 	c->launches += 1;
-	cudaMemcpyAsync(buffer, d, bytes, cudaMemcpyDeviceToHost, c->st);
+	if (!r)
+		CUDA_OK(cudaMemcpyAsync(buffer, d, bytes, cudaMemcpyDeviceToHost, c->st));
 	cudaError_t e = cudaStreamSynchronize(c->st);
-	cudaFree(d);
 	if (r || e != cudaSuccess) {
 		if (!r)
 			dwt_set_error("colour transform: %s", cudaGetErrorString(e));
@@ -361,7 +382,14 @@ struct dwt_pool {
 	int device = 0;
 	std::vector<dwt_ctx *> ctx;
 	XferGate gate; // shared by the contexts: one large copy per direction at a time
+	std::mutex err_lock;
+	char err[512] = "";
 };
+
+extern "C" const char *dwt_pool_last_error(const dwt_pool *p)
+{
+	return p ? p->err : "";
+}
 
 // How many contexts the caller keeps busy on this device at the same time (default 1).  With several frames in flight the
 // library prefers kernels that do less total work over kernels that finish one frame sooner (decoder scan).
@@ -421,8 +449,11 @@ static int pool_run(dwt_pool *p, int n, F &&one)
 			const int i = next.fetch_add(1);
 			if (i >= n)
 				break;
-			if (one(p->ctx[(size_t)w], i))
+			if (one(p->ctx[(size_t)w], i)) {
 				failed.fetch_add(1);
+				std::lock_guard<std::mutex> hold(p->err_lock); // dwt_last_error() is per thread: keep the reason with the pool
+				snprintf(p->err, sizeof(p->err), "item %d: %s", i, dwt_last_error());
+			}
 		}
 	};
 	const int nw = (int)p->ctx.size() < n ? (int)p->ctx.size() : n;

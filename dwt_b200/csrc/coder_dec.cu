@@ -1392,14 +1392,7 @@ int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b, int nchunks, cu
 	                                                           b.winTT, b.link);
 	dec_resolve_kernel<<<1, 32, 0, st>>>(g, nchunks, b);
 	{
-		static int sms = 0;
-		if (!sms) {
-			int dev = 0;
-			cudaGetDevice(&dev);
-			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-			if (sms <= 0)
-				sms = 1;
-		}
+		const int sms = dwt_device_sms();
 		const u32 want = b.nwin + (u32)nchunks, cap = (u32)sms * 64u;
 		dec_emit_kernel<<<want < cap ? want : cap, WS, 0, st>>>(b);
 	}

@@ -51,6 +51,7 @@ struct Sched {
 	} while (0)
 
 void dwt_set_error(const char *fmt, ...);
+int dwt_device_sms(); // multiprocessors of the calling thread's current device (cached per device)
 
 #ifdef __CUDACC__
 

@@ -552,14 +552,7 @@ void hilbert_plan_free(HilbertPlan *plan)
 
 static int full_grid(int nlist)
 {
-	static int sms = 0;
-	if (!sms) {
-		int dev = 0;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		if (sms <= 0)
-			sms = 1;
-	}
+	const int sms = dwt_device_sms();
 	const int want = (nlist + 7) / 8;
 	return want < sms * 8 ? want : sms * 8;
 }

@@ -843,14 +843,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) lift_tail_inv_kernel(LiftTail t)
 
 int resident_blocks()
 {
-	static int n = 0;
-	if (!n) {
-		int dev = 0, sms = 0;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		n = (sms > 0 ? sms : 1) * 8;
-	}
-	return n;
+	return dwt_device_sms() * 8;
 }
 
 int pick_rows(int W, int H, int planes)

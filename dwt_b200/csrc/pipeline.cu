@@ -10,6 +10,8 @@
 #include "../host/streamio_internal.h"
 #include "dwt_b200.h"
 
+#include <atomic>
+
 #include <sched.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -30,6 +32,22 @@ void dwt_set_error(const char *fmt, ...)
 extern "C" const char *dwt_last_error(void)
 {
 	return g_err;
+}
+
+int dwt_device_sms()
+{
+	static std::atomic<int> cache[64];
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0)
+		dev = 0;
+	const int slot = dev & 63;
+	int n = cache[slot].load(std::memory_order_relaxed);
+	if (n <= 0) {
+		if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+			n = 1;
+		cache[slot].store(n, std::memory_order_relaxed);
+	}
+	return n;
 }
 
 // ------------------------------------------------------------------------------------------------ buffers
@@ -422,6 +440,62 @@ static inline size_t round_up(size_t v, size_t a)
 	return (v + a - 1) / a * a;
 }
 
+// the host-side writers of the stream prefix: released on every return path
+struct PrefixWriters {
+	struct bytes_writer *bw = nullptr;
+	struct bits_writer *bits = nullptr;
+	struct vli_writer *vli = nullptr;
+	void finish() // pads the last byte into bw; bw stays readable until the guard goes out of scope
+	{
+		if (vli)
+			delete_vli_writer(vli);
+		if (bits)
+			close_bits_writer(bits);
+		vli = nullptr;
+		bits = nullptr;
+	}
+	~PrefixWriters()
+	{
+		finish();
+		if (bw)
+			close_bytes_writer(bw);
+	}
+};
+
+// header, root image and plane counts through the reference-shaped writers, return values ignored like encode.c:169-182
+// does.  capacity > 0 makes the byte sink refuse like bytes.h:77-78 (used to reproduce the stderr counters of a cut that
+// lands inside the prefix: every write call then stops at its first refused byte, so the counts are not a closed form).
+static void write_prefix(PrefixWriters &pw, int capacity, const Geom &g, const int *root, const int *planes, long long *meta_bits,
+                         long long *root_end)
+{
+	const int C = g.channels, L = g.levels;
+	struct bytes_writer *bw = pw.bw = bytes_writer_mem(capacity);
+	put_byte(bw, 'W');
+	put_byte(bw, C == 3 ? '6' : '5');
+	write_bytes(bw, g.w[L] - 1, 2);
+	write_bytes(bw, g.h[L] - 1, 2);
+	struct bits_writer *bits = pw.bits = bits_writer(bw);
+	struct vli_writer *vli = pw.vli = vli_writer(bits);
+	*meta_bits = bits_count(bits);
+	for (int ch = 0; ch < C; ++ch) {
+		const int *v = root + (size_t)ch * g.pix[0];
+		int mx = 0;
+		for (int i = 0; i < (int)g.pix[0]; ++i)
+			if (abs(v[i]) > mx)
+				mx = abs(v[i]);
+		int cnt = 1 + ilog2(mx);
+		put_vli(vli, cnt);
+		for (int i = 0; cnt && i < (int)g.pix[0]; ++i) {
+			vli_write_bits(vli, abs(v[i]), cnt);
+			if (v[i])
+				vli_put_bit(vli, v[i] < 0);
+		}
+	}
+	*root_end = bits_count(bits);
+	for (int ch = 0; ch < C; ++ch)
+		put_vli(vli, planes[ch]);
+}
+
 extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stats *stt)
 {
 	if (!c || !c->img_resident) {
@@ -463,32 +537,13 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 	const Sched &S = c->sched;
 
 	// ---- stream prefix on the host: header (encode.c:169-172), root image (encode.c:97-110), planes (encode.c:181-182)
-	struct bytes_writer *bw = bytes_writer_mem(0);
-	put_byte(bw, 'W');
-	put_byte(bw, C == 3 ? '6' : '5');
-	write_bytes(bw, g.w[L] - 1, 2);
-	write_bytes(bw, g.h[L] - 1, 2);
-	struct bits_writer *bits = bits_writer(bw);
-	struct vli_writer *vli = vli_writer(bits);
-	const long long meta_bits = bits_count(bits);
+	PrefixWriters pw;
 	const int *root = h_small + 4;
-	for (int ch = 0; ch < C; ++ch) {
-		const int *v = root + (size_t)ch * g.pix[0];
-		int mx = 0;
-		for (int i = 0; i < (int)g.pix[0]; ++i)
-			if (abs(v[i]) > mx)
-				mx = abs(v[i]);
-		int cnt = 1 + ilog2(mx);
-		put_vli(vli, cnt);
-		for (int i = 0; cnt && i < (int)g.pix[0]; ++i) {
-			vli_write_bits(vli, abs(v[i]), cnt);
-			if (v[i])
-				vli_put_bit(vli, v[i] < 0);
-		}
-	}
-	const long long root_end = bits_count(bits);
-	for (int ch = 0; ch < C; ++ch)
-		put_vli(vli, planes[ch]);
+	long long meta_bits = 0, root_end = 0;
+	write_prefix(pw, 0, g, root, planes, &meta_bits, &root_end);
+	struct bits_writer *bits = pw.bits;
+	struct vli_writer *vli = pw.vli;
+	struct bytes_writer *bw = pw.bw;
 	u64 prefix_bits = (u64)bits_count(bits);
 	int k0 = dwt_vli_writer_order(vli);
 	u64 total_bits = 0;
@@ -503,8 +558,7 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 		total_bits = (u64)bits_count(bits);
 		prefix_bits = total_bits;
 	}
-	delete_vli_writer(vli);
-	close_bits_writer(bits); // pads the last byte
+	pw.finish(); // pads the last byte
 	size_t prefix_len = 0;
 	const uint8_t *prefix = bytes_writer_data(bw, &prefix_len);
 
@@ -607,7 +661,6 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 	}
 	CUDA_OK(cudaEventRecord(c->ev[3], st));
 	CUDA_OK(ctx_stream_sync(c));
-	close_bytes_writer(bw);
 
 	if (stt) {
 		memset(stt, 0, sizeof(*stt));
@@ -616,12 +669,22 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 		stt->levels = L;
 		for (int ch = 0; ch < 3; ++ch)
 			stt->planes[ch] = planes[ch];
-		// the three stderr counters of encode.c (capacity lands after the prefix in every practical case)
-		stt->meta_bits = capacity > 0 && capacity < 6 ? 8LL * capacity : meta_bits;
+		// the three stderr counters of encode.c:175-180,226-230.  bits_count() = bits->cnt + 8 * bytes_count() (bits.h:41-44):
+		// once the byte sink refuses (bytes.h:77-78) the byte count stays at the capacity, and every prefix write call stops
+		// at its first refused byte -- the counters of a cut inside the prefix come from a replay against a capped sink
+		const long long cap8 = 8LL * capacity;
+		stt->meta_bits = meta_bits;
 		stt->root_bits = root_end - meta_bits;
-		const bool cut = capacity > 0 && full >= 8LL * (capacity + 1);
-		stt->total_bits = cut ? 8LL * capacity : full;
-		long long byte_cnt = cut ? capacity : full / 8;
+		if (capacity > 0 && cap8 < (long long)prefix_bits) { // the cut lands inside the prefix: replay it against a capped sink
+			PrefixWriters sim;
+			long long m = 0, r = 0;
+			write_prefix(sim, capacity, g, root, planes, &m, &r);
+			stt->meta_bits = m;
+			stt->root_bits = r - m;
+		}
+		const bool cut = capacity > 0 && full >= 8LL * (capacity + 1); // a payload byte was refused: `goto end` at a byte boundary
+		stt->total_bits = cut ? cap8 : full;
+		long long byte_cnt = (full + 7) / 8; // bytes_count() after close_bits_writer() wrote the padded last byte
 		if (capacity > 0 && byte_cnt > capacity)
 			byte_cnt = capacity;
 		stt->kib = (byte_cnt + 512) / 1024;
@@ -688,8 +751,16 @@ extern "C" int dwt_debug_front_end(dwt_ctx *c, const uint8_t *pixels, int width,
 		planes_out[ch] = planes[ch];
 	const long long npix = g.pix[L];
 	const size_t n = (size_t)npix * C;
-	int *tmp = nullptr;
-	CUDA_OK(cudaMalloc(&tmp, n * sizeof(int)));
+	struct TmpGuard { // released on every return path
+		int *p = nullptr;
+		~TmpGuard()
+		{
+			if (p)
+				cudaFree(p);
+		}
+	} guard;
+	CUDA_OK(cudaMalloc(&guard.p, n * sizeof(int)));
+	int *tmp = guard.p;
 	if (pyramid) {
 		export_pyramid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->pyr.as<int>(), ctx_root_ll(c), tmp, g.w[L],
 		                                                                   g.h[L], C, g.w[0], g.h[0]);
@@ -700,17 +771,13 @@ extern "C" int dwt_debug_front_end(dwt_ctx *c, const uint8_t *pixels, int width,
 		build_schedule(g, planes, &c->sched);
 		const Sched &S = c->sched;
 		const size_t bs_words = (size_t)S.bsbase[C];
-		if (c->bs.ensure(bs_words * 4 + 64)) {
-			cudaFree(tmp);
+		if (c->bs.ensure(bs_words * 4 + 64))
 			return -1;
-		}
 		CUDA_OK(cudaMemsetAsync(c->bs.p, 0, bs_words * 4, st));
 		CUDA_OK(cudaMemsetAsync(tmp, 0, n * sizeof(int), st));
 		if (hilbert_linearize(g, c->plan, S, c->pyr.as<int>(), npix, g.w[L], c->bs.as<u32>(), L, st, &c->launches) ||
-		    hilbert_unslice(g, S, c->bs.as<u32>(), tmp, npix, st)) {
-			cudaFree(tmp);
+		    hilbert_unslice(g, S, c->bs.as<u32>(), tmp, npix, st))
 			return -1;
-		}
 		// root raster first (encode.c:37-45)
 		for (int ch = 0; ch < C; ++ch)
 			CUDA_OK(cudaMemcpyAsync(tmp + (size_t)ch * npix, ctx_root_ll(c) + (size_t)ch * g.pix[0],
@@ -718,6 +785,5 @@ extern "C" int dwt_debug_front_end(dwt_ctx *c, const uint8_t *pixels, int width,
 		CUDA_OK(cudaMemcpyAsync(planar, tmp, n * sizeof(int), cudaMemcpyDeviceToHost, st));
 		CUDA_OK(ctx_stream_sync(c));
 	}
-	cudaFree(tmp);
 	return 0;
 }

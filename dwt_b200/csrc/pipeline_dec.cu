@@ -13,6 +13,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 static inline size_t round_up(size_t v, size_t a)
 {
 	return (v + a - 1) / a * a;
@@ -92,6 +94,33 @@ static int decode_schedule_length(const Geom &g, const Sched &S, int levels_max)
 	return n;
 }
 
+// the host-side readers of the stream prefix: released on every return path
+struct PrefixReaders {
+	struct bytes_reader *br = nullptr;
+	struct bits_reader *bits = nullptr;
+	struct vli_reader *vli = nullptr;
+	~PrefixReaders()
+	{
+		if (vli)
+			delete_vli_reader(vli);
+		if (bits)
+			close_bits_reader(bits);
+		if (br)
+			close_bytes_reader(br);
+	}
+};
+
+// order-0 token table of the decoder: built once per process, immutable afterwards
+static const u32 *dec_token_table_host()
+{
+	static const std::vector<u32> table = [] {
+		std::vector<u32> t(DWT_DEC_LUT_WORDS);
+		dec_token_table(t.data());
+		return t;
+	}();
+	return table.data();
+}
+
 extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_stats *stt)
 {
 	if (!c || !c->stream_resident) {
@@ -103,37 +132,41 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 	// ---- header + root image + plane counts on the host (the bytes are still in the pinned staging buffer)
 	const uint8_t *bytes = c->pin_stream.as<uint8_t>();
 	const size_t len = c->stream_len;
-	struct bytes_reader *br = bytes_reader_mem(bytes, c->stream_head); // prefix only (see dwt_ctx_upload_stream)
+	PrefixReaders pr;
+	struct bytes_reader *br = pr.br = bytes_reader_mem(bytes, c->stream_head); // prefix only (see dwt_ctx_upload_stream)
+	// decode.c:145-159: the reference exits 1 either silently (wrong magic, size below 8: return 2 here) or after get_byte
+	// printed "reached end of file" (bytes.h:99-103: return 1 here)
 	int width = 0, height = 0;
-	int letter = get_byte(br);
-	int number = letter == 'W' ? get_byte(br) : -1;
-	if (letter != 'W' || (number != '5' && number != '6') || read_bytes(br, &width, 2) || read_bytes(br, &height, 2)) {
-		close_bytes_reader(br);
-		return 1; // decode.c:145-156
-	}
+	const int letter = get_byte(br);
+	if (letter < 0)
+		return 1;
+	if (letter != 'W')
+		return 2;
+	const int number = get_byte(br);
+	if (number < 0)
+		return 1;
+	if (number != '5' && number != '6')
+		return 2;
+	if (read_bytes(br, &width, 2) || read_bytes(br, &height, 2))
+		return 1;
 	++width;
 	++height;
-	if (width < 8 || height < 8) {
-		close_bytes_reader(br);
-		return 1; // decode.c:157-159
-	}
+	if (width < 8 || height < 8)
+		return 2;
 	const int C = number == '6' ? 3 : 1;
-	if (ctx_set_geometry(c, width, height, C)) {
-		close_bytes_reader(br);
+	if (ctx_set_geometry(c, width, height, C))
 		return -1;
-	}
 	const Geom &g = c->geom;
 	const int L = g.levels;
 	int levels_max = L;
 	if (pixels_max >= 0)
 		while (levels_max > 0 && g.pix[levels_max] > pixels_max)
 			--levels_max; // decode.c:165-171
-	struct bits_reader *bits = bits_reader(br);
-	struct vli_reader *vli = vli_reader(bits);
+	struct bits_reader *bits = pr.bits = bits_reader(br);
+	struct vli_reader *vli = pr.vli = vli_reader(bits);
 	const int nroot = (int)g.pix[0];
-	if (c->pin_small.ensure(sizeof(int) * (size_t)(nroot * C + 64) + sizeof(DecState) + 64)) {
+	if (c->pin_small.ensure(sizeof(int) * (size_t)(nroot * C + 64) + sizeof(DecState) + 64))
 		return -1;
-	}
 	int *h_root = c->pin_small.as<int>();
 	memset(h_root, 0, sizeof(int) * (size_t)nroot * C);
 	int planes[3] = {0, 0, 0};
@@ -164,11 +197,8 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 			bad = true; // decode.c:183-186
 	const int k0 = dwt_vli_reader_order(vli);
 	const long long b0 = dwt_bits_reader_position(bits);
-	delete_vli_reader(vli);
-	close_bits_reader(bits);
-	close_bytes_reader(br);
 	if (bad)
-		return 1;
+		return 1; // EOF inside the root image or the plane counts (decode.c:180-186)
 	int planes_max = 0;
 	for (int ch = 0; ch < C; ++ch) {
 		if (planes[ch] > planes_max)
@@ -216,11 +246,10 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		    c->dec_chunks.ensure((size_t)DWT_MAX_CHUNKS * sizeof(DecChunk)) || c->dsched.ensure(sizeof(Sched)))
 			return -1;
 		if (!c->dec_lut_ready) {
-			static u32 table[DWT_DEC_LUT_WORDS];
-			dec_token_table(table);
-			if (c->dec_lut.ensure(sizeof(table)))
+			const size_t table_bytes = sizeof(u32) * DWT_DEC_LUT_WORDS;
+			if (c->dec_lut.ensure(table_bytes))
 				return -1;
-			CUDA_OK(cudaMemcpyAsync(c->dec_lut.p, table, sizeof(table), cudaMemcpyHostToDevice, st));
+			CUDA_OK(cudaMemcpyAsync(c->dec_lut.p, dec_token_table_host(), table_bytes, cudaMemcpyHostToDevice, st));
 			CUDA_OK(ctx_stream_sync(c));
 			c->dec_lut_ready = true;
 		}

@@ -206,10 +206,12 @@ int main(int argc, char **argv)
 			const char *path = files[which[i]];
 			const int status = enc ? ei[i].status : di[i].status;
 			if (status) {
-				if (status > 0)
-					fprintf(stderr, "reached end of file \"%s\"\n", path); /* decode.c:180-186 */
+				if (status == 1)
+					fprintf(stderr, "reached end of file \"%s\"\n", path); /* decode.c:180-186, bytes.h:99-103 */
+				else if (status > 1)
+					fprintf(stderr, "%s: not a .dwt stream\n", path);   /* decode.c:146-159 (the reference is silent) */
 				else
-					fprintf(stderr, "%s: coding failed\n", path);
+					fprintf(stderr, "%s: coding failed: %s\n", path, dwt_pool_last_error(pool));
 				++failed;
 				continue;
 			}

@@ -40,8 +40,9 @@ int main(int argc, char **argv)
 	if (r) {
 		if (r < 0)
 			fprintf(stderr, "%s: %s\n", argv[0], dwt_last_error());
-		else
+		else if (r == 1) /* the stream ended inside header, root image or plane counts: bytes.h:99-103 prints this */
 			fprintf(stderr, "reached end of file \"%s\"\n", argv[1]);
+		/* r == 2: wrong magic or size below 8 -- the reference exits 1 silently (decode.c:146-159) */
 		return 1;
 	}
 	if (!dwt_write_pnm(argv[2], pixels, width, height, channels))

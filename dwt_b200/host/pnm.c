@@ -18,71 +18,98 @@ static const char *real_name(const char *name, const char *dash)
 	return (name[0] == '-' && !name[1]) ? dash : name;
 }
 
+/* header tokenizer: `cur` is the byte most recently taken from the file */
+struct cursor {
+	FILE *file;
+	int cur;
+};
+
+static int advance(struct cursor *k)
+{
+	k->cur = fgetc(k->file);
+	return k->cur != EOF;
+}
+
+static int is_digit(int c)
+{
+	return c >= '0' && c <= '9';
+}
+
+/* One decimal header field.  Entered with `cur` = the byte that ended the previous field (or the single byte
+ * behind the magic), which is dropped.  '#' right at the start of a field opens a comment line, any number of
+ * them (pnm.h:38-41); everything else that is not a digit is skipped; at most 15 digits are taken (pnm.h:45-54);
+ * the byte that ends the field is consumed -- behind the third field that is the one separator in front of the
+ * pixel data.  Returns 0 when the file ends first. */
+static int header_field(struct cursor *k, long *value)
+{
+	if (!advance(k))
+		return 0;
+	while (k->cur == '#') {
+		do {
+			if (!advance(k))
+				return 0;
+		} while (k->cur != '\n');
+		if (!advance(k))
+			return 0;
+	}
+	while (!is_digit(k->cur))
+		if (!advance(k))
+			return 0;
+	long v = 0;
+	for (int digits = 0; is_digit(k->cur) && digits < 15; ++digits) {
+		v = 10 * v + (k->cur - '0');
+		if (!advance(k))
+			return 0;
+	}
+	*value = v;
+	return 1;
+}
+
 uint8_t *dwt_read_pnm(const char *name, int *width, int *height, int *channels)
 {
 	const char *fname = real_name(name, "/dev/stdin");
-	FILE *file = fopen(fname, "r");
-	if (!file) {
+	struct cursor k = {fopen(fname, "r"), 0};
+	if (!k.file) {
 		fprintf(stderr, "could not open \"%s\" file to read.\n", fname);
 		return 0;
 	}
-	int letter = fgetc(file), number = fgetc(file);
-	if (letter != 'P' || (number != '5' && number != '6')) {
-		fprintf(stderr, "file \"%s\" neither P5 nor P6 image.\n", fname);
-		fclose(file);
-		return 0;
-	}
-	int ch = number == '5' ? 1 : 3;
-	int integer[3];
 	uint8_t *pix = 0;
-	int c = fgetc(file);
-	if (c == EOF)
-		goto eof;
-	for (int i = 0; i < 3; ++i) {
-		/* the reference looks at the next byte for '#': comment lines are skipped (pnm.h:38-41) */
-		while ((c = fgetc(file)) == '#')
-			while ((c = fgetc(file)) != '\n')
-				if (c == EOF)
-					goto eof;
-		while (c < '0' || c > '9')
-			if ((c = fgetc(file)) == EOF)
-				goto eof;
-		char str[16];
-		int n = 0;
-		while (c >= '0' && c <= '9' && n < 15) {
-			str[n++] = (char)c;
-			if ((c = fgetc(file)) == EOF)
-				goto eof;
-		}
-		str[n] = 0;
-		integer[i] = atoi(str);
-	}
-	if (!(integer[0] && integer[1] && integer[2])) {
-		fprintf(stderr, "could not read image file \"%s\".\n", fname);
-		fclose(file);
-		return 0;
-	}
-	if (integer[2] != 255) {
-		fprintf(stderr, "cant read \"%s\", only 8 bit per channel SRGB supported at the moment.\n", fname);
-		fclose(file);
-		return 0;
-	}
-	{
-		size_t total = (size_t)integer[0] * integer[1] * ch;
+	const char *complaint = 0;
+	int truncated = 0;
+	const int magic0 = fgetc(k.file), magic1 = fgetc(k.file);
+	long field[3] = {0, 0, 0}; /* width, height, maxval */
+	if (magic0 != 'P' || (magic1 != '5' && magic1 != '6')) {
+		complaint = "file \"%s\" neither P5 nor P6 image.\n";
+	} else if (!advance(&k) || !header_field(&k, &field[0]) || !header_field(&k, &field[1]) || !header_field(&k, &field[2])) {
+		truncated = 1;
+	} else if (!field[0] || !field[1] || !field[2]) {
+		complaint = "could not read image file \"%s\".\n";
+	} else if (field[2] != 255) { /* pnm.h:63-67 */
+		complaint = "cant read \"%s\", only 8 bit per channel SRGB supported at the moment.\n";
+	} else if (field[0] > 0x7fffffffL || field[1] > 0x7fffffffL) {
+		complaint = "could not read image file \"%s\".\n";
+	} else {
+		const int ch = magic1 == '5' ? 1 : 3;
+		const size_t total = (size_t)field[0] * (size_t)field[1] * ch;
 		pix = malloc(total ? total : 1);
-		if (!pix || fread(pix, 1, total, file) != total)
-			goto eof;
+		if (!pix || fread(pix, 1, total, k.file) != total) {
+			truncated = 1;
+		} else {
+			*width = (int)field[0];
+			*height = (int)field[1];
+			*channels = ch;
+		}
 	}
-	fclose(file);
-	*width = integer[0];
-	*height = integer[1];
-	*channels = ch;
+	if (truncated)
+		fprintf(stderr, "EOF while reading from \"%s\".\n", fname);
+	else if (complaint)
+		fprintf(stderr, complaint, fname);
+	fclose(k.file);
+	if (truncated || complaint) {
+		free(pix);
+		return 0;
+	}
 	return pix;
-eof:
-	fprintf(stderr, "EOF while reading from \"%s\".\n", fname);
-	fclose(file);
-	free(pix);
-	return 0;
 }
 
 int dwt_write_pnm(const char *name, const uint8_t *pixels, int width, int height, int channels)

@@ -58,15 +58,20 @@ int dwt_encode(dwt_ctx *ctx, const uint8_t *pixels, int width, int height, int c
 
 /* Decode a (possibly truncated) .dwt stream.  pixels_max < 0: no PIXELS argument (decode.c:165-171).
  * Returns 0 and a malloc()ed interleaved u8 image whose size may be smaller than the coded size when
- * the stream was truncated (decode.c:251-255); returns 1 where the reference exits 1 without output
- * (bad magic, short header, dimensions < 8, EOF inside root image or plane counts); -1 on CUDA errors. */
+ * the stream was truncated (decode.c:251-255).  Where the reference exits 1 without output the return value is
+ * positive: 1 when the stream ended inside the header, the root image or the plane counts (the reference's
+ * get_byte prints "reached end of file" there, bytes.h:99-103), 2 when the magic is wrong or a dimension is
+ * below 8 (decode.c:146-159: silent).  -1 on CUDA errors. */
 int dwt_decode(dwt_ctx *ctx, const uint8_t *stream, size_t len, int pixels_max,
                uint8_t **pixels, int *width, int *height, int *channels, struct dwt_stats *stats);
 
 void dwt_free(void *p);
 
 /* Device-resident variants used by the benchmark: the image / stream is uploaded once, the kernels run
- * on data already in HBM, and results stay in HBM until downloaded.  Same return conventions. */
+ * on data already in HBM, and results stay in HBM until downloaded.  Same return conventions.
+ * dwt_ctx_upload_image() only queues its copy: the caller's buffer must stay untouched until the next
+ * dwt_ctx_encode_resident() or dwt_ctx_sync() on the context has returned (dwt_ctx_upload_stream() waits
+ * for its copy itself). */
 int dwt_ctx_upload_image(dwt_ctx *ctx, const uint8_t *pixels, int width, int height, int channels);
 int dwt_ctx_encode_resident(dwt_ctx *ctx, int capacity, struct dwt_stats *stats);
 int dwt_ctx_download_stream(dwt_ctx *ctx, uint8_t **out, size_t *out_len);
@@ -116,6 +121,9 @@ typedef struct dwt_pool dwt_pool;
 dwt_pool *dwt_pool_create(int device, int workers);
 void dwt_pool_destroy(dwt_pool *pool);
 int dwt_pool_workers(const dwt_pool *pool);
+/* why the most recent failed item of the pool failed (dwt_last_error() is per thread and the items run on the
+ * pool's own threads); "" when nothing has failed yet.  Valid until the next batch call on the pool. */
+const char *dwt_pool_last_error(const dwt_pool *pool);
 int dwt_pool_encode(dwt_pool *pool, struct dwt_encode_item *items, int n);
 int dwt_pool_decode(dwt_pool *pool, struct dwt_decode_item *items, int n);
 /* both kinds of item in one call, interleaved on the workers (pixel uploads overlap pixel downloads) */
