@@ -17,6 +17,7 @@ ABI_SYMBOLS = [
     "dwt_ctx_create", "dwt_ctx_destroy", "dwt_last_error", "dwt_encode", "dwt_decode", "dwt_free",
     "dwt_ctx_upload_image", "dwt_ctx_encode_resident", "dwt_ctx_download_stream", "dwt_ctx_upload_stream",
     "dwt_ctx_decode_resident", "dwt_ctx_download_image", "dwt_ctx_launch_count", "dwt_ctx_sync", "dwt_ctx_set_in_flight",
+    "dwt_ctx_set_decoder_scan",
     "dwt_host_alloc", "dwt_host_free", "dwt_encode_into", "dwt_decode_into", "dwt_ctx_flush_l2",
     "dwt_ctx_event_record", "dwt_ctx_event_elapsed_ms", "dwt_ctx_wait_for",
     "dwt_pool_create", "dwt_pool_destroy", "dwt_pool_workers", "dwt_pool_last_error", "dwt_pool_encode", "dwt_pool_decode", "dwt_pool_run",
@@ -98,6 +99,7 @@ def lib():
     L.dwt_ctx_event_elapsed_ms.restype = C.c_float
     L.dwt_ctx_wait_for.argtypes = [vp, vp]
     L.dwt_ctx_set_in_flight.argtypes = [vp, C.c_int]
+    L.dwt_ctx_set_decoder_scan.argtypes = [vp, C.c_int]
     L.dwt_pool_create.argtypes = [C.c_int, C.c_int]
     L.dwt_pool_create.restype = vp
     L.dwt_pool_destroy.argtypes = [vp]
@@ -270,6 +272,11 @@ class Codec:
         """how many contexts the caller keeps busy on this device at once (throughput- vs latency-oriented kernels)"""
         if lib().dwt_ctx_set_in_flight(self._h, int(contexts)):
             raise DwtError("set_in_flight failed")
+
+    def set_scan(self, mode):
+        """pin the decoder's scan kernel: "auto", "parallel" or "serial" (dwt_ctx_set_decoder_scan)"""
+        if lib().dwt_ctx_set_decoder_scan(self._h, {"auto": 0, "parallel": 1, "serial": 2}[mode]):
+            raise DwtError("set_decoder_scan failed")
 
     def wait_for(self, other):
         """this context's stream waits for the work queued so far on `other`'s stream"""

@@ -401,6 +401,14 @@ extern "C" int dwt_ctx_set_in_flight(dwt_ctx *c, int contexts)
 	return 0;
 }
 
+extern "C" int dwt_ctx_set_decoder_scan(dwt_ctx *c, int mode)
+{
+	if (!c || mode < 0 || mode > 2)
+		return -1;
+	c->scan_mode = mode;
+	return 0;
+}
+
 extern "C" dwt_pool *dwt_pool_create(int device, int workers)
 {
 	if (workers < 1)

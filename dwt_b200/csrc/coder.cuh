@@ -107,6 +107,7 @@ struct DecBuffers {
 	u64 end_bits;
 	u32 nwin;             // scan windows covering the stream
 	int in_flight;        // contexts the caller keeps busy on this device (dwt_ctx_set_in_flight): picks the scan kernel
+	int scan_mode;        // 0: by in_flight and stream size, 1: parallel scan kernel, 2: serial scan kernel
 	u32 *E;               // per slice: canonical entry states of the two classes (e0 | e1 << 16)
 	ulonglong2 *P;        // per slice: members consumed by each class since the window start
 	u32 *TK;              // per slice: tokens started by each class since the window start (t0 | t1 << 16)

@@ -1383,7 +1383,8 @@ void dec_token_table(u32 *host_table)
 
 int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b, int nchunks, cudaStream_t st, long long *launches)
 {
-	if (b.nwin >= DEC_SERIAL_MIN_WINDOWS && b.in_flight >= DEC_SERIAL_MIN_IN_FLIGHT)
+	const bool serial = b.scan_mode == 2 || (b.scan_mode == 0 && b.nwin >= DEC_SERIAL_MIN_WINDOWS && b.in_flight >= DEC_SERIAL_MIN_IN_FLIGHT);
+	if (serial)
 		dec_scan_serial_kernel<<<(2 * b.nwin + 127) / 128, 128, 0, st>>>(b.stream, b.end_bits, b.toklut, b.nwin, b.E, b.P, b.TK,
 		                                                                  b.winX, b.winPT, b.winTT);
 	else

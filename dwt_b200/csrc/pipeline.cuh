@@ -55,6 +55,7 @@ struct dwt_ctx {
 	DevBuf dec_lut;    // decoder: order-0 token table
 	bool dec_lut_ready = false;
 	int sm_count = 1;
+	int scan_mode = 0;   // dwt_ctx_set_decoder_scan: 0 auto, 1 parallel, 2 serial
 	int in_flight = 1;   // contexts the caller keeps busy on this device (throughput- vs latency-oriented kernels)
 	PinBuf pin_small, pin_io, pin_stream;
 

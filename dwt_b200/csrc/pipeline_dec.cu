@@ -267,6 +267,7 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		b.end_bits = end_bits;
 		b.nwin = (u32)nwin;
 		b.in_flight = c->in_flight;
+		b.scan_mode = c->scan_mode;
 		char *sp = c->dec_scan.as<char>();
 		b.P = (ulonglong2 *)sp;
 		sp += nslice * 16;

@@ -84,6 +84,10 @@ int dwt_ctx_sync(dwt_ctx *ctx);
 /* number of contexts the caller keeps busy on this device at the same time (default 1; dwt_pool sets its worker count):
  * with several frames in flight the library prefers kernels that do less total work over lower single-frame latency */
 int dwt_ctx_set_in_flight(dwt_ctx *ctx, int contexts);
+/* testing aid: pin the decoder's stream-scan kernel.  0 = choose by stream size and the in-flight hint (default),
+ * 1 = one CTA per scan window (lowest latency), 2 = one thread per window and chain (least work).  Both produce the
+ * same tables; the parity tests run every corrupted stream through both. */
+int dwt_ctx_set_decoder_scan(dwt_ctx *ctx, int mode);
 
 /* Caller-owned buffer variants of dwt_encode / dwt_decode (same semantics and return values; -1 with
  * *out_len = needed size when the buffer is too small).  With buffers from dwt_host_alloc() (page-locked

@@ -1,7 +1,7 @@
 """Generate tests/golden/pins.json from the UNMODIFIED reference programs (oracle/_ref/encode, decode).
 
 Run in the build container (where /root/reference exists and oracle/Makefile has built oracle/_ref):
-    python tests/golden/make_golden.py [--big]
+    python tests/golden/make_golden.py [--big | --batch]
 
 Inputs are the integer-only synthetic images of SURVEY.md App. E.2 (oracle.pyoracle.synth), so they can be
 regenerated anywhere; only hashes, sizes and a few short streams are stored.  Every record is produced by
@@ -63,7 +63,32 @@ def record(spec, caps, pixel_args, keep_stream=False):
     return rec
 
 
+def batch_pins():
+    """BASELINE config 4: 64 of the 4096 per-image seeds of the 1080p batch through the reference encoder (8 at a time)"""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(seed):
+        img = O.synth(1920, 1080, "photo", seed)
+        full = O.ref_encode(img)
+        rec = dict(seed=seed, len=len(full), sha=sha(full))
+        if seed < 8:
+            cut = O.ref_encode(img, 200000)
+            assert cut == full[:200000]
+            rec["sha_cap200000"] = sha(cut)
+        return rec
+    seeds = list(range(8)) + [8 + 73 * k for k in range(56)]   # spread over 0..4095
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        out = list(ex.map(one, seeds))
+    with open(os.path.join(HERE, "pins_batch.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    print("wrote pins_batch.json", len(out), "records")
+
+
 def main():
+    if "--batch" in sys.argv:
+        if not O.have_ref():
+            raise SystemExit("oracle/_ref is not built: run `make -C oracle` where /root/reference exists")
+        return batch_pins()
     big = "--big" in sys.argv
     if not O.have_ref():
         raise SystemExit("oracle/_ref is not built: run `make -C oracle` where /root/reference exists")

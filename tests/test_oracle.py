@@ -102,3 +102,67 @@ def test_smpte_pins(oracle):
         assert sha(s)[:32] == s_pin
         d = oracle.decode(s)
         assert sha(oracle.pnm_bytes(d))[:32] == d_pin
+
+
+def test_oracle_corrupted_payloads_match_reference_program(oracle):
+    """bit flips inside the payload and random tails (tests/fuzz_util.py): the restatement must decode what the unmodified
+    reference program decodes -- this is what lets the GPU fuzz test use the oracle as its checker"""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    from tests import fuzz_util as F
+    compared = 0
+    for i in range(0, F.N_CASES, 2):
+        desc, s = F.fuzz_case(i)
+        kind, ref = F.ref_decode_guarded(s)
+        if kind == "undefined":
+            continue
+        mine = oracle.decode(s)
+        assert (mine is None) == (ref is None), (i, desc)
+        if ref is not None:
+            assert mine.shape == ref.shape and np.array_equal(mine, ref), (i, desc)
+        compared += 1
+    assert compared >= 100
+
+
+def test_pnm_reader_accepts_what_the_reference_accepts(oracle, tmp_path):
+    """dwt_b200/host/pnm.c (a tokenizer) against read_pnm of pnm.h:14-80 through the reference encoder's exit status and
+    output: comment lines, odd separators, 15-digit fields, missing fields, wrong maxval, truncated pixel data"""
+    import ctypes as C
+    import subprocess
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = tmp_path / "pnm.so"
+    subprocess.run(["gcc", "-std=c99", "-O1", "-shared", "-fPIC", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "dwt_b200", "host", "pnm.c"), "-o", str(so)], check=True)
+    L = C.CDLL(str(so))
+    L.dwt_read_pnm.restype = C.POINTER(C.c_uint8)
+    L.dwt_read_pnm.argtypes = [C.c_char_p] + [C.POINTER(C.c_int)] * 3
+    px = bytes(range(192))
+    gray = bytes(range(64))
+    cases = [b"P6\n8 8\n255\n" + px, b"P6 8 8 255\n" + px, b"P6\n# one\n# two\n8 8\n255\n" + px, b"P6\n8\n# c\n8\n# d\n255\n" + px,
+             b"P6\t8\r\n8  255 " + px, b"P6\n 8 8 255\n" + px, b"P6x8y8z255q" + px, b"P5\n8 8\n255\n" + gray, b"P6\n08 008\n0255\n" + px,
+             b"P6\n8 8\n65535\n" + px, b"P6\n8 8\n254\n" + px, b"P6\n0 8\n255\n" + px, b"P6\n8 8\n255\n" + px[:100], b"P6\n8 8\n255",
+             b"P6\n8 8\n", b"P6", b"P", b"", b"P7\n8 8\n255\n" + px, b"P6\n8 8\n255\n\n" + px, b"P6\n  # not a comment 9 9\n8 8\n255\n" + px + px,
+             b"P6\n000000000000008 8 255\n" + px, b"P6\n8 8 255#" + px, b"P6#\n8 8 255\n" + px]
+    for i, data in enumerate(cases):
+        f, o = tmp_path / ("c%d.pnm" % i), tmp_path / ("c%d.dwt" % i)
+        f.write_bytes(data)
+        r = subprocess.run([os.path.join(oracle.REF_DIR, "encode"), str(f), str(o)], capture_output=True)
+        w, h, ch = C.c_int(), C.c_int(), C.c_int()
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(2)
+        os.dup2(devnull, 2)
+        try:
+            p = L.dwt_read_pnm(str(f).encode(), C.byref(w), C.byref(h), C.byref(ch))
+        finally:
+            os.dup2(saved, 2)
+            os.close(saved)
+            os.close(devnull)
+        ref_ok = r.returncode == 0
+        ours_ok = bool(p) and w.value >= 8 and h.value >= 8   # the 8x8 minimum is main()'s test (encode.c:144-146)
+        assert ours_ok == ref_ok, (i, data[:24])
+        if ref_ok:
+            img = np.ctypeslib.as_array(p, shape=(w.value * h.value * ch.value,)).copy()
+            shape = (h.value, w.value, 3) if ch.value == 3 else (h.value, w.value)
+            assert o.read_bytes() == oracle.encode(img.reshape(shape))[0], i
