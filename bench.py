@@ -13,8 +13,11 @@ one CUDA stream + one host thread per frame; images are independent).  Mpixel/s 
   single_frame / stages / roofline : a pass with ONE frame at a time, so that every kernel runs alone on the GPU
 Images are independent, so ranks shard frames with no collective on the data path ("weak" scaling: one frame
 stream per GPU); torch.distributed is only the barrier and the max-over-ranks of the timing.
+  configs : every BASELINE.json config behind its reference pin -- 4K lossless, 8K at the 64 KiB / 1 MiB / 8 MiB budgets
+          (encode and decode), 16384 x 16384, and the batch of 1920x1080 images through dwt_pool from host buffers
+          (per-rank seeds; the one config that is also reported at N > 1)
 --impl reference times the UNMODIFIED reference programs (oracle/_ref, built by oracle/Makefile) on the host
-cores, on bands of the same frame (one process per band).
+cores, on bands of the same frame (one process per band), and once on the whole 8K frame (one process).
 """
 import argparse
 import json
@@ -38,6 +41,14 @@ sys.path.insert(0, ROOT)
 W, H, CH = 7680, 4320, 3
 WORKLOAD = "synthetic 7680x4320 RGB 'photo' frame (SURVEY App. E.2, seed = rank+1), lossless encode + decode round trip"
 LIFT_BYTES_PER_PIXEL = 23.0   # u8 in (colour fused), int32 between levels, RGB
+BATCH_W, BATCH_H = 1920, 1080  # BASELINE config 4: images of the batch
+# reference pins of the single-image configs (tests/golden/pins_big.json): stream length, sha256[:32] of
+# the stream, shape and sha256[:32] of the decoded pixels
+PIN_4K = (12216090, "63f44307a0de6ba2a26ae9074d724298")
+PIN_8K_CAPS = {65536: ("66fb128c746d9933afd5c104a7198fb1", (2160, 3840, 3)),
+               1048576: ("eee08d5ce1e3e02bf111483c9c6cbd03", (4320, 7680, 3)),
+               8388608: ("26c40605427826496473915b202408d7", (4320, 7680, 3))}
+PIN_16K = (395131715, "c77d5aff9242788e9bb23170a7ee730d")
 L2_NOTE = ("inputs larger than L2: a step touches ~1.5 GB per frame (126 MB L2); L2 flushed (256 MB write) before the timed "
            "region and between the frames of the single-frame pass")
 
@@ -142,6 +153,29 @@ def reference_step(paths, workers):
     return dt
 
 
+def reference_single_process_8k():
+    """the stock reference programs on the whole 8K frame, one process: seconds for encode / decode"""
+    from oracle import pyoracle as O
+    tmp = tempfile.mkdtemp(prefix="dwtref8k", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        src, out, back = os.path.join(tmp, "f.pnm"), os.path.join(tmp, "f.dwt"), os.path.join(tmp, "b.pnm")
+        with open(src, "wb") as f:
+            f.write(O.pnm_bytes(O.synth(W, H, "photo", 1)))
+        t0 = time.perf_counter()
+        rc1 = subprocess.call([os.path.join(O.REF_DIR, "encode"), src, out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        t1 = time.perf_counter()
+        rc2 = subprocess.call([os.path.join(O.REF_DIR, "decode"), out, back], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        t2 = time.perf_counter()
+        if rc1 or rc2 or os.path.getsize(out) != 48863617:
+            raise RuntimeError("reference 8K run failed")
+        npx = W * H
+        return dict(encode_s=round(t1 - t0, 2), decode_s=round(t2 - t1, 2), encode_mpx_s=round(npx / (t1 - t0) / 1e6, 3),
+                    decode_mpx_s=round(npx / (t2 - t1) / 1e6, 3), round_trip_mpx_s=round(npx / (t2 - t0) / 1e6, 3), cores=1,
+                    sample="one reference encode + one decode process on the whole 7680x4320 frame, files in /dev/shm, CLI wall time")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def reference_bench(steps, warmup, quick=False):
     """Mpixel/s of the unmodified reference programs on the host cores: the 8K frame cut into 16 tiles of 1920x1080,
     one reference process per tile, as many at a time as there are cores (the reference is single-threaded)."""
@@ -191,6 +225,166 @@ def reduce_over_ranks(total_ms, e2e_ms, launches, device):
     l = torch.tensor([launches], dtype=torch.int64, device=device)
     dist.all_reduce(l, op=dist.ReduceOp.SUM)
     return float(t[0]), float(t[1]), int(l[0])
+
+
+def reduce_max(values, device):
+    """max over ranks of a list of floats (timings of the sharded batch config)"""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def batch_seeds(rank, distinct):
+    """BASELINE config 4: image i of the batch has seed i (0..4095); rank r owns the seeds r*512 .. r*512+511"""
+    return [rank * 512 + i for i in range(distinct)]
+
+
+def single_image_config(D, cod, img, caps, reps, check):
+    """one image, device resident: per capacity the encode time (CUDA events around all kernels of the call), the decode
+    time of that stream, and the same through the host-buffer calls (wall time incl. the copies).  check(cap, stream,
+    decoded) raises when the result is not the reference's."""
+    import hashlib
+    h, w = img.shape[:2]
+    npx = w * h
+    src, o1 = D.pinned_array(img.size)
+    src[:] = img.reshape(-1)
+    src = src.reshape(img.shape)
+    out, o2 = D.pinned_array(img.size + 4096)
+    dec, o3 = D.pinned_array(img.size)
+    res = {}
+    for cap in caps:
+        n = cod.encode_into(src, out, cap)           # also the warm-up: buffers of this geometry get allocated here
+        stream = out[:n].copy()
+        shp = cod.decode_into(out, n, dec)
+        check(cap, stream, dec[:shp[0] * shp[1] * shp[2]].reshape(shp))
+        cod.upload_image(src)
+        enc_ms, coder_ms = [], []
+        for _ in range(reps):
+            cod.flush_l2()
+            st = cod.encode_resident(cap)
+            enc_ms.append(st.ms_total)
+            coder_ms.append(st.ms_coder)
+        cod.upload_stream(stream)
+        dec_ms, dcoder_ms = [], []
+        for _ in range(reps):
+            cod.flush_l2()
+            cod.decode_resident(-1)
+            dec_ms.append(cod.stats.ms_total)
+            dcoder_ms.append(cod.stats.ms_coder)
+        t0 = time.perf_counter()
+        cod.encode_into(src, out, cap)
+        t1 = time.perf_counter()
+        cod.decode_into(out, n, dec)
+        t2 = time.perf_counter()
+        e, d = statistics.median(enc_ms), statistics.median(dec_ms)
+        res[cap] = dict(stream_bytes=int(n), decoded_shape=list(shp), parity="reference pin ok",
+                        encode_ms=round(e, 4), decode_ms=round(d, 4), encode_coder_ms=round(statistics.median(coder_ms), 4),
+                        decode_coder_ms=round(statistics.median(dcoder_ms), 4),
+                        encode_mpx_s=round(npx / e / 1e3, 1), decode_mpx_s=round(npx / d / 1e3, 1),
+                        e2e_encode_ms=round((t1 - t0) * 1e3, 3), e2e_decode_ms=round((t2 - t1) * 1e3, 3),
+                        e2e_encode_mpx_s=round(npx / (t1 - t0) / 1e6, 1), e2e_decode_mpx_s=round(npx / (t2 - t1) / 1e6, 1))
+    del o1, o2, o3
+    return res
+
+
+def single_image_suite(D, O, cod, img8k, reps=5):
+    """4K lossless, 8K with the three byte budgets, 16384 x 16384 -- each behind its reference pin"""
+    import hashlib
+
+    def sha(b):
+        return hashlib.sha256(bytes(b)).hexdigest()[:32]
+    out = {}
+
+    img4k = O.synth(3840, 2160, "photo", 1)
+
+    def check4k(cap, stream, dec):
+        assert (len(stream), sha(stream)) == PIN_4K, "4K stream differs from the reference pin"
+        assert np.array_equal(dec, img4k), "4K round trip is not lossless"
+    out["4k_lossless"] = dict(workload="synthetic 3840x2160 RGB photo (seed 1), lossless",
+                              **single_image_config(D, cod, img4k, [0], reps, check4k)[0])
+
+    with open(os.path.join(ROOT, "tests", "golden", "pins_big.json")) as f:
+        big = [r for r in json.load(f) if r["spec"] == dict(kind="photo", w=W, h=H, seed=1)][0]
+    dec_pin = {c["cap"]: c["decoded"] for c in big["cases"]}
+
+    def check8k(cap, stream, dec):
+        pin, shape = PIN_8K_CAPS[cap]
+        assert len(stream) == cap and sha(stream) == pin, "8K stream at %d bytes differs from the reference pin" % cap
+        assert tuple(dec.shape) == shape == tuple(dec_pin[cap]["shape"])
+        assert hashlib.sha256(np.ascontiguousarray(dec).tobytes()).hexdigest() == dec_pin[cap]["sha"], \
+            "8K decode at %d bytes differs from the reference" % cap
+    r8 = single_image_config(D, cod, img8k, sorted(PIN_8K_CAPS), reps, check8k)
+    for cap, name in [(65536, "8k_cap_64KiB"), (1048576, "8k_cap_1MiB"), (8388608, "8k_cap_8MiB")]:
+        out[name] = dict(workload="synthetic 7680x4320 RGB photo (seed 1), capacity %d bytes" % cap, **r8[cap])
+
+    img16 = O.synth(16384, 16384, "photo", 1)
+
+    def check16k(cap, stream, dec):
+        assert (len(stream), sha(stream)) == PIN_16K, "16384^2 stream differs from the reference pin"
+        assert np.array_equal(dec, img16), "16384^2 round trip is not lossless"
+    out["16384sq_lossless"] = dict(workload="synthetic 16384x16384 RGB photo (seed 1), lossless, 12 levels",
+                                   **single_image_config(D, cod, img16, [0], max(2, reps // 2), check16k)[0])
+    return out
+
+
+def batch_config(D, O, device, rank, n_images, workers, keep):
+    """BASELINE config 4 on this rank's GPU: n_images 1920x1080 images through dwt_pool from page-locked host buffers.
+    Returns (encode seconds, decode seconds, info).  Gate: the streams of the pinned seeds equal the reference's
+    (tests/golden/pins_batch.json) and every decoded image equals its source."""
+    import hashlib
+    distinct = min(n_images, 128)
+    seeds = batch_seeds(rank, distinct)
+    imgs = [O.synth(BATCH_W, BATCH_H, "photo", sd) for sd in seeds]
+    raw = BATCH_W * BATCH_H * CH
+    out_room = raw + 4096
+    pool = D.Pool(device, workers)
+    src, outs, decs = [], [], []
+    for i in range(distinct):
+        a, o = D.pinned_array(raw)
+        a[:] = imgs[i].reshape(-1)
+        keep.append(o)
+        src.append(a)
+    enc = (D.EncodeItem * n_images)()
+    dec = (D.DecodeItem * n_images)()
+    for i in range(n_images):
+        b, o2 = D.pinned_array(out_room)
+        c, o3 = D.pinned_array(raw)
+        keep.extend([o2, o3])
+        outs.append(b)
+        decs.append(c)
+        enc[i] = D.EncodeItem(src[i % distinct].ctypes.data, BATCH_W, BATCH_H, CH, 0, b.ctypes.data, b.size, 0, 0)
+    warm = min(n_images, 2 * workers)
+    assert pool.encode_items(enc, warm) == 0
+    for i in range(warm):
+        dec[i] = D.DecodeItem(outs[i].ctypes.data, enc[i].out_len, -1, decs[i].ctypes.data, raw, 0, 0, 0, 0)
+    assert pool.decode_items(dec, warm) == 0
+    t0 = time.perf_counter()
+    bad = pool.encode_items(enc, n_images)
+    t_enc = time.perf_counter() - t0
+    assert bad == 0, "batch encode failed"
+    for i in range(n_images):
+        dec[i] = D.DecodeItem(outs[i].ctypes.data, enc[i].out_len, -1, decs[i].ctypes.data, raw, 0, 0, 0, 0)
+    t0 = time.perf_counter()
+    bad = pool.decode_items(dec, n_images)
+    t_dec = time.perf_counter() - t0
+    assert bad == 0, "batch decode failed"
+    pool.close()
+    with open(os.path.join(ROOT, "tests", "golden", "pins_batch.json")) as f:
+        pins = {p["seed"]: p for p in json.load(f)}
+    checked = 0
+    for i in range(distinct):
+        p = pins.get(seeds[i])
+        if p:
+            n = enc[i].out_len
+            assert (n, hashlib.sha256(outs[i][:n].tobytes()).hexdigest()) == (p["len"], p["sha"]), "batch seed %d differs from the reference" % seeds[i]
+            checked += 1
+    for i in range(n_images):
+        assert np.array_equal(decs[i], src[i % distinct]), "batch image %d does not round-trip" % i
+    stream_bytes = sum(int(enc[i].out_len) for i in range(n_images))
+    return t_enc, t_dec, dict(images_per_gpu=n_images, distinct_seeds_per_gpu=distinct, pool_workers=workers, pinned_seeds_checked=checked,
+                              stream_bytes_per_gpu=stream_bytes, raw_bytes_per_gpu=n_images * raw)
 
 
 def our_bench(args, rank, world, local):
@@ -359,15 +553,51 @@ def our_bench(args, rank, world, local):
     assert np.array_equal(jobs[4][-1], pin_img[(jobs[0] - 1) % F].reshape(-1)), "end-to-end round trip is not lossless"
     assert bytes(jobs[3][0][:stream_bytes]) == bytes(pin_out[0][:stream_bytes]), "end-to-end stream differs from the gate's"
     dpool.close()
+    # the page-locked job buffers of the passes above (~8 GB) go back before the batch config takes its own
+    del jobs, warm_jobs, pin_img, pin_out, pin_dec
+    keep.clear()
+    import gc
+    gc.collect()
+
+    # ---- per-config numbers (BASELINE.json configs), each behind its reference pin
+    mode = args.configs if args.configs != "auto" else ("all" if world == 1 else "batch")
+    configs = {}
+    batch = None
+    if mode in ("all", "batch"):
+        nb = max(1, args.batch_images)
+        t_enc, t_dec, binfo = batch_config(D, O, local, rank, nb, 16, keep)
+        barrier()
+        batch = (t_enc, t_dec, binfo)
+    if mode == "all" and rank == 0:
+        for cd in cods[1:]:
+            cd.close()
+        cod.set_in_flight(1)
+        configs.update(single_image_suite(D, O, cod, img))
 
     # ---- max over ranks
     if use_dist:
         total_ms, e2e_total, launches = reduce_over_ranks(total_ms, e2e_total, launches, torch.device("cuda", local))
+        if batch:
+            t_enc, t_dec = reduce_max(batch[:2], torch.device("cuda", local))
+            batch = (t_enc, t_dec, batch[2])
     if rank != 0:
         if use_dist:
             dist.destroy_process_group()
         return None
 
+    if batch:
+        t_enc, t_dec, binfo = batch
+        n_all = binfo["images_per_gpu"] * world
+        bpx = BATCH_W * BATCH_H
+        configs["batch_1080p"] = dict(
+            workload="batch of 1920x1080 RGB photo images (seeds rank*512+i), lossless, through dwt_pool_encode / dwt_pool_decode "
+                     "from page-locked host buffers (copies inside the timed calls); one call per direction per GPU, max over ranks",
+            images=n_all, n_gpus=world, parity="pinned seeds equal the reference, every image round-trips", **binfo,
+            encode_s=round(t_enc, 4), decode_s=round(t_dec, 4),
+            encode_images_s=round(n_all / t_enc, 1), decode_images_s=round(n_all / t_dec, 1),
+            encode_mpx_s=round(n_all * bpx / t_enc / 1e6, 1), decode_mpx_s=round(n_all * bpx / t_dec / 1e6, 1),
+            h2d_bytes=int(world * (binfo["raw_bytes_per_gpu"] + binfo["stream_bytes_per_gpu"])),
+            d2h_bytes=int(world * (binfo["raw_bytes_per_gpu"] + binfo["stream_bytes_per_gpu"])))
     value = job_mpixels_per_s(npx * F, args.steps, world, total_ms)
     e2e_value = job_mpixels_per_s(npx * F, args.steps, world, e2e_total)
     peak, peak_kind = peaks()
@@ -399,6 +629,19 @@ def our_bench(args, rank, world, local):
         dec_coder=dict(roof(med["dec_coder"], 4 * nsamples + stream_bytes), kernel="dec_* (scan, link, resolve, emit, prep/tilescan/deposit per plane depth)"),
         reconstruct=dict(roof(med["reconstruct"], 4 * nsamples + nsamples * 10 / 8), kernel="reconstruct_full_kernel + reconstruct_kernel (Hilbert scatter + bias)"),
     )
+    stage_bytes = {k: v["bytes"] for k, v in stages.items()}
+    frame_bytes = sum(stage_bytes.values())          # SURVEY 8(d) algorithmic bytes of all six stages of a round trip
+    single_ms = statistics.median(serial_ms)
+    dominant = max(stages, key=lambda k: stages[k]["ms"])
+    whole_frame = dict(bound="hbm", unit="GB/s", peak=peak, bytes=int(frame_bytes),
+                       in_flight=dict(ms_per_frame=round(total_ms / args.steps / F, 4),
+                                      achieved=round(frame_bytes / (total_ms / args.steps / F / 1e3) / 1e9, 1),
+                                      frac=round(frame_bytes / (total_ms / args.steps / F / 1e3) / 1e9 / peak, 4)),
+                       single_frame=dict(ms_per_frame=round(single_ms, 4), achieved=round(frame_bytes / (single_ms / 1e3) / 1e9, 1),
+                                         frac=round(frame_bytes / (single_ms / 1e3) / 1e9 / peak, 4)),
+                       time_dominant_stage=dominant, time_dominant_share=round(stages[dominant]["ms"] / single_ms, 3),
+                       note="sum of the six stages' algorithmic bytes (lifting 23 B/pixel each way, Hilbert 4 B/sample + planes/8, "
+                            "coder 4 B/sample + stream) over the time of a whole encode + decode")
     out = dict(metric="encode/decode Mpixel/s, 8K RGB", value=round(value, 2), unit="Mpixel/s", n_gpus=world, steps=args.steps,
                warmup=args.warmup, ms_per_step=round(total_ms / args.steps, 3), higher_is_better=True, scaling="weak",
                vs_baseline=None, dtype="int32", data="synthetic",
@@ -411,7 +654,7 @@ def our_bench(args, rank, world, local):
                         d2h_bytes_per_step=int(world * F * (stream_bytes + img.size)),
                         api="dwt_pool_run: dwt_encode_into of %d frames + dwt_decode_into of %d streams per step, interleaved on %d contexts, "
                             "page-locked host buffers, the K steps in one call (runs of more than ~50 jobs: several calls on the same buffers)" % (F, F, 2 * F)),
-               gpu_launches=int(launches), clocks=clocks, roofline=roofline, stages=stages,
+               gpu_launches=int(launches), clocks=clocks, roofline=roofline, stages=stages, whole_frame=whole_frame, configs=configs,
                single_frame=dict(ms_per_frame=round(statistics.median(serial_ms), 3),
                                  mpixel_s=round(npx / (statistics.median(serial_ms) / 1e3) / 1e6, 1),
                                  encode_mpx_s=round(npx / (med["enc"] / 1e3) / 1e6, 1),
@@ -436,6 +679,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pool-workers", type=int, default=0, help="contexts of the end-to-end pool (default 2 x frames)")
     ap.add_argument("--frames", type=int, default=8, help="frames per step, coded concurrently (one context each)")
+    ap.add_argument("--configs", default="auto", choices=["auto", "all", "batch", "none"],
+                    help="per-config numbers: auto = all at N=1, only the sharded batch config at N>1")
+    ap.add_argument("--batch-images", type=int, default=512, help="1920x1080 images per GPU in the batch config")
+    ap.add_argument("--no-single-process-8k", action="store_true", help="reference arm: skip the one-process run on the whole frame")
     args = ap.parse_args()
     rank, world, local = dist_env()
     # the one JSON line goes to the real stdout; anything a library prints to fd 1 meanwhile (the NCCL version banner) is
@@ -447,11 +694,18 @@ def main():
         if rank != 0:
             return 0
         r = reference_bench(max(1, args.steps), max(0, args.warmup))
+        single = None
+        if not args.no_single_process_8k:
+            try:
+                single = reference_single_process_8k()
+            except Exception as ex:
+                single = dict(unavailable=str(ex))
         line = dict(impl="reference", metric="encode/decode Mpixel/s, 8K RGB", value=round(r["value"], 3), unit="Mpixel/s",
                     n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=round(r["ms_per_step"], 1),
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32", data="synthetic",
                     config=dict(workload=WORKLOAD, sample=r["sample"]),
-                    cpu_baseline=dict(value=round(r["value"], 3), unit="Mpixel/s", cores=r["cores"], kind="reference", sample=r["sample"]),
+                    cpu_baseline=dict(value=round(r["value"], 3), unit="Mpixel/s", cores=r["cores"], kind="reference", sample=r["sample"],
+                                      single_process_8k=single),
                     e2e=dict(value=round(r["value"], 3), unit="Mpixel/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()

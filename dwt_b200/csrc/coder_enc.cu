@@ -156,22 +156,42 @@ __global__ void __launch_bounds__(1024) enc_scan_fix_kernel(u32 *ez, u32 *e1, u3
 	}
 }
 
+// slack behind the capacity before a chunk counts as unreachable: keeps "the stream is longer than the capacity" certain
+// for the host's stderr counters (a cut stream reports 8 * capacity bits, encode.c:226-230)
+constexpr u64 CUT_SLACK_BITS = 64;
+
 __global__ void __launch_bounds__(1024) enc_chunk_setup_kernel(const Sched *__restrict__ S, const u32 *ez, const u32 *e1,
                                                                 const u32 *er, EncChunks *C, EncInfo *info, u32 *Z,
-                                                                u32 *specbuf, u32 max_tokens)
+                                                                u32 *specbuf, u32 max_tokens, u64 prefix_bits, u64 limit_bits)
 {
 	__shared__ u64 ws[32];
+	__shared__ int s_jcut;
 	const int J = S->nchunks;
 	const int per = (J + 1 + 1023) / 1024;
 	const int b = threadIdx.x * per, e = min(b + per, J);
 	const u32 tz = (u32)info->tot_zero, t1 = (u32)info->tot_one, tr = (u32)info->tot_ref;
+	if (threadIdx.x == 0)
+		s_jcut = J;
+	__syncthreads();
+	// capacity cut: a one costs at least 2 bits (VLI >= 1 bit, sign), a refinement bit 1 -- the first chunk whose lower
+	// bound lies behind the capacity, and every chunk after it, cannot reach the output (bytes.h:77-78)
+	if (limit_bits) {
+		for (int j = b; j < e; ++j) {
+			const u64 lb = prefix_bits + 2ull * e1[S->ebase[j]] + er[S->ebase[j]];
+			if (lb >= limit_bits + CUT_SLACK_BITS) {
+				atomicMin(&s_jcut, j);
+				break;
+			}
+		}
+	}
 	u64 nf = 0;
 	for (int j = b; j < e; ++j) {
 		u32 r0 = er[S->ebase[j]], r1 = j + 1 < J ? er[S->ebase[j + 1]] : tr;
 		nf += (r1 != r0);
 	}
 	u64 tot;
-	u64 F = block_exscan_u64(nf, ws, &tot);
+	u64 F = block_exscan_u64(nf, ws, &tot); // syncs: s_jcut is final behind it
+	const int jcut = s_jcut;
 	for (int j = b; j < e; ++j) {
 		const int e0 = S->ebase[j];
 		u32 r0 = er[e0], r1 = j + 1 < J ? er[S->ebase[j + 1]] : tr;
@@ -184,21 +204,32 @@ __global__ void __launch_bounds__(1024) enc_chunk_setup_kernel(const Sched *__re
 		C->ref_pos[j] = 0;
 		if (r1 != r0) { // flush candidate right after the chunk's last 1 (rle.h:79-89)
 			u32 t = o1 + (u32)F;
-			if (t < max_tokens) {
+			if (t < max_tokens && j < jcut) {
 				Z[t + 1] = z1;
 				atomicOr(specbuf + (t >> 5), 1u << (t & 31));
 			}
 			++F;
 		}
 	}
+	__syncthreads(); // tok_start / ref_start of chunk jcut (written by its owner) are read by thread 0
 	if (threadIdx.x == 0) {
 		u32 tf = t1 + (u32)tot; // final rle_flush token (rle.h:37-40)
+		u32 zf = tz;
 		C->tok_start[J] = tf;
 		C->tok_adj[J] = (u32)tot;
 		C->ref_start[J] = tr;
+		info->jcut = jcut;
+		info->ref_cut = tr;
+		if (jcut < J) {
+			// the token list ends in front of chunk jcut; its last entry stands for "whatever follows": it is placed
+			// behind the capacity, so its bits never reach the output (enc_scatter clips at the capacity)
+			tf = C->tok_start[jcut];
+			zf = ez[S->ebase[jcut]];
+			info->ref_cut = C->ref_start[jcut];
+		}
 		Z[0] = 0;
 		if (tf < max_tokens) {
-			Z[tf + 1] = tz;
+			Z[tf + 1] = zf;
 			atomicOr(specbuf + (tf >> 5), 1u << (tf & 31));
 		} else {
 			info->error = 3;
@@ -213,12 +244,16 @@ __global__ void __launch_bounds__(1024) enc_chunk_setup_kernel(const Sched *__re
 __global__ void __launch_bounds__(TG) enc_emit_kernel(const __grid_constant__ Geom G, const Sched *__restrict__ S,
                                                        const u32 *__restrict__ bs, const u32 *__restrict__ ez,
                                                        const u32 *__restrict__ e1, const u32 *__restrict__ er,
-                                                       const EncChunks *__restrict__ C, u32 *Z, u32 *signbuf, u32 *refbuf)
+                                                       const EncChunks *__restrict__ C, const EncInfo *__restrict__ info, u32 *Z,
+                                                       u32 *signbuf, u32 *refbuf)
 {
 	__shared__ u64 ws[32];
 	int c, l, i;
 	tile_coords(G, blockIdx.x, c, l, i);
 	const int P = S->planes[c];
+	const int jcut = info->jcut; // chunks from here on lie behind the capacity (enc_chunk_setup_kernel)
+	if (P == 0 || S->chunk_of[c][l][P - 1] >= jcut)
+		return; // the planes of a (channel, level) are coded top down: nothing of this tile is needed
 	const int g = i * TG + threadIdx.x;
 	const u32 vm = group_valid_mask(G, l, g);
 	const u32 *base = bs + S->bsbase[c] + G.gbase[l] + g;
@@ -229,9 +264,11 @@ __global__ void __launch_bounds__(TG) enc_emit_kernel(const __grid_constant__ Ge
 		u32 member = vm & ~sig;
 		u32 ones = B & member, zeros = member & ~B;
 		u32 n1 = __popc(ones), nz = __popc(zeros), nr = __popc(sig);
+		const int j = S->chunk_of[c][l][p];
+		if (j >= jcut)
+			break; // block-uniform: this plane and the ones below it are cut
 		u64 packed = (u64)nz | ((u64)n1 << 21) | ((u64)nr << 42), tot;
 		u64 ex = block_exscan_u64(packed, ws, &tot);
-		const int j = S->chunk_of[c][l][p];
 		const int e = S->ebase[j] + i;
 		if (n1) {
 			u32 zb = ez[e] + (u32)(ex & 0x1fffffu);
@@ -602,7 +639,8 @@ int enc_count(const Geom &g, const Sched &hs, const EncBuffers &b, cudaStream_t 
 	return 0;
 }
 
-int enc_scan_and_setup(const Geom &g, const Sched &hs, const EncBuffers &b, cudaStream_t st, long long *launches)
+int enc_scan_and_setup(const Geom &g, const Sched &hs, const EncBuffers &b, u64 prefix_bits, u64 limit_bits, cudaStream_t st,
+                       long long *launches)
 {
 	(void)g;
 	(void)hs;
@@ -612,7 +650,7 @@ int enc_scan_and_setup(const Geom &g, const Sched &hs, const EncBuffers &b, cuda
 	enc_scan_fix_kernel<<<nb, 1024, 0, st>>>(b.ent_z, b.ent_1, b.ent_r, b.nent, bsum, b.info);
 	++*launches;
 	enc_chunk_setup_kernel<<<1, 1024, 0, st>>>(b.sched, b.ent_z, b.ent_1, b.ent_r, b.chunks, b.info, b.Z, b.specbuf,
-	                                           b.max_tokens);
+	                                           b.max_tokens, prefix_bits, limit_bits);
 	*launches += 2;
 	CUDA_OK(cudaGetLastError());
 	return 0;
@@ -622,7 +660,7 @@ int enc_emit(const Geom &g, const Sched &hs, const EncBuffers &b, cudaStream_t s
 {
 	(void)hs;
 	int blocks = g.channels * g.tbase[g.levels];
-	enc_emit_kernel<<<blocks, TG, 0, st>>>(g, b.sched, b.bs, b.ent_z, b.ent_1, b.ent_r, b.chunks, b.Z, b.signbuf,
+	enc_emit_kernel<<<blocks, TG, 0, st>>>(g, b.sched, b.bs, b.ent_z, b.ent_1, b.ent_r, b.chunks, b.info, b.Z, b.signbuf,
 	                                       b.refbuf);
 	++*launches;
 	CUDA_OK(cudaGetLastError());

@@ -618,7 +618,8 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 		b.chunks = c->chunks.as<EncChunks>();
 		b.info = c->info.as<EncInfo>();
 		b.sched = c->dsched.as<Sched>();
-		if (enc_count(g, S, b, st, &c->launches) || enc_scan_and_setup(g, S, b, st, &c->launches) ||
+		const u64 limit_bits = capacity > 0 ? 8ull * (u64)capacity : 0ull;
+		if (enc_count(g, S, b, st, &c->launches) || enc_scan_and_setup(g, S, b, prefix_bits, limit_bits, st, &c->launches) ||
 		    enc_emit(g, S, b, st, &c->launches) || enc_vli_orders(b, k0, st, &c->launches))
 			return -1;
 		EncInfo *h_info = (EncInfo *)(h_small + 4 + nroot + 2);
@@ -629,7 +630,9 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 			dwt_set_error("coder: input outside the supported range (code %d)", h_info->error);
 			return -1;
 		}
-		tot_ref = h_info->tot_ref;
+		// chunks that provably start behind the capacity were not coded (enc_chunk_setup_kernel): total_bits is then a
+		// lower bound of the untruncated length that still lies >= 64 bits behind the capacity
+		tot_ref = h_info->jcut < S.nchunks ? h_info->ref_cut : h_info->tot_ref;
 		total_bits = prefix_bits + h_info->tok_bits + tot_ref;
 
 		// ---- output stream: zero, prefix bytes, then scatter

@@ -30,7 +30,8 @@ struct dwt_stats {
 	long long root_bits;  /* "%d bits for root image"  encode.c:179-180 */
 	long long total_bits; /* "%d bits (%d KiB) encoded" encode.c:226-230 (first number)  */
 	long long kib;        /*                                    (second number)          */
-	long long full_bits;  /* size of the untruncated stream in bits (header included)    */
+	long long full_bits;  /* size of the untruncated stream in bits (header included); a lower bound (still behind
+	                         the capacity) when a capacity let the encoder skip the chunks that cannot reach the output */
 	int levels;
 	int planes[3];
 	/* device time of the last call, milliseconds (CUDA events on the context's stream) */
