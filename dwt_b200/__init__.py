@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "dwt_ctx_set_decoder_scan",
     "dwt_host_alloc", "dwt_host_free", "dwt_encode_into", "dwt_decode_into", "dwt_ctx_flush_l2",
     "dwt_ctx_event_record", "dwt_ctx_event_elapsed_ms", "dwt_ctx_wait_for",
-    "dwt_pool_create", "dwt_pool_destroy", "dwt_pool_workers", "dwt_pool_last_error", "dwt_pool_encode", "dwt_pool_decode", "dwt_pool_run",
+    "dwt_pool_create", "dwt_pool_create_multi", "dwt_pool_devices", "dwt_pool_destroy", "dwt_pool_workers", "dwt_pool_last_error", "dwt_pool_encode", "dwt_pool_decode", "dwt_pool_run",
     "cdf53", "icdf53", "dwt_forward", "dwt_inverse", "dwt_ycocg_from_rgb", "dwt_rgb_from_ycocg",
     "compute_lengths", "ilog2", "dwt_debug_front_end",
     "bytes_reader", "bytes_writer", "bytes_count", "close_bytes_reader", "close_bytes_writer", "put_byte",
@@ -102,6 +102,9 @@ def lib():
     L.dwt_ctx_set_decoder_scan.argtypes = [vp, C.c_int]
     L.dwt_pool_create.argtypes = [C.c_int, C.c_int]
     L.dwt_pool_create.restype = vp
+    L.dwt_pool_create_multi.argtypes = [ip, C.c_int, C.c_int]
+    L.dwt_pool_create_multi.restype = vp
+    L.dwt_pool_devices.argtypes = [vp, ip, C.c_int]
     L.dwt_pool_destroy.argtypes = [vp]
     L.dwt_pool_destroy.restype = None
     L.dwt_pool_workers.argtypes = [vp]
@@ -300,9 +303,21 @@ class Pool:
     """dwt_pool: `workers` contexts on one device coding the items of a batch concurrently (one host thread each)"""
 
     def __init__(self, device=0, workers=4):
-        self._h = lib().dwt_pool_create(int(device), int(workers))
+        """device: one device index, a list of them, or "all" (dwt_pool_create_multi: item i -> devices[i mod G])"""
+        if device == "all":
+            self._h = lib().dwt_pool_create_multi(None, 0, int(workers))
+        elif isinstance(device, (list, tuple)):
+            arr = (C.c_int * len(device))(*[int(d) for d in device])
+            self._h = lib().dwt_pool_create_multi(arr, len(device), int(workers))
+        else:
+            self._h = lib().dwt_pool_create(int(device), int(workers))
         if not self._h:
             raise DwtError("dwt_pool_create failed: " + last_error())
+
+    def devices(self):
+        arr = (C.c_int * 64)()
+        n = lib().dwt_pool_devices(self._h, arr, 64)
+        return list(arr)[:n]
 
     def close(self):
         if self._h:

@@ -6,6 +6,7 @@
 #include "dwt_b200.h"
 
 #include <atomic>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -334,9 +335,14 @@ extern "C" int dwt_encode_into(dwt_ctx *c, const uint8_t *pixels, int width, int
 		dwt_set_error("null context (no CUDA device?)");
 		return -1;
 	}
-	if (dwt_ctx_upload_image(c, pixels, width, height, channels) || dwt_ctx_encode_resident(c, capacity, stats))
+	if (dwt_ctx_upload_image(c, pixels, width, height, channels))
 		return -1;
+	if (dwt_ctx_encode_resident(c, capacity, stats)) {
+		cudaStreamSynchronize(c->st); // the upload may still be reading `pixels`
+		return -1;
+	}
 	if (c->out_bytes > out_room) {
+		cudaStreamSynchronize(c->st);
 		dwt_set_error("output buffer too small: need %zu bytes", c->out_bytes);
 		*out_len = c->out_bytes;
 		return -1;
@@ -355,16 +361,19 @@ extern "C" int dwt_decode_into(dwt_ctx *c, const uint8_t *stream, size_t len, in
 		dwt_set_error("null context (no CUDA device?)");
 		return -1;
 	}
-	if (dwt_ctx_upload_stream(c, stream, len))
+	if (ctx_upload_stream(c, stream, len, false)) // `stream` outlives the call: no separate wait for the upload
 		return -1;
 	int r = dwt_ctx_decode_resident(c, pixels_max, stats);
-	if (r)
+	if (r) {
+		cudaStreamSynchronize(c->st); // the upload may still be reading `stream`
 		return r;
+	}
 	const size_t n = (size_t)c->dec_w * c->dec_h * c->dec_ch;
 	*width = c->dec_w;
 	*height = c->dec_h;
 	*channels = c->dec_ch;
 	if (n > pixels_room) {
+		cudaStreamSynchronize(c->st);
 		dwt_set_error("pixel buffer too small: need %zu bytes", n);
 		return -1;
 	}
@@ -379,9 +388,10 @@ extern "C" int dwt_decode_into(dwt_ctx *c, const uint8_t *stream, size_t len, in
 // single-warp stages of one frame hide behind the wide kernels of its neighbours.  One pool per GPU; no collective.
 
 struct dwt_pool {
-	int device = 0;
-	std::vector<dwt_ctx *> ctx;
-	XferGate gate; // shared by the contexts: one large copy per direction at a time
+	std::vector<int> devices;              // the GPUs of the pool, in the caller's order
+	int workers = 1;                       // contexts (and host threads) per device
+	std::vector<dwt_ctx *> ctx;            // device d owns ctx[d * workers .. (d + 1) * workers)
+	std::vector<std::unique_ptr<XferGate>> gate; // one per device: large copies of a direction take turns on that GPU's link
 	std::mutex err_lock;
 	char err[512] = "";
 };
@@ -409,25 +419,46 @@ extern "C" int dwt_ctx_set_decoder_scan(dwt_ctx *c, int mode)
 	return 0;
 }
 
-extern "C" dwt_pool *dwt_pool_create(int device, int workers)
+extern "C" dwt_pool *dwt_pool_create_multi(const int *devices, int n_devices, int workers)
 {
 	if (workers < 1)
 		workers = 1;
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+		dwt_set_error("no CUDA device: libdwt_b200 has no CPU fallback");
+		return nullptr;
+	}
 	dwt_pool *p = new dwt_pool();
-	for (int i = 0; i < workers; ++i) {
-		dwt_ctx *c = dwt_ctx_create(device);
-		if (!c) {
-			for (dwt_ctx *d : p->ctx)
-				dwt_ctx_destroy(d);
-			delete p;
-			return nullptr;
+	p->workers = workers;
+	if (!devices || n_devices <= 0) { // every visible device
+		for (int d = 0; d < count; ++d)
+			p->devices.push_back(d);
+	} else {
+		for (int i = 0; i < n_devices; ++i)
+			p->devices.push_back(devices[i]);
+	}
+	for (size_t d = 0; d < p->devices.size(); ++d) {
+		p->gate.emplace_back(new XferGate());
+		for (int i = 0; i < workers; ++i) {
+			dwt_ctx *c = dwt_ctx_create(p->devices[d]);
+			if (!c) {
+				for (dwt_ctx *x : p->ctx)
+					dwt_ctx_destroy(x);
+				delete p;
+				return nullptr;
+			}
+			c->in_flight = workers;
+			c->gate = workers > 1 ? p->gate[d].get() : nullptr;
+			p->ctx.push_back(c);
+			p->devices[d] = c->device; // device < 0 resolved to the current device
 		}
-		c->in_flight = workers;
-		c->gate = workers > 1 ? &p->gate : nullptr;
-		p->ctx.push_back(c);
-		p->device = c->device;
 	}
 	return p;
+}
+
+extern "C" dwt_pool *dwt_pool_create(int device, int workers)
+{
+	return dwt_pool_create_multi(&device, 1, workers);
 }
 
 extern "C" void dwt_pool_destroy(dwt_pool *p)
@@ -444,6 +475,17 @@ extern "C" int dwt_pool_workers(const dwt_pool *p)
 	return p ? (int)p->ctx.size() : 0;
 }
 
+extern "C" int dwt_pool_devices(const dwt_pool *p, int *devices, int room)
+{
+	if (!p)
+		return 0;
+	for (int i = 0; i < room && i < (int)p->devices.size(); ++i)
+		devices[i] = p->devices[(size_t)i];
+	return (int)p->devices.size();
+}
+
+// Item i of a batch belongs to device i mod G (G = devices of the pool): images are independent, so the GPUs share nothing
+// (no collective).  The `workers` threads of a device hand its items out among themselves.
 template <typename F>
 static int pool_run(dwt_pool *p, int n, F &&one)
 {
@@ -451,25 +493,30 @@ static int pool_run(dwt_pool *p, int n, F &&one)
 		dwt_set_error("bad batch arguments");
 		return -1;
 	}
-	std::atomic<int> next(0), failed(0);
-	auto work = [&](int w) {
+	const int G = (int)p->devices.size();
+	std::vector<std::atomic<int>> next((size_t)G);
+	for (auto &a : next)
+		a.store(0);
+	std::atomic<int> failed(0);
+	auto work = [&](int d, int w) {
 		for (;;) {
-			const int i = next.fetch_add(1);
+			const int i = d + G * next[(size_t)d].fetch_add(1);
 			if (i >= n)
 				break;
-			if (one(p->ctx[(size_t)w], i)) {
+			if (one(p->ctx[(size_t)(d * p->workers + w)], i)) {
 				failed.fetch_add(1);
 				std::lock_guard<std::mutex> hold(p->err_lock); // dwt_last_error() is per thread: keep the reason with the pool
 				snprintf(p->err, sizeof(p->err), "item %d: %s", i, dwt_last_error());
 			}
 		}
 	};
-	const int nw = (int)p->ctx.size() < n ? (int)p->ctx.size() : n;
 	std::vector<std::thread> th;
-	for (int w = 1; w < nw; ++w)
-		th.emplace_back(work, w);
-	if (nw > 0)
-		work(0);
+	for (int d = 0; d < G; ++d) {
+		const int items = n > d ? (n - d + G - 1) / G : 0;
+		const int nw = p->workers < items ? p->workers : items;
+		for (int w = 0; w < nw; ++w)
+			th.emplace_back(work, d, w);
+	}
 	for (auto &t : th)
 		t.join();
 	return failed.load();

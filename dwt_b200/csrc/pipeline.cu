@@ -11,6 +11,7 @@
 #include "dwt_b200.h"
 
 #include <atomic>
+#include <chrono>
 
 #include <sched.h>
 #include <stdarg.h>
@@ -124,29 +125,33 @@ extern "C" dwt_ctx *dwt_ctx_create(int device)
 	}
 	for (auto &e : c->ev)
 		cudaEventCreate(&e);
-	cudaEventCreateWithFlags(&c->sync_ev, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&c->sync_ev, cudaEventDisableTiming | cudaEventBlockingSync);
+	for (auto &e : c->xfer_ev)
+		cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
 	c->plan.cell_base = nullptr;
 	return c;
 }
 
 cudaError_t ctx_stream_sync(dwt_ctx *c)
 {
-	// default: cudaStreamSynchronize (spins in the driver).  DWT_SYNC=poll: poll an event and give the core away between
-	// polls, for hosts with far fewer cores than waiting threads; with 8 cores per GPU (16 pool threads) the driver's spin
-	// measured 1-3 % faster end to end at N = 1 and N = 4
-	static const bool poll = getenv("DWT_SYNC") && !strcmp(getenv("DWT_SYNC"), "poll");
-	if (!poll || !c->sync_ev)
+	static const bool spin = getenv("DWT_SYNC") && !strcmp(getenv("DWT_SYNC"), "spin");
+	static const long spin_us = getenv("DWT_SPIN_US") ? atol(getenv("DWT_SPIN_US")) : 20;
+	if (spin || !c->sync_ev)
 		return cudaStreamSynchronize(c->st);
 	cudaError_t e = cudaEventRecord(c->sync_ev, c->st);
 	if (e != cudaSuccess)
 		return e;
-	for (int polls = 0;; ++polls) {
-		e = cudaEventQuery(c->sync_ev);
-		if (e != cudaErrorNotReady)
-			return e;
-		if (polls >= 64)
-			sched_yield();
+	if (spin_us > 0) {
+		const auto t0 = std::chrono::steady_clock::now();
+		for (;;) {
+			e = cudaEventQuery(c->sync_ev);
+			if (e != cudaErrorNotReady)
+				return e;
+			if (std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() >= spin_us)
+				break;
+		}
 	}
+	return cudaEventSynchronize(c->sync_ev); // the event was created with cudaEventBlockingSync: the thread sleeps
 }
 
 cudaError_t ctx_copy(dwt_ctx *c, void *dst, const void *src, size_t n, cudaMemcpyKind kind, bool wait)
@@ -157,15 +162,22 @@ cudaError_t ctx_copy(dwt_ctx *c, void *dst, const void *src, size_t n, cudaMemcp
 		cudaError_t e = cudaMemcpyAsync(dst, src, n, kind, c->st);
 		return e == cudaSuccess && wait ? ctx_stream_sync(c) : e;
 	}
-	const bool down = kind == cudaMemcpyDeviceToHost;
-	if (down) {
-		cudaError_t e = ctx_stream_sync(c);
-		if (e != cudaSuccess)
-			return e;
+	const int d = kind == cudaMemcpyDeviceToHost ? 1 : 0;
+	cudaError_t e = cudaSuccess;
+	if (d == 1 && (e = ctx_stream_sync(c)) != cudaSuccess) // the stream's kernels first: the chain only ever waits for copies
+		return e;
+	{
+		std::lock_guard<std::mutex> hold(c->gate->dir[d]);
+		if (c->gate->last[d] && c->gate->last[d] != c->xfer_ev[d])
+			e = cudaStreamWaitEvent(c->st, c->gate->last[d], 0);
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(dst, src, n, kind, c->st);
+		if (e == cudaSuccess)
+			e = cudaEventRecord(c->xfer_ev[d], c->st);
+		if (e == cudaSuccess)
+			c->gate->last[d] = c->xfer_ev[d];
 	}
-	std::lock_guard<std::mutex> hold(c->gate->dir[down ? 1 : 0]);
-	cudaError_t e = cudaMemcpyAsync(dst, src, n, kind, c->st);
-	return e == cudaSuccess ? ctx_stream_sync(c) : e;
+	return e == cudaSuccess && wait ? ctx_stream_sync(c) : e;
 }
 
 extern "C" void dwt_ctx_destroy(dwt_ctx *c)
@@ -186,6 +198,11 @@ extern "C" void dwt_ctx_destroy(dwt_ctx *c)
 	hilbert_plan_free(&c->plan);
 	for (auto &e : c->ev)
 		cudaEventDestroy(e);
+	for (auto &e : c->xfer_ev)
+		if (e)
+			cudaEventDestroy(e);
+	if (c->sync_ev)
+		cudaEventDestroy(c->sync_ev);
 	cudaStreamDestroy(c->st);
 	delete c;
 }
@@ -663,7 +680,9 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 		c->out_bytes = out_bytes;
 	}
 	CUDA_OK(cudaEventRecord(c->ev[3], st));
-	CUDA_OK(ctx_stream_sync(c));
+	// the stage timers need the stream drained; a caller without stats (the pool) waits once, behind its download
+	if (stt)
+		CUDA_OK(ctx_stream_sync(c));
 
 	if (stt) {
 		memset(stt, 0, sizeof(*stt));

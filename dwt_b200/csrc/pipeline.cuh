@@ -31,7 +31,8 @@ struct dwt_ctx {
 	long long launches = 0;
 	cudaEvent_t ev[9] = {};   // 0..3 stage timers, 4..7 caller slots, 8 cross-context waits
 	struct XferGate *gate = nullptr; // set by a pool: see ctx_copy
-	cudaEvent_t sync_ev = nullptr; // polled by ctx_stream_sync
+	cudaEvent_t sync_ev = nullptr; // ctx_stream_sync: polled briefly, then waited for with the thread asleep
+	cudaEvent_t xfer_ev[2] = {};   // completion of this context's latest gated copy, per direction
 
 	// geometry cache
 	bool have_geom = false;
@@ -80,12 +81,19 @@ int ensure_transform_buffers(dwt_ctx *c);
 // One large host<->device copy per direction at a time among the contexts of a pool: copies issued together share the link,
 // so every job of a batch would get its data only when all of them have it (an idle GPU for the first ~20 ms of a batch
 // of 8K frames); one after the other, the first job computes after one copy time.
+// The turn-taking is an event chain on the device's timeline, not a lock held by a waiting host thread: a gated copy
+// waits (cudaStreamWaitEvent) for the previous gated copy of its direction and leaves its own completion event behind.
+// The mutex only covers the few microseconds of queueing those three calls.
 struct XferGate {
-	std::mutex dir[2]; // [0] host -> device, [1] device -> host
+	std::mutex dir[2];                      // [0] host -> device, [1] device -> host
+	cudaEvent_t last[2] = {nullptr, nullptr}; // completion of the most recent gated copy (owned by the context that queued it)
 };
-// copy on the context's stream and, if `wait` or gated, wait for it.  Gated device -> host copies first wait for the
-// stream's kernels, so that the gate is only held for the copy itself.
+// copy on the context's stream and, if `wait`, wait for it.  Gated device -> host copies first wait for the stream's
+// kernels, so that the copies queued behind them in the chain are not held up by this context's compute.
 cudaError_t ctx_copy(dwt_ctx *c, void *dst, const void *src, size_t n, cudaMemcpyKind kind, bool wait);
-// wait for the context's stream (cudaStreamSynchronize; with DWT_SYNC=poll an event poll that yields the core between polls)
+// wait for the context's stream: a short poll of an event (the common wait is a few microseconds), then a blocking
+// cudaEventSynchronize that leaves the core to other threads (a pool has more waiting threads than a GPU box has cores
+// per GPU).  DWT_SYNC=spin restores cudaStreamSynchronize, DWT_SPIN_US sets the poll time (default 20).
 cudaError_t ctx_stream_sync(dwt_ctx *c);
+int ctx_upload_stream(dwt_ctx *c, const uint8_t *stream, size_t len, bool wait);
 const int *ctx_root_ll(dwt_ctx *c);      // device pointer to the planar root LL after ctx_forward_transform

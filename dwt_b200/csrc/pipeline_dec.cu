@@ -30,7 +30,8 @@ static float ev_ms(cudaEvent_t a, cudaEvent_t b)
 	return ms;
 }
 
-extern "C" int dwt_ctx_upload_stream(dwt_ctx *c, const uint8_t *stream, size_t len)
+// wait = false: the caller keeps `stream` alive and unchanged until it has waited for the context itself
+int ctx_upload_stream(dwt_ctx *c, const uint8_t *stream, size_t len, bool wait)
 {
 	if (!c) {
 		dwt_set_error("null context");
@@ -46,12 +47,17 @@ extern "C" int dwt_ctx_upload_stream(dwt_ctx *c, const uint8_t *stream, size_t l
 	CUDA_OK(cudaMemsetAsync((char *)c->stream.p + (len / 4) * 4, 0, room - (len / 4) * 4, c->st));
 	if (len) {
 		memcpy(c->pin_stream.p, stream, head);
-		CUDA_OK(ctx_copy(c, c->stream.p, stream, len, cudaMemcpyHostToDevice, true)); // the caller's buffer is free again
+		CUDA_OK(ctx_copy(c, c->stream.p, stream, len, cudaMemcpyHostToDevice, wait));
 	}
 	c->stream_head = head;
 	c->stream_len = len;
 	c->stream_resident = true;
 	return 0;
+}
+
+extern "C" int dwt_ctx_upload_stream(dwt_ctx *c, const uint8_t *stream, size_t len)
+{
+	return ctx_upload_stream(c, stream, len, true); // the caller's buffer is free again when this returns
 }
 
 // chunk list of decode.c:199-243: the encoder's order, cut where a level loop reaches l >= levels_max
@@ -325,7 +331,8 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 	if (ctx_inverse_transform(c, levels_used, true, nullptr, true))
 		return -1;
 	CUDA_OK(cudaEventRecord(c->ev[3], st));
-	CUDA_OK(ctx_stream_sync(c));
+	if (stt) // stage timers; a caller without stats waits once, behind its download
+		CUDA_OK(ctx_stream_sync(c));
 	c->dec_w = ow;
 	c->dec_h = oh;
 	c->dec_ch = C;
@@ -380,10 +387,12 @@ extern "C" int dwt_decode(dwt_ctx *c, const uint8_t *stream, size_t len, int pix
 		dwt_set_error("null context (no CUDA device?)");
 		return -1;
 	}
-	if (dwt_ctx_upload_stream(c, stream, len))
+	if (ctx_upload_stream(c, stream, len, false)) // `stream` outlives the call: no separate wait for the upload
 		return -1;
 	int r = dwt_ctx_decode_resident(c, pixels_max, stats);
-	if (r)
+	if (r) {
+		cudaStreamSynchronize(c->st); // the upload may still be reading `stream`
 		return r;
+	}
 	return dwt_ctx_download_image(c, pixels, width, height, channels);
 }

@@ -4,8 +4,11 @@
  * it -- same streams, same pixels, same acceptance rules -- but the images share a pool of GPU contexts, so file
  * I/O, host<->device copies and kernels of different images overlap.
  *
- *   dwtbatch encode [-c CAPACITY] [-j WORKERS] OUTDIR [FILE.pnm ...]     -> OUTDIR/<name>.dwt
- *   dwtbatch decode [-p PIXELS]   [-j WORKERS] OUTDIR [FILE.dwt ...]     -> OUTDIR/<name>.pnm
+ *   dwtbatch encode [-c CAPACITY] [-j WORKERS] [-g GPUS] OUTDIR [FILE.pnm ...]     -> OUTDIR/<name>.dwt
+ *   dwtbatch decode [-p PIXELS]   [-j WORKERS] [-g GPUS] OUTDIR [FILE.dwt ...]     -> OUTDIR/<name>.pnm
+ *
+ * -g all | N | a,b,c : the GPUs of this box to shard the files over (file i -> GPU i mod G, WORKERS contexts on each;
+ * images are independent, so there is no exchange between the GPUs).  Default: one GPU (DWT_DEVICE or the current one).
  *
  * Without FILE arguments the paths are read from stdin, one per line.  Exit status: 0 when every file was coded,
  * 1 otherwise (each failure is reported on stderr and the other files are still coded; no output file is created
@@ -94,14 +97,15 @@ static char **stdin_paths(int *n)
 
 int main(int argc, char **argv)
 {
-	const char *usage = "usage: %s encode [-c CAPACITY] [-j WORKERS] OUTDIR [FILE.pnm ...]\n"
-	                    "       %s decode [-p PIXELS] [-j WORKERS] OUTDIR [FILE.dwt ...]\n";
+	const char *usage = "usage: %s encode [-c CAPACITY] [-j WORKERS] [-g all|N|a,b,..] OUTDIR [FILE.pnm ...]\n"
+	                    "       %s decode [-p PIXELS] [-j WORKERS] [-g all|N|a,b,..] OUTDIR [FILE.dwt ...]\n";
 	if (argc < 3 || (strcmp(argv[1], "encode") && strcmp(argv[1], "decode"))) {
 		fprintf(stderr, usage, argv[0], argv[0]);
 		return 1;
 	}
 	const int enc = !strcmp(argv[1], "encode");
 	int capacity = 0, pixels_max = -1, workers = 8, a = 2;
+	const char *gpus = 0;
 	for (; a + 1 < argc && argv[a][0] == '-' && argv[a][1] && !argv[a][2]; a += 2) {
 		if (argv[a][1] == 'c' && enc)
 			capacity = atoi(argv[a + 1]); /* <= 0: unlimited, encode.c:150-152 */
@@ -109,6 +113,8 @@ int main(int argc, char **argv)
 			pixels_max = atoi(argv[a + 1]) < 0 ? 0 : atoi(argv[a + 1]); /* decode.c:165-171 */
 		else if (argv[a][1] == 'j')
 			workers = atoi(argv[a + 1]);
+		else if (argv[a][1] == 'g')
+			gpus = argv[a + 1];
 		else
 			break;
 	}
@@ -125,7 +131,26 @@ int main(int argc, char **argv)
 			return 1;
 	}
 	const char *dev = getenv("DWT_DEVICE");
-	dwt_pool *pool = dwt_pool_create(dev ? atoi(dev) : -1, workers);
+	dwt_pool *pool;
+	if (!gpus) {
+		pool = dwt_pool_create(dev ? atoi(dev) : -1, workers);
+	} else if (!strcmp(gpus, "all")) {
+		pool = dwt_pool_create_multi(0, 0, workers);
+	} else {
+		int list[64], n = 0;
+		if (!strchr(gpus, ',')) { /* a count: devices 0 .. N-1 */
+			for (int d = 0; d < atoi(gpus) && n < 64; ++d)
+				list[n++] = d;
+		} else {
+			for (const char *q = gpus; *q && n < 64; q = strchr(q, ',') ? strchr(q, ',') + 1 : q + strlen(q))
+				list[n++] = atoi(q);
+		}
+		if (n < 1) {
+			fprintf(stderr, usage, argv[0], argv[0]);
+			return 1;
+		}
+		pool = dwt_pool_create_multi(list, n, workers);
+	}
 	if (!pool) {
 		fprintf(stderr, "%s: %s\n", argv[0], dwt_last_error());
 		return 1;

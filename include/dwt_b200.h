@@ -103,9 +103,11 @@ int dwt_decode_into(dwt_ctx *ctx, const uint8_t *stream, size_t len, int pixels_
  * contexts on one device and codes the items on as many host threads, so host<->device copies and kernels of different
  * items overlap.  Buffers should come from dwt_host_alloc().  status per item: the value dwt_encode_into /
  * dwt_decode_into would have returned.  Return value: number of items whose status is non-zero, -1 on bad arguments.
- * The contexts of a pool take turns for host<->device copies of 16 MB and more (one per direction at a time), so the
- * first items of a batch start computing after one copy time.  Environment (debugging aids): DWT_XFER_GATE=0 switches
- * the turn-taking off, DWT_SYNC=poll makes waiting host threads poll and yield instead of spinning in the driver. */
+ * The contexts of a device take turns for host<->device copies of 16 MB and more (one per direction at a time, chained
+ * with events on the device, never a lock held across a wait), so the first items of a batch start computing after one
+ * copy time.  Waiting host threads poll for ~20 us and then sleep (cudaEventBlockingSync).  Environment (debugging
+ * aids): DWT_XFER_GATE=0 switches the turn-taking off, DWT_SYNC=spin makes waiting threads spin in the driver,
+ * DWT_SPIN_US=<n> sets the poll time. */
 struct dwt_encode_item {
 	const uint8_t *pixels;
 	int width, height, channels, capacity;
@@ -124,6 +126,12 @@ struct dwt_decode_item {
 };
 typedef struct dwt_pool dwt_pool;
 dwt_pool *dwt_pool_create(int device, int workers);
+/* The same over several GPUs of one box (images are independent, no exchange step, no collective):
+ * `workers` contexts and host threads on each of the n_devices devices; item i of a batch is coded on
+ * devices[i mod n_devices].  devices == NULL or n_devices <= 0: every visible device.  dwt_pool_workers() then
+ * returns the total number of contexts, dwt_pool_devices() the device list (returns its length). */
+dwt_pool *dwt_pool_create_multi(const int *devices, int n_devices, int workers);
+int dwt_pool_devices(const dwt_pool *pool, int *devices, int room);
 void dwt_pool_destroy(dwt_pool *pool);
 int dwt_pool_workers(const dwt_pool *pool);
 /* why the most recent failed item of the pool failed (dwt_last_error() is per thread and the items run on the

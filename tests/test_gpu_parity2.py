@@ -174,3 +174,37 @@ def test_8k_with_frames_in_flight(oracle, pins_big):
     finally:
         for cd in cods:
             cd.close()
+
+
+def test_multi_device_pool_and_batch_cli(oracle, tmp_path):
+    """dwt_pool_create_multi / dwtbatch -g: item i is coded on devices[i mod G] (no exchange between GPUs).  On a
+    one-GPU box the device list names GPU 0 twice, which runs the same sharding code; with more GPUs "all" spans them."""
+    import dwt_b200 as D
+    imgs = [oracle.synth(160 + 31 * i, 96 + 17 * i, "photo" if i % 2 else "noise", 80 + i) for i in range(11)]
+    want = [oracle.encode(im)[0] for im in imgs]
+    for dev in ([0, 0], "all"):
+        pool = D.Pool(dev, 2)
+        try:
+            assert len(pool.devices()) >= 1
+            assert pool.encode_batch(imgs) == want
+            assert pool.encode_batch(imgs, 999) == [w[:999] for w in want]
+            dec = pool.decode_batch(want, [im.shape for im in imgs])
+            for a, b in zip(dec, imgs):
+                assert np.array_equal(a, b)
+        finally:
+            pool.close()
+    tool = os.path.join(ROOT, "dwtbatch")
+    src, enc_dir, dec_dir = tmp_path / "src", tmp_path / "enc", tmp_path / "dec"
+    for d in (src, enc_dir, dec_dir):
+        d.mkdir()
+    for i, im in enumerate(imgs):
+        (src / ("im%02d.pnm" % i)).write_bytes(oracle.pnm_bytes(im))
+    names = sorted(str(p) for p in src.iterdir())
+    r = subprocess.run([tool, "encode", "-j", "2", "-g", "all", str(enc_dir)] + names, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    for i, w in enumerate(want):
+        assert (enc_dir / ("im%02d.dwt" % i)).read_bytes() == w
+    r = subprocess.run([tool, "decode", "-g", "0,0", str(dec_dir)] + sorted(str(p) for p in enc_dir.iterdir()), capture_output=True)
+    assert r.returncode == 0, r.stderr
+    for i, im in enumerate(imgs):
+        assert (dec_dir / ("im%02d.pnm" % i)).read_bytes() == oracle.pnm_bytes(im)
