@@ -58,7 +58,8 @@ int enc_scatter(const Sched &hs, const EncBuffers &b, u64 prefix_bits, u64 tot_r
 
 // ---------------------------------------------------------------------------------------------- decoder
 
-#define DWT_DEC_WS 512            // stream slices (64 bits each) per scan window
+#define DWT_DEC_WS 128            // stream slices (64 bits each) per scan window (1 KB of stream)
+#define DWT_DEC_SUPER 32          // windows per super-window (the resolver's second level)
 
 struct DecState {                 // device-resident cursor of the serial parse (decode.c:187-243); read back by the host
 	u64 bitpos;                   // next stream bit
@@ -69,9 +70,9 @@ struct DecState {                 // device-resident cursor of the serial parse 
 	int level;                    // highest level started
 	int missing[48];
 	u32 nseg;                     // (chunk, window) segments handed to the emit kernel
-	u32 dbg_slow, dbg_stray;      // resolver statistics: slow-path entries, stray slices walked
-	u64 dbg_cyc[4];               // resolver cycles: exact steps, linked windows, end search, total
-	unsigned short dbg_cs[DWT_MAX_CHUNKS]; // stray slices per chunk
+	u32 nbulk;                    // super-windows consumed whole: their 32 segments each are written by dec_bulk_kernel
+	u32 exact_steps, slow_entries; // resolver statistics: slices stepped token by token, entries into that mode
+	int guard_tripped;            // the resolver's iteration guard fired (a bug, never a property of a stream)
 };
 
 struct DecChunk {                 // per chunk, written by the resolver, read by emit + deposit
@@ -105,6 +106,22 @@ struct DecSeg {                   // one (chunk, window) visit of the true chain
 	u32 cum_m;                    // ... before slice m
 };
 
+struct DecSuper {                 // DWT_DEC_SUPER windows entered with the exit state of class q of the window in front
+	u64 mem;                      // members consumed by all of them
+	u32 tok;                      // tokens started in them
+	unsigned short exit_state;    // state behind the last window when the chain left it without joining (qn == 2)
+	unsigned char qn;             // class behind the last window
+	unsigned char clean;          // every window exists and is entered with a canonical class: the sums are the whole story
+};
+
+struct DecBulk {                  // one super-window consumed whole by chunk j
+	u32 w0;                       // first window
+	u32 seg_base;                 // its 32 segment records go to seg[seg_base ..]
+	u32 cum0;                     // members of the chunk consumed before window w0 (after r0)
+	unsigned short j;
+	unsigned short cls;           // class the chain enters window w0 with
+};
+
 struct DecBuffers {
 	u32 *bs;              // bit-sliced store being filled
 	u32 *sig;             // significance words [c][GT]
@@ -121,6 +138,9 @@ struct DecBuffers {
 	ulonglong2 *winPT;    // per window: member totals
 	u32 *winTT;           // per window: token totals
 	DecLink *link;        // [window][class]
+	DecSuper *super;      // [super-window][class]
+	u32 nsuper;
+	DecBulk *bulk;
 	DecSeg *seg;
 	DecChunk *chunks;
 	u32 *tile_sums, *tile_base; // per (channel, tile): (member, refinement) counts and their exclusive prefixes

@@ -629,9 +629,99 @@ __device__ __forceinline__ void load_link(const DecLink *src, DecLink &L) // two
 	L.qm = (unsigned char)((r1.z >> 8) & 0xffu);
 }
 
+__device__ __forceinline__ void dead_link(DecLink &L) // what a window behind the stream looks like
+{
+	L.mem = 0;
+	L.tok = 0;
+	L.stray_mem = 0;
+	L.stray_tok = 0;
+	L.exit_state = (unsigned short)PDEAD;
+	L.m = WS;
+	L.qn = 3;
+	L.qm = 0;
+}
+
+__device__ __forceinline__ u64 shfl_u64(u64 v, int src)
+{
+	const u32 lo = __shfl_sync(0xffffffffu, (u32)v, src), hi = __shfl_sync(0xffffffffu, (u32)(v >> 32), src);
+	return (u64)lo | ((u64)hi << 32);
+}
+
+__device__ __forceinline__ u32 scan_class_maps(u32 inc, int lane) // inclusive scan of 2-state class maps over the warp
+{
+#pragma unroll
+	for (int dd = 1; dd < 32; dd <<= 1) {
+		const u32 t = __shfl_up_sync(0xffffffffu, inc, dd);
+		if (lane >= dd)
+			inc = map_compose(t, inc);
+	}
+	return inc;
+}
+
+// ---------------------------------------------------------------------------------------------- super records
+
+// One warp per super-window of DWT_DEC_SUPER windows: what the 32 windows consume when the chain enters the first of
+// them with class 0 / class 1 -- the link records composed, so that the resolver crosses 32 windows with one record.
+__global__ void __launch_bounds__(128) dec_super_kernel(u32 nwin, u32 nsuper, const DecLink *__restrict__ link, DecSuper *super)
+{
+	static_assert(DWT_DEC_SUPER == 32, "one lane per window of a super-window");
+	const u32 FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const u32 s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (s >= nsuper)
+		return;
+	const u32 w = s * DWT_DEC_SUPER + lane;
+	const bool valid = w < nwin;
+	DecLink L0, L1;
+	if (valid) {
+		load_link(link + 2 * (u64)w, L0);
+		load_link(link + 2 * (u64)w + 1, L1);
+	} else {
+		dead_link(L0);
+		dead_link(L1);
+	}
+	const u32 inc = scan_class_maps((u32)L0.qn | ((u32)L1.qn << 2), lane);
+	const u32 excl = __shfl_up_sync(FULL, inc, 1);
+	const u32 last = __shfl_sync(FULL, inc, 31);
+#pragma unroll
+	for (int q = 0; q < 2; ++q) {
+		const u32 cls = lane == 0 ? (u32)q : (excl >> (2 * q)) & 3u; // class the chain enters my window with
+		const bool canon = cls < 2u && valid;
+		const DecLink &my = cls == 1u ? L1 : L0;
+		u64 mem = canon ? my.mem : 0ull;
+		const u32 tok = __reduce_add_sync(FULL, canon ? my.tok : 0u);
+#pragma unroll
+		for (int dd = 16; dd >= 1; dd >>= 1)
+			mem += shfl_u64(mem, lane ^ dd);
+		const bool clean = __all_sync(FULL, canon);
+		const u32 ex = __shfl_sync(FULL, (u32)my.exit_state, 31);
+		if (lane == 0) {
+			uint4 r;
+			r.x = (u32)mem;
+			r.y = (u32)(mem >> 32);
+			r.z = tok;
+			r.w = ex | (((last >> (2 * q)) & 3u) << 16) | ((clean ? 1u : 0u) << 24);
+			((uint4 *)super)[2 * (u64)s + q] = r;
+		}
+	}
+}
+
+__device__ __forceinline__ void load_super(const DecSuper *src, DecSuper &S)
+{
+	const uint4 r = __ldg((const uint4 *)src);
+	S.mem = (u64)r.x | ((u64)r.y << 32);
+	S.tok = r.z;
+	S.exit_state = (unsigned short)(r.w & 0xffffu);
+	S.qn = (unsigned char)((r.w >> 16) & 3u);
+	S.clean = (unsigned char)((r.w >> 24) & 1u);
+}
+
+// ---------------------------------------------------------------------------------------------- resolve
+
 __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__ Geom G, int nchunks,
                                                           const __grid_constant__ DecBuffers B)
 {
+	static_assert(WS == 128, "the end search loads four slices per lane");
 	__shared__ u32 sigcount[48];
 	__shared__ int missing[48];
 	__shared__ u32 lut[1 << LUT_BITS];
@@ -642,7 +732,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 	const Sched *S = B.sched;
 	const u32 *__restrict__ stream = B.stream;
 	const u64 end_bits = B.end_bits;
-	const u32 nwin = B.nwin;
+	const u32 nwin = B.nwin, nsuper = B.nsuper;
 	for (int i = lane; i < 48; i += 32) {
 		sigcount[i] = 0;
 		missing[i] = st->missing[i];
@@ -660,9 +750,11 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 	int level = -1;
 	bool stopped = false;
 	u64 rank_base = 0;
-	u32 nseg = 0, dbg_slow = 0, dbg_stray = 0;
-	long long cyc[4] = {0, 0, 0, 0};
-	const long long t_begin = clock64();
+	u32 nseg = 0, nbulk = 0, slow_entries = 0, exact_steps = 0;
+	int tripped = 0;
+	// every pass of the loops below moves on by at least one window or ends the chunk; the guard only exists so that a
+	// bug can never hang the device
+	const u32 guard_max = 8u * nwin + 4096u;
 
 	for (int j = 0; j < nchunks && !stopped; ++j) {
 		const int c = s_chan[j], l = s_level[j];
@@ -710,17 +802,27 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 			u64 cum = 0;
 			u64 gs = bitpos >> 6;
 			int d = (int)(bitpos & 63), k = order;
-			int mode = 0;        // 0 stray (exact steps), 1 linked (whole windows)
+			int mode = 0;        // 0 stray (exact steps), 1 linked (whole windows / super-windows)
 			u32 w = 0, q = 0;    // linked mode: next window, class of the chain behind window w-1
 			u32 carry_state = PDEAD;
+			bool force_window = false; // linked mode: the super-window at w has to be looked at window by window
 			// end search on class sq of window sw from slice sm (cum = members before slice sm)
 			bool search = false;
 			u32 sw = 0, sq = 0;
 			int sm = 0;
-			++dbg_slow;
-			const u32 stray_before = dbg_stray;
+			// link records fetched together with a window's slices, for the window round that usually follows
+			u32 pf_w = 0xffffffffu, pfX = 0;
+			DecLink pfL0, pfL1;
+			dead_link(pfL0);
+			dead_link(pfL1);
+			u32 guard = 0;
+			++slow_entries;
 			while (event == EV_NONE) {
-				const long long t0 = clock64();
+				if (++guard > guard_max) {
+					tripped = 1;
+					event = EV_STOP;
+					break;
+				}
 				if (mode == 0) {
 					// ---- exact steps from slice gs until the chain joins a canonical chain, the window ends or the pass ends
 					const u32 cw = (u32)(gs / WS);
@@ -729,33 +831,52 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 						event = EV_STOP; // behind the scanned stream: nothing left to read
 						break;
 					}
+					// everything the visit can need is requested at once: the window's totals, the link records of the windows
+					// behind it, and (in the batch loop) slices with their tables -- one round trip instead of three
+					const ulonglong2 ptw = B.winPT[cw];
+					const u32 ttw = B.winTT[cw], xw = B.winX[cw];
+					{
+						const u32 wl = cw + 1 + (u32)lane;
+						if (wl < nwin) {
+							load_link(B.link + 2 * (u64)wl, pfL0);
+							load_link(B.link + 2 * (u64)wl + 1, pfL1);
+							pfX = B.winX[wl - 1];
+						} else {
+							dead_link(pfL0);
+							dead_link(pfL1);
+							pfX = 0xffffffffu;
+						}
+						pf_w = cw + 1;
+					}
 					const u32 seg_state = (u32)d | ((u32)k << 6);
 					const u64 seg_cum0 = cum;
 					int i = i0, m = WS, qm = 0;
+					u64 pm = 0;   // members of class qm before the join slice
+					u32 tkm = 0;  // tokens of both classes before the join slice
 					while (i < WS && event == EV_NONE && m == WS) {
 						const int nb = min(32, WS - i);
 						const u64 mgs = (u64)cw * WS + i + lane;
 						u64 ma = 0, mb = 0;
-						u32 me = 0;
+						u32 me = 0, mtk = 0;
+						ulonglong2 mp = make_ulonglong2(0ull, 0ull);
 						if (lane < nb) {
 							load_slice(stream, end_bits, mgs, ma, mb);
 							me = B.E[mgs];
+							mp = B.P[mgs];
+							mtk = B.TK[mgs];
 						}
 						for (int t = 0; t < nb; ++t) {
-							const u64 a = __shfl_sync(FULL, ma, t), b = __shfl_sync(FULL, mb, t);
+							const u64 a = shfl_u64(ma, t), b = shfl_u64(mb, t);
 							const u32 e = __shfl_sync(FULL, me, t);
 							const u32 state = (u32)d | ((u32)k << 6);
-							if (state == (e & 0xffffu)) {
+							if (state == (e & 0xffffu) || state == (e >> 16)) {
 								m = i + t;
-								qm = 0;
+								qm = state == (e & 0xffffu) ? 0 : 1;
+								pm = shfl_u64(qm ? mp.y : mp.x, t);
+								tkm = __shfl_sync(FULL, mtk, t);
 								break;
 							}
-							if (state == (e >> 16)) {
-								m = i + t;
-								qm = 1;
-								break;
-							}
-							++dbg_stray;
+							++exact_steps;
 							const u64 sgs = (u64)cw * WS + i + t;
 							event = walk_events(lut, a, b, clamp_avail(end_bits, sgs << 6), T, d, k, cum, ones, f_pending);
 							if (event != EV_NONE) {
@@ -780,7 +901,6 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 						B.seg[nseg] = sg;
 					}
 					++nseg;
-					cyc[0] += clock64() - t0;
 					if (event != EV_NONE)
 						break;
 					if (m == WS) { // the window ended before the chain joined: go on exactly in the next one
@@ -788,19 +908,16 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 						continue;
 					}
 					// joined class qm at slice m: is the rest of the window enough to end the pass?
-					const u64 mgs = (u64)cw * WS + m;
-					const ulonglong2 pm = B.P[mgs], pt = B.winPT[cw];
-					const u64 rest = qm ? pt.y - pm.y : pt.x - pm.x;
+					const u64 rest = (qm ? ptw.y : ptw.x) - pm;
 					if (cum + rest >= T) {
 						search = true;
 						sw = cw;
 						sq = (u32)qm;
 						sm = m;
 					} else {
-						const u32 tkm = B.TK[mgs], tt = B.winTT[cw];
 						cum += rest;
-						ones += qm ? (tt >> 16) - (tkm >> 16) : (tt & 0xffffu) - (tkm & 0xffffu);
-						const u32 x = (B.winX[cw] >> (16 * qm)) & 0xffffu;
+						ones += qm ? (ttw >> 16) - (tkm >> 16) : (ttw & 0xffffu) - (tkm & 0xffffu);
+						const u32 x = (xw >> (16 * qm)) & 0xffffu;
 						if (x == PDEAD) {
 							event = EV_STOP; // the chain dies inside this window
 							break;
@@ -808,38 +925,93 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 						mode = 1;
 						w = cw + 1;
 						q = (u32)qm;
+						force_window = false;
 					}
-				} else {
-					// ---- whole windows, 32 at a time: lane i looks at window w + i
-					const u32 wl = w + lane;
-					const bool valid = wl < nwin;
-					DecLink L0, L1;
-					if (valid) {
-						load_link(B.link + 2 * (u64)wl, L0);
-						load_link(B.link + 2 * (u64)wl + 1, L1);
+				} else if ((w & (DWT_DEC_SUPER - 1)) == 0 && !force_window) {
+					// ---- whole super-windows, 32 at a time: lane i looks at super-window w / 32 + i
+					const u32 sl = w / DWT_DEC_SUPER + (u32)lane;
+					DecSuper R0, R1;
+					if (sl < nsuper) {
+						load_super(B.super + 2 * (u64)sl, R0);
+						load_super(B.super + 2 * (u64)sl + 1, R1);
 					} else {
-						L0.qn = L1.qn = 3;
-						L0.mem = L1.mem = 0;
-						L0.tok = L1.tok = 0;
-						L0.exit_state = L1.exit_state = (unsigned short)PDEAD;
-						L0.m = L1.m = WS;
-						L0.qm = L1.qm = 0;
-						L0.stray_mem = L1.stray_mem = 0;
-						L0.stray_tok = L1.stray_tok = 0;
+						R0.mem = R1.mem = 0;
+						R0.tok = R1.tok = 0;
+						R0.exit_state = R1.exit_state = (unsigned short)PDEAD;
+						R0.qn = R1.qn = 3;
+						R0.clean = R1.clean = 0;
 					}
-					const u32 xprev = valid ? B.winX[wl - 1] : 0xffffffffu; // w >= 1 in linked mode
-					u32 inc = (u32)L0.qn | ((u32)L1.qn << 2);
+					const u32 inc = scan_class_maps((u32)R0.qn | ((u32)R1.qn << 2), lane);
+					const u32 excl = __shfl_up_sync(FULL, inc, 1);
+					const u32 cls = q >= 2u ? q : (lane == 0 ? q : (excl >> (2 * q)) & 3u);
+					const DecSuper &my = cls == 1u ? R1 : R0;
+					const bool ok = cls < 2u && my.clean != 0;
+					const u64 mymem = ok ? my.mem : 0ull;
+					const u32 mytok = ok ? my.tok : 0u;
+					u64 incm = mymem;
+					u32 inct = mytok;
 #pragma unroll
 					for (int dd = 1; dd < 32; dd <<= 1) {
-						const u32 t = __shfl_up_sync(FULL, inc, dd);
-						if (lane >= dd)
-							inc = map_compose(t, inc);
+						const u64 tm = shfl_u64(incm, max(lane - dd, 0));
+						const u32 tt = __shfl_up_sync(FULL, inct, dd);
+						if (lane >= dd) {
+							incm += tm;
+							inct += tt;
+						}
 					}
+					const bool reached = ok && cum + incm >= T;
+					const u32 bal = __ballot_sync(FULL, reached || !ok);
+					const int f = bal ? __ffs((int)bal) - 1 : 32;
+					if (lane < f) { // consumed whole: dec_bulk_kernel writes its 32 segment records
+						DecBulk bk;
+						bk.w0 = sl * DWT_DEC_SUPER;
+						bk.seg_base = nseg + 32u * (u32)lane;
+						bk.cum0 = (u32)(cum + (incm - mymem));
+						bk.j = (unsigned short)j;
+						bk.cls = (unsigned short)cls;
+						B.bulk[nbulk + lane] = bk;
+					}
+					nseg += 32u * (u32)f;
+					nbulk += (u32)f;
+					if (f > 0) {
+						cum += shfl_u64(incm, f - 1);
+						ones += __shfl_sync(FULL, inct, f - 1);
+						carry_state = __shfl_sync(FULL, (u32)my.exit_state, f - 1);
+						q = (__shfl_sync(FULL, inc, f - 1) >> (2 * q)) & 3u;
+						w += DWT_DEC_SUPER * (u32)f;
+					}
+					if (f < 32)
+						force_window = true; // something happens inside super-window w / 32: look at its windows
+				} else {
+					// ---- whole windows, lane i looks at window w + i, up to the end of the super-window
+					const int nlim = DWT_DEC_SUPER - (int)(w & (DWT_DEC_SUPER - 1));
+					force_window = false;
+					const u32 wl = w + (u32)lane;
+					const bool valid = wl < nwin && lane < nlim;
+					DecLink L0, L1;
+					u32 xprev;
+					if (pf_w == w) {
+						L0 = pfL0;
+						L1 = pfL1;
+						xprev = pfX;
+					} else if (wl < nwin) {
+						load_link(B.link + 2 * (u64)wl, L0);
+						load_link(B.link + 2 * (u64)wl + 1, L1);
+						xprev = B.winX[wl - 1]; // w >= 1 in linked mode
+					} else {
+						dead_link(L0);
+						dead_link(L1);
+						xprev = 0xffffffffu;
+					}
+					if (!valid) {
+						dead_link(L0);
+						dead_link(L1);
+					}
+					const u32 inc = scan_class_maps((u32)L0.qn | ((u32)L1.qn << 2), lane);
 					const u32 excl = __shfl_up_sync(FULL, inc, 1);
 					// class the chain enters my window with
 					const u32 cls = q >= 2u ? q : (lane == 0 ? q : (excl >> (2 * q)) & 3u);
 					const DecLink &my = cls == 1u ? L1 : L0;
-					const bool open = my.qn == 2u && my.exit_state == LINK_OPEN; // not joined within LINK_CAP: step it exactly
 					const bool canon = cls < 2u && valid;
 					const u64 mymem = canon ? my.mem : 0ull;
 					const u32 mytok = canon ? my.tok : 0u;
@@ -847,7 +1019,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 					u32 inct = mytok;
 #pragma unroll
 					for (int dd = 1; dd < 32; dd <<= 1) {
-						const u64 tm = __shfl_up_sync(FULL, incm, dd);
+						const u64 tm = shfl_u64(incm, max(lane - dd, 0));
 						const u32 tt = __shfl_up_sync(FULL, inct, dd);
 						if (lane >= dd) {
 							incm += tm;
@@ -855,7 +1027,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 						}
 					}
 					const u64 pre = incm - mymem;
-					const bool reached = canon && (open || cum + incm >= T);
+					const bool reached = canon && cum + incm >= T;
 					const u32 bal = __ballot_sync(FULL, reached || !canon);
 					const int f = bal ? __ffs((int)bal) - 1 : 32;
 					const u32 my_entry = (xprev >> (16 * (cls & 1u))) & 0xffffu;
@@ -872,27 +1044,26 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 						B.seg[nseg + lane] = sg;
 					}
 					nseg += (u32)f;
-					cyc[1] += clock64() - t0;
-					if (f == 32) {
-						cum += __shfl_sync(FULL, incm, 31);
-						ones += __shfl_sync(FULL, inct, 31);
-						carry_state = __shfl_sync(FULL, (u32)L0.exit_state | ((u32)L1.exit_state << 16), 31);
-						const u32 last = __shfl_sync(FULL, inc, 31);
-						const u32 qn = (last >> (2 * q)) & 3u;
-						carry_state = (carry_state >> (16 * ((__shfl_sync(FULL, cls, 31)) & 1u))) & 0xffffu;
-						q = qn;
-						w += 32;
+					const u32 exits = (u32)L0.exit_state | ((u32)L1.exit_state << 16);
+					if (f >= nlim) { // every window up to the super-window boundary was consumed (f == nlim)
+						const int src = nlim - 1;
+						cum += shfl_u64(incm, src);
+						ones += __shfl_sync(FULL, inct, src);
+						const u32 ex = __shfl_sync(FULL, exits, src);
+						carry_state = (ex >> (16 * (__shfl_sync(FULL, cls, src) & 1u))) & 0xffffu;
+						q = (__shfl_sync(FULL, inc, src) >> (2 * q)) & 3u;
+						w += (u32)nlim;
 						continue;
 					}
 					// lane f holds the window where something happens
 					const u32 wf = w + (u32)f;
 					const u32 cls_f = __shfl_sync(FULL, cls, f);
 					const bool valid_f = __shfl_sync(FULL, (int)valid, f) != 0;
-					const u64 cum_f = cum + __shfl_sync(FULL, pre, f);
+					const u64 cum_f = cum + shfl_u64(pre, f);
 					const u32 ones_f = ones + __shfl_sync(FULL, inct - mytok, f);
 					if (f > 0) {
 						const u32 pcls = __shfl_sync(FULL, cls, f - 1);
-						const u32 ex = __shfl_sync(FULL, (u32)L0.exit_state | ((u32)L1.exit_state << 16), f - 1);
+						const u32 ex = __shfl_sync(FULL, exits, f - 1);
 						carry_state = (ex >> (16 * (pcls & 1u))) & 0xffffu;
 					}
 					cum = cum_f;
@@ -906,7 +1077,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 						gs = (u64)wf * WS;
 						d = (int)(carry_state & 63u);
 						k = (int)(carry_state >> 6);
-						++dbg_slow;
+						++slow_entries;
 						continue;
 					}
 					const u32 m_f = __shfl_sync(FULL, (u32)my.m, f), qm_f = __shfl_sync(FULL, (u32)my.qm, f);
@@ -917,7 +1088,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 						gs = (u64)wf * WS;
 						d = (int)(entry_f & 63u);
 						k = (int)(entry_f >> 6);
-						++dbg_slow;
+						++slow_entries;
 						continue;
 					}
 					if (lane == 0) {
@@ -941,44 +1112,64 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 					sm = (int)m_f;
 				}
 				if (search) {
-					// ---- the pass ends on class sq of window sw at or behind slice sm: smallest slice i with
-					// cum + P(i + 1) - P(sm) >= T, by a 32-ary search on the member prefixes
+					// ---- the pass ends on class sq of window sw at or behind slice sm: smallest slice i >= sm with
+					// cum + P(i + 1) - P(sm) >= T.  A window has 128 slices: every lane fetches the tables and the stream
+					// words of four of them in one go, a ballot finds the slice, and that slice is stepped exactly.
 					search = false;
-					const long long t1 = clock64();
 					const u64 wbase = (u64)sw * WS;
-					const ulonglong2 pm2 = B.P[wbase + sm], pt2 = B.winPT[sw];
-					const u64 pm = sq ? pm2.y : pm2.x, ptot = sq ? pt2.y : pt2.x;
-					int lo = sm, hi = WS - 1;
-					while (hi > lo) {
-						const int span = hi - lo + 1;
-						const int step = (span + 31) / 32;
-						int probe = lo + lane * step + step - 1;
-						if (probe > hi)
-							probe = hi;
-						u64 pn;
-						if (probe + 1 < WS) {
-							const ulonglong2 v = B.P[wbase + probe + 1];
-							pn = sq ? v.y : v.x;
-						} else {
-							pn = ptot;
-						}
-						const u32 bal = __ballot_sync(FULL, cum + (pn - pm) >= T);
-						const int f = bal ? __ffs((int)bal) - 1 : 31; // bal != 0 by construction
-						const int nlo = lo + f * step;
-						int nhi = nlo + step - 1;
-						if (nhi > hi)
-							nhi = hi;
-						lo = nlo < hi ? nlo : hi;
-						hi = nhi;
+					const u64 g4 = wbase + 4u * (u32)lane;
+					ulonglong2 p4[4];
+#pragma unroll
+					for (int t = 0; t < 4; ++t)
+						p4[t] = B.P[g4 + t];
+					const uint4 e4 = *reinterpret_cast<const uint4 *>(B.E + g4);
+					const uint4 t4 = *reinterpret_cast<const uint4 *>(B.TK + g4);
+					u64 s5[5]; // stream words of my four slices and the one behind them
+#pragma unroll
+					for (int t = 0; t < 5; ++t)
+						s5[t] = ((g4 + t) << 6) < end_bits + 128 ? __ldg((const u64 *)stream + g4 + t) : 0ull;
+					const ulonglong2 pt2 = B.winPT[sw];
+					const u64 ptot = sq ? pt2.y : pt2.x;
+					u64 pv[5]; // members of class sq before my four slices and before the slice behind them
+#pragma unroll
+					for (int t = 0; t < 4; ++t)
+						pv[t] = sq ? p4[t].y : p4[t].x;
+					pv[4] = shfl_u64(pv[0], min(lane + 1, 31));
+					if (lane == 31)
+						pv[4] = ptot;
+					const u32 tk4[4] = {t4.x, t4.y, t4.z, t4.w};
+					const u32 en4[4] = {e4.x, e4.y, e4.z, e4.w};
+					// P and TK at the start slice sm
+					const int sm_lane = sm >> 2, sm_k = sm & 3;
+					const u64 pm = shfl_u64(sm_k == 0 ? pv[0] : (sm_k == 1 ? pv[1] : (sm_k == 2 ? pv[2] : pv[3])), sm_lane);
+					const u32 tkm = __shfl_sync(FULL, sm_k == 0 ? tk4[0] : (sm_k == 1 ? tk4[1] : (sm_k == 2 ? tk4[2] : tk4[3])), sm_lane);
+					u32 hit = 0;
+#pragma unroll
+					for (int t = 0; t < 4; ++t) {
+						const int idx = 4 * lane + t;
+						if (idx >= sm && cum + (pv[t + 1] - pm) >= T)
+							hit |= 1u << t;
 					}
+					const u32 bal = __ballot_sync(FULL, hit != 0);
+					if (!bal) {
+						event = EV_STOP; // cannot happen: the caller saw that the window covers the rest
+						tripped = 2;
+						break;
+					}
+					const int fl = __ffs((int)bal) - 1;
+					const int fk = __ffs((int)__shfl_sync(FULL, hit, fl)) - 1;
+					const int lo = 4 * fl + fk;
 					const u64 egs = wbase + lo;
-					const ulonglong2 pi2 = B.P[egs];
-					const u32 tki = B.TK[egs], tkm = B.TK[wbase + sm];
-					const u32 e = (B.E[egs] >> (16 * sq)) & 0xffffu;
-					cum += (sq ? pi2.y : pi2.x) - pm;
+					const u64 pi = shfl_u64(fk == 0 ? pv[0] : (fk == 1 ? pv[1] : (fk == 2 ? pv[2] : pv[3])), fl);
+					const u32 tki = __shfl_sync(FULL, fk == 0 ? tk4[0] : (fk == 1 ? tk4[1] : (fk == 2 ? tk4[2] : tk4[3])), fl);
+					const u32 e2 = __shfl_sync(FULL, fk == 0 ? en4[0] : (fk == 1 ? en4[1] : (fk == 2 ? en4[2] : en4[3])), fl);
+					const u64 a = shfl_u64(fk == 0 ? s5[0] : (fk == 1 ? s5[1] : (fk == 2 ? s5[2] : s5[3])), fl);
+					u64 b = shfl_u64(fk == 0 ? s5[1] : (fk == 1 ? s5[2] : (fk == 2 ? s5[3] : s5[4])), fl);
+					if (((egs + 1) << 6) >= end_bits + 64)
+						b = 0ull; // load_slice's rule for the second word
+					const u32 e = (e2 >> (16 * sq)) & 0xffffu;
+					cum += pi - pm;
 					ones += sq ? (tki >> 16) - (tkm >> 16) : (tki & 0xffffu) - (tkm & 0xffffu);
-					u64 a, b;
-					load_slice(stream, end_bits, egs, a, b);
 					d = (int)(e & 63u);
 					k = (int)(e >> 6);
 					if (e == PDEAD) {
@@ -992,11 +1183,8 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 					}
 					f_pos = (egs << 6) + (u64)d;
 					f_k = k;
-					cyc[2] += clock64() - t1;
 				}
 			}
-			if (lane == 0)
-				st->dbg_cs[j] = (unsigned short)min(dbg_stray - stray_before, 65535u);
 			if (event == EV_COVERED)
 				f_pending = 0;
 		}
@@ -1054,12 +1242,52 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 		st->stopped = stopped ? 1 : 0;
 		st->level = level;
 		st->nseg = nseg;
-		st->dbg_slow = dbg_slow;
-		st->dbg_stray = dbg_stray;
-		st->dbg_cyc[0] = (u64)cyc[0];
-		st->dbg_cyc[1] = (u64)cyc[1];
-		st->dbg_cyc[2] = (u64)cyc[2];
-		st->dbg_cyc[3] = (u64)(clock64() - t_begin);
+		st->nbulk = nbulk;
+		st->slow_entries = slow_entries;
+		st->exact_steps = exact_steps;
+		st->guard_tripped = tripped;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------- bulk segments
+
+// The 32 segment records of every super-window the resolver consumed whole: the same class scan the resolver runs for a
+// window round, one warp per super-window, all of them in parallel.
+__global__ void __launch_bounds__(128) dec_bulk_kernel(const __grid_constant__ DecBuffers B)
+{
+	const u32 FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const u32 nbulk = B.state->nbulk;
+	for (u32 r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nbulk; r += gridDim.x * (blockDim.x >> 5)) {
+		const DecBulk bk = B.bulk[r];
+		const u32 wl = bk.w0 + (u32)lane; // a clean super-window: every window exists, w0 >= 32
+		DecLink L0, L1;
+		load_link(B.link + 2 * (u64)wl, L0);
+		load_link(B.link + 2 * (u64)wl + 1, L1);
+		const u32 xprev = B.winX[wl - 1];
+		const u32 inc = scan_class_maps((u32)L0.qn | ((u32)L1.qn << 2), lane);
+		const u32 excl = __shfl_up_sync(FULL, inc, 1);
+		const u32 q = bk.cls;
+		const u32 cls = lane == 0 ? q : (excl >> (2 * q)) & 3u;
+		const DecLink &my = cls == 1u ? L1 : L0;
+		u64 incm = my.mem;
+#pragma unroll
+		for (int dd = 1; dd < 32; dd <<= 1) {
+			const u64 tm = shfl_u64(incm, max(lane - dd, 0));
+			if (lane >= dd)
+				incm += tm;
+		}
+		const u64 pre = incm - my.mem;
+		DecSeg sg;
+		sg.w = wl;
+		sg.j = bk.j;
+		sg.state = (unsigned short)((xprev >> (16 * (cls & 1u))) & 0xffffu);
+		sg.i0 = 0;
+		sg.m = my.m;
+		sg.qm = my.qm;
+		sg.cum0 = (u32)((u64)bk.cum0 + pre);
+		sg.cum_m = (u32)((u64)bk.cum0 + pre + my.stray_mem);
+		B.seg[bk.seg_base + lane] = sg;
 	}
 }
 
@@ -1383,7 +1611,9 @@ void dec_token_table(u32 *host_table)
 
 int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b, int nchunks, cudaStream_t st, long long *launches)
 {
-	const bool serial = b.scan_mode == 2 || (b.scan_mode == 0 && b.nwin >= DEC_SERIAL_MIN_WINDOWS && b.in_flight >= DEC_SERIAL_MIN_IN_FLIGHT);
+	// windows of 128 slices give the one-thread-per-chain walk enough warps to hide its latencies at any stream size, and it
+	// decodes every token once: it is the default; the CTA-per-window kernel stays as the cross-check (scan_mode 1)
+	const bool serial = b.scan_mode != 1;
 	if (serial)
 		dec_scan_serial_kernel<<<(2 * b.nwin + 127) / 128, 128, 0, st>>>(b.stream, b.end_bits, b.toklut, b.nwin, b.E, b.P, b.TK,
 		                                                                  b.winX, b.winPT, b.winTT);
@@ -1391,13 +1621,15 @@ int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b, int nchunks, cu
 		dec_scan_kernel<<<b.nwin, WS, 0, st>>>(b.stream, b.end_bits, b.toklut, b.E, b.P, b.TK, b.winX, b.winPT, b.winTT);
 	dec_link_kernel<<<(2 * b.nwin + 127) / 128, 128, 0, st>>>(b.stream, b.end_bits, b.nwin, b.E, b.P, b.TK, b.winX, b.winPT,
 	                                                           b.winTT, b.link);
+	dec_super_kernel<<<(b.nsuper + 3) / 4, 128, 0, st>>>(b.nwin, b.nsuper, b.link, b.super);
 	dec_resolve_kernel<<<1, 32, 0, st>>>(g, nchunks, b);
+	dec_bulk_kernel<<<(b.nsuper + 3) / 4 < 1184u ? (b.nsuper + 3) / 4 : 1184u, 128, 0, st>>>(b);
 	{
 		const int sms = dwt_device_sms();
-		const u32 want = b.nwin + (u32)nchunks, cap = (u32)sms * 64u;
+		const u32 want = b.nwin + 2u * (u32)nchunks, cap = (u32)sms * 64u;
 		dec_emit_kernel<<<want < cap ? want : cap, WS, 0, st>>>(b);
 	}
-	*launches += 4;
+	*launches += 6;
 	int depth_max = 0;
 	for (int c = 0; c < g.channels; ++c)
 		if (hs.planes[c] > depth_max)

@@ -244,11 +244,13 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		const size_t nslice = nwin * DWT_DEC_WS;
 		const size_t rank_words = (size_t)(dec_rank_bits(g, S, nchunks) / 32) + 8;
 		// per slice: E 4 B + P 16 B + TK 4 B; per window: X 4 B + PT 16 B + TT 4 B + two link records
-		const size_t scan_bytes = nslice * 24 + nwin * (24 + 2 * sizeof(DecLink)) + 256;
+		const size_t nsuper = (nwin + DWT_DEC_SUPER - 1) / DWT_DEC_SUPER;
+		const size_t scan_bytes = nslice * 24 + nwin * (24 + 2 * sizeof(DecLink)) + nsuper * 2 * sizeof(DecSuper) +
+		                          (nsuper + (size_t)nchunks + 8) * sizeof(DecBulk) + 256;
 		if (c->bs.ensure(bs_words * 4 + 64) || c->sig.ensure(sig_words * 4 + 64) || c->dstate.ensure(sizeof(DecState)) ||
 		    c->mem_pref.ensure(ntiles * 8 + 64) || c->ref_pref.ensure(ntiles * 8 + 64) ||
 		    c->ones_rank.ensure(rank_words * 8 + 64) || c->dec_scan.ensure(scan_bytes) ||
-		    c->dec_seg.ensure((nwin + (size_t)nchunks + 1) * sizeof(DecSeg)) ||
+		    c->dec_seg.ensure((nwin + 2 * (size_t)nchunks + 64) * sizeof(DecSeg)) ||
 		    c->dec_chunks.ensure((size_t)DWT_MAX_CHUNKS * sizeof(DecChunk)) || c->dsched.ensure(sizeof(Sched)))
 			return -1;
 		if (!c->dec_lut_ready) {
@@ -281,6 +283,11 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		sp += nwin * 16;
 		b.link = (DecLink *)sp;
 		sp += nwin * 2 * sizeof(DecLink);
+		b.super = (DecSuper *)sp;
+		sp += nsuper * 2 * sizeof(DecSuper);
+		b.nsuper = (u32)nsuper;
+		b.bulk = (DecBulk *)sp;
+		sp += (nsuper + (size_t)nchunks + 8) * sizeof(DecBulk);
 		b.E = (u32 *)sp;
 		sp += nslice * 4;
 		b.TK = (u32 *)sp;
@@ -301,6 +308,10 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		CUDA_OK(cudaMemcpyAsync(h_state, c->dstate.p, sizeof(DecState), cudaMemcpyDeviceToHost, st));
 		CUDA_OK(cudaEventRecord(c->ev[1], st));
 		CUDA_OK(ctx_stream_sync(c));
+		if (h_state->guard_tripped) {
+			dwt_set_error("decoder: the resolver's iteration guard fired (code %d): internal error", h_state->guard_tripped);
+			return -1;
+		}
 		level = h_state->level;
 	}
 	if (planes_max == 0 || nchunks == 0)
@@ -348,16 +359,8 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		stt->ms_total = ev_ms(c->ev[0], c->ev[3]);
 		stt->full_bits = (long long)h_state->bitpos;
 		stt->parse_windows = h_state->nseg;
-		stt->parse_jumps = h_state->dbg_slow;
-		stt->parse_exact = h_state->dbg_stray;
-		if (getenv("DWT_DEBUG")) {
-			fprintf(stderr, "resolve cycles: exact %llu linked %llu search %llu total %llu\n", h_state->dbg_cyc[0],
-			        h_state->dbg_cyc[1], h_state->dbg_cyc[2], h_state->dbg_cyc[3]);
-			for (int j = 0; j < nchunks; ++j)
-				if (h_state->dbg_cs[j] > 8)
-					fprintf(stderr, "  chunk %d (c%d l%d p%d): %u stray slices\n", j, S.chan[j], S.level[j], S.plane[j],
-					        h_state->dbg_cs[j]);
-		}
+		stt->parse_jumps = h_state->slow_entries;
+		stt->parse_exact = h_state->exact_steps;
 	}
 	return 0;
 }
