@@ -2,7 +2,7 @@
 NVCC    ?= /usr/local/cuda/bin/nvcc
 CC      ?= gcc
 ARCH    := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -Idwt_b200/csrc --use_fast_math
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -Idwt_b200/csrc --use_fast_math $(EXTRA)
 CFLAGS  := -std=c99 -O2 -W -Wall -fPIC -Iinclude
 CSRC    := dwt_b200/csrc
 LIB     := dwt_b200/libdwt_b200.so

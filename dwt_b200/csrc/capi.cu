@@ -448,6 +448,7 @@ extern "C" dwt_pool *dwt_pool_create_multi(const int *devices, int n_devices, in
 				return nullptr;
 			}
 			c->in_flight = workers;
+			c->sleepy_wait = workers > 1;
 			c->gate = workers > 1 ? p->gate[d].get() : nullptr;
 			p->ctx.push_back(c);
 			p->devices[d] = c->device; // device < 0 resolved to the current device

@@ -72,6 +72,9 @@ struct DecState {                 // device-resident cursor of the serial parse 
 	u32 nseg;                     // (chunk, window) segments handed to the emit kernel
 	u32 nbulk;                    // super-windows consumed whole: their 32 segments each are written by dec_bulk_kernel
 	u32 exact_steps, slow_entries; // resolver statistics: slices stepped token by token, entries into that mode
+	u32 n_super, n_window, n_search; // ... super-window rounds, window rounds, end searches
+	u32 dbg_hist[10];              // exact slice steps per window visit: 0, 1, 2, <=4, <=8, <=16, <=32, <=64, <=128, visits that joined
+	u32 dbg_reason[4];             // entries: chunk start, stray class, pass ends before the join, window not joined
 	int guard_tripped;            // the resolver's iteration guard fired (a bug, never a property of a stream)
 };
 
@@ -135,6 +138,8 @@ struct DecBuffers {
 	ulonglong2 *P;        // per slice: members consumed by each class since the window start
 	u32 *TK;              // per slice: tokens started by each class since the window start (t0 | t1 << 16)
 	u32 *winX;            // per window: exit states of the two classes
+	u32 *winX2;           // second copy for the lineage passes (they read one and write the other)
+	unsigned char *chg;   // 2 * nwin flags: windows whose class-1 chain a lineage pass replaced
 	ulonglong2 *winPT;    // per window: member totals
 	u32 *winTT;           // per window: token totals
 	DecLink *link;        // [window][class]

@@ -25,6 +25,8 @@
 //            stream, significance is updated.
 #include "coder.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int TG = DWT_TILE_GROUPS;
@@ -380,32 +382,25 @@ __global__ void __launch_bounds__(WS) dec_scan_kernel(const u32 *__restrict__ st
 constexpr u32 DEC_SERIAL_MIN_WINDOWS = 2048;
 constexpr int DEC_SERIAL_MIN_IN_FLIGHT = 4;
 
-__global__ void __launch_bounds__(128) dec_scan_serial_kernel(const u32 *__restrict__ stream, u64 end_bits,
-                                                               const u32 *__restrict__ toklut, u32 nwin, u32 *E, ulonglong2 *P,
-                                                               u32 *TK, u32 *winX, ulonglong2 *winPT, u32 *winTT)
+// chain q of window w walked serially from the state (d0, k0) at its first slice; fills the chain's per-slice tables and
+// the window's exit state / totals.  One flat loop over the token steps of the whole window: the lanes of a warp
+// (different windows) do not wait for each other at slice boundaries, a lane that crosses one closes the slice and
+// opens the next on the side.
+__device__ __forceinline__ void walk_window_chain(const u32 *__restrict__ stream, u64 end_bits, const u32 *lut, u32 w, u32 q, int d0,
+                                                  int k0, u32 *E, ulonglong2 *P, u32 *TK, u32 *winX, ulonglong2 *winPT, u32 *winTT)
 {
-	__shared__ u32 lut[1 << LUT_BITS];
-	for (int i = threadIdx.x; i < (1 << LUT_BITS); i += 128)
-		lut[i] = __ldg(toklut + i);
-	__syncthreads();
-	const u32 t = blockIdx.x * 128 + threadIdx.x;
-	const u32 w = t >> 1, q = t & 1u;
-	if (w >= nwin)
-		return;
 	unsigned short *E16 = reinterpret_cast<unsigned short *>(E), *TK16 = reinterpret_cast<unsigned short *>(TK);
 	u64 *P64 = reinterpret_cast<u64 *>(P);
 	const u64 gs0 = (u64)w * WS;
 	auto word = [&](u64 slice) { return (slice << 6) < end_bits + 128 ? __ldg((const u64 *)stream + slice) : 0ull; };
 	u64 a = word(gs0), b = word(gs0 + 1), c = word(gs0 + 2), dnext = word(gs0 + 3); // two slices of look-ahead
-	// One flat loop over the token steps of the whole window: the lanes of a warp (different windows) do not wait for
-	// each other at slice boundaries, a lane that crosses one closes the slice and opens the next on the side.
-	int i = 0, d = (int)q, k = 0;
+	int i = 0, d = d0, k = k0;
 	int avail = clamp_avail(end_bits, gs0 << 6);
 	bool lut_ok = avail >= 64 + LUT_BITS + 4;
-	u32 x = q;
+	u32 x = (u32)d0 | ((u32)k0 << 6);
 	u64 pm = 0, m = 0;  // members before the slice / inside it so far
 	u32 ptok = 0, n = 0;
-	E16[2 * gs0 + q] = (unsigned short)q;
+	E16[2 * gs0 + q] = (unsigned short)x;
 	P64[2 * gs0 + q] = 0;
 	TK16[2 * gs0 + q] = 0;
 	for (;;) {
@@ -465,6 +460,83 @@ __global__ void __launch_bounds__(128) dec_scan_serial_kernel(const u32 *__restr
 	reinterpret_cast<unsigned short *>(winX)[2 * w + q] = (unsigned short)x;
 	reinterpret_cast<u64 *>(winPT)[2 * w + q] = pm;
 	reinterpret_cast<unsigned short *>(winTT)[2 * w + q] = (unsigned short)ptok;
+}
+
+// ONE thread per (window, chain) walks its 128 slices serially from the seed (bit q of the window, order 0), so every
+// token is decoded once per chain.  A stream of a few MB has tens of thousands of windows, which is all the parallelism
+// the latency-bound walks need.
+__global__ void __launch_bounds__(128) dec_scan_serial_kernel(const u32 *__restrict__ stream, u64 end_bits,
+                                                               const u32 *__restrict__ toklut, u32 nwin, u32 *E, ulonglong2 *P,
+                                                               u32 *TK, u32 *winX, ulonglong2 *winPT, u32 *winTT)
+{
+	__shared__ u32 lut[1 << LUT_BITS];
+	for (int i = threadIdx.x; i < (1 << LUT_BITS); i += 128)
+		lut[i] = __ldg(toklut + i);
+	__syncthreads();
+	const u32 t = blockIdx.x * 128 + threadIdx.x;
+	const u32 w = t >> 1, q = t & 1u;
+	if (w >= nwin)
+		return;
+	walk_window_chain(stream, end_bits, lut, w, q, (int)q, 0, E, P, TK, winX, winPT, winTT);
+}
+
+// Lineage pass.  A chain seeded at a window start needs a while to fall onto the stream's true token grid: a few
+// tokens where the Rice order is 0 (dense planes), but on the order of a hundred slices where runs are long (the top
+// planes of the big levels: the order there is ~10 and a chain at order 0 reads payload bits as short tokens until a
+// long zero string lifts it).  With 128-slice windows such regions would never have a canonical chain old enough to be
+// the true one.  So class 1 of window w is replaced by the CONTINUATION of class 1 of window w - 1 wherever that
+// continuation does not fall onto one of w's chains within a few slices; every pass makes the oldest chain of such a
+// region one window older (pass p reads the exits of pass p - 1: no ordering between the threads of a pass).  Dense
+// regions are left alone: there the continuation joins at once.
+constexpr int EXTEND_JOIN_SLICES = 6;
+
+__global__ void __launch_bounds__(128) dec_scan_extend_kernel(const u32 *__restrict__ stream, u64 end_bits,
+                                                               const u32 *__restrict__ toklut, u32 nwin, u32 *E, ulonglong2 *P,
+                                                               u32 *TK, const u32 *__restrict__ winX_in, u32 *winX_out,
+                                                               ulonglong2 *winPT, u32 *winTT, const unsigned char *changed_in,
+                                                               unsigned char *changed_out)
+{
+	__shared__ u32 lut[1 << LUT_BITS];
+	const u32 w = blockIdx.x * 128 + threadIdx.x;
+	bool replace = false;
+	u32 st = PDEAD;
+	if (w < nwin) {
+		const u32 xin = winX_in[w];
+		winX_out[w] = xin;
+		changed_out[w] = 0;
+		if (w >= 1 && (!changed_in || changed_in[w - 1])) {
+			st = winX_in[w - 1] >> 16; // where the class-1 chain of the window in front ends
+			if (st != PDEAD) {
+				// does it fall onto one of this window's chains within a few slices?  (no table: a handful of tokens)
+				const u64 gs0 = (u64)w * WS;
+				u32 s = st;
+				replace = true;
+				for (int i = 0; i < EXTEND_JOIN_SLICES; ++i) {
+					const u32 e = E[gs0 + i];
+					if (s == (e & 0xffffu) || s == (e >> 16)) {
+						replace = false;
+						break;
+					}
+					u64 a, b;
+					load_slice(stream, end_bits, gs0 + i, a, b);
+					s = slice_exit(a, b, clamp_avail(end_bits, (gs0 + i) << 6), s);
+					if (s == PDEAD) {
+						replace = false; // a chain that dies here is not worth keeping
+						break;
+					}
+				}
+			}
+		}
+	}
+	if (!__syncthreads_or(replace))
+		return;
+	for (int i = threadIdx.x; i < (1 << LUT_BITS); i += 128)
+		lut[i] = __ldg(toklut + i);
+	__syncthreads();
+	if (!replace)
+		return;
+	walk_window_chain(stream, end_bits, lut, w, 1u, (int)(st & 63u), (int)(st >> 6), E, P, TK, winX_out, winPT, winTT);
+	changed_out[w] = 1;
 }
 
 // ---------------------------------------------------------------------------------------------- link
@@ -718,10 +790,23 @@ __device__ __forceinline__ void load_super(const DecSuper *src, DecSuper &S)
 
 // ---------------------------------------------------------------------------------------------- resolve
 
+// make EXTRA=-DDWT_RESOLVE_PROFILE: cycles per part of the resolver (development aid; not in the shipped library)
+#ifdef DWT_RESOLVE_PROFILE
+#define RP_BEGIN() const long long rp_t0 = clock64()
+#define RP_END(slot) rp_cyc[slot] += clock64() - rp_t0
+#else
+#define RP_BEGIN()
+#define RP_END(slot)
+#endif
+
 __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__ Geom G, int nchunks,
                                                           const __grid_constant__ DecBuffers B)
 {
 	static_assert(WS == 128, "the end search loads four slices per lane");
+#ifdef DWT_RESOLVE_PROFILE
+	long long rp_cyc[5] = {0, 0, 0, 0, 0};
+	const long long rp_start = clock64();
+#endif
 	__shared__ u32 sigcount[48];
 	__shared__ int missing[48];
 	__shared__ u32 lut[1 << LUT_BITS];
@@ -750,7 +835,8 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 	int level = -1;
 	bool stopped = false;
 	u64 rank_base = 0;
-	u32 nseg = 0, nbulk = 0, slow_entries = 0, exact_steps = 0;
+	u32 nseg = 0, nbulk = 0, slow_entries = 0, exact_steps = 0, n_super = 0, n_window = 0, n_search = 0;
+	u32 hist[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, reason[4] = {0, 0, 0, 0};
 	int tripped = 0;
 	// every pass of the loops below moves on by at least one window or ends the chunk; the guard only exists so that a
 	// bug can never hang the device
@@ -817,6 +903,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 			dead_link(pfL1);
 			u32 guard = 0;
 			++slow_entries;
+			++reason[0];
 			while (event == EV_NONE) {
 				if (++guard > guard_max) {
 					tripped = 1;
@@ -825,6 +912,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 				}
 				if (mode == 0) {
 					// ---- exact steps from slice gs until the chain joins a canonical chain, the window ends or the pass ends
+					RP_BEGIN();
 					const u32 cw = (u32)(gs / WS);
 					const int i0 = (int)(gs - (u64)cw * WS);
 					if (cw >= nwin) {
@@ -850,6 +938,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 					}
 					const u32 seg_state = (u32)d | ((u32)k << 6);
 					const u64 seg_cum0 = cum;
+					const u32 steps0 = exact_steps;
 					int i = i0, m = WS, qm = 0;
 					u64 pm = 0;   // members of class qm before the join slice
 					u32 tkm = 0;  // tokens of both classes before the join slice
@@ -901,9 +990,19 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 						B.seg[nseg] = sg;
 					}
 					++nseg;
+					RP_END(0);
+					{
+						const u32 n = exact_steps - steps0;
+						const int b = n <= 2 ? (int)n : (n <= 4 ? 3 : (n <= 8 ? 4 : (n <= 16 ? 5 : (n <= 32 ? 6 : (n <= 64 ? 7 : 8)))));
+#pragma unroll
+						for (int t = 0; t < 9; ++t)
+							hist[t] += b == t;
+						hist[9] += m < WS;
+					}
 					if (event != EV_NONE)
 						break;
 					if (m == WS) { // the window ended before the chain joined: go on exactly in the next one
+						++reason[3];
 						gs = ((u64)cw + 1) * WS;
 						continue;
 					}
@@ -929,6 +1028,8 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 					}
 				} else if ((w & (DWT_DEC_SUPER - 1)) == 0 && !force_window) {
 					// ---- whole super-windows, 32 at a time: lane i looks at super-window w / 32 + i
+					++n_super;
+					RP_BEGIN();
 					const u32 sl = w / DWT_DEC_SUPER + (u32)lane;
 					DecSuper R0, R1;
 					if (sl < nsuper) {
@@ -982,10 +1083,13 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 					}
 					if (f < 32)
 						force_window = true; // something happens inside super-window w / 32: look at its windows
+					RP_END(1);
 				} else {
 					// ---- whole windows, lane i looks at window w + i, up to the end of the super-window
 					const int nlim = DWT_DEC_SUPER - (int)(w & (DWT_DEC_SUPER - 1));
 					force_window = false;
+					++n_window;
+					RP_BEGIN();
 					const u32 wl = w + (u32)lane;
 					const bool valid = wl < nwin && lane < nlim;
 					DecLink L0, L1;
@@ -1044,6 +1148,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 						B.seg[nseg + lane] = sg;
 					}
 					nseg += (u32)f;
+					RP_END(2);
 					const u32 exits = (u32)L0.exit_state | ((u32)L1.exit_state << 16);
 					if (f >= nlim) { // every window up to the super-window boundary was consumed (f == nlim)
 						const int src = nlim - 1;
@@ -1078,6 +1183,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 						d = (int)(carry_state & 63u);
 						k = (int)(carry_state >> 6);
 						++slow_entries;
+						++reason[1];
 						continue;
 					}
 					const u32 m_f = __shfl_sync(FULL, (u32)my.m, f), qm_f = __shfl_sync(FULL, (u32)my.qm, f);
@@ -1089,6 +1195,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 						d = (int)(entry_f & 63u);
 						k = (int)(entry_f >> 6);
 						++slow_entries;
+						++reason[2];
 						continue;
 					}
 					if (lane == 0) {
@@ -1116,6 +1223,8 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 					// cum + P(i + 1) - P(sm) >= T.  A window has 128 slices: every lane fetches the tables and the stream
 					// words of four of them in one go, a ballot finds the slice, and that slice is stepped exactly.
 					search = false;
+					++n_search;
+					RP_BEGIN();
 					const u64 wbase = (u64)sw * WS;
 					const u64 g4 = wbase + 4u * (u32)lane;
 					ulonglong2 p4[4];
@@ -1183,6 +1292,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 					}
 					f_pos = (egs << 6) + (u64)d;
 					f_k = k;
+					RP_END(3);
 				}
 			}
 			if (event == EV_COVERED)
@@ -1245,7 +1355,18 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 		st->nbulk = nbulk;
 		st->slow_entries = slow_entries;
 		st->exact_steps = exact_steps;
+		st->n_super = n_super;
+		st->n_window = n_window;
+		st->n_search = n_search;
+		for (int t = 0; t < 10; ++t)
+			st->dbg_hist[t] = hist[t];
+		for (int t = 0; t < 4; ++t)
+			st->dbg_reason[t] = reason[t];
 		st->guard_tripped = tripped;
+#ifdef DWT_RESOLVE_PROFILE
+		printf("resolver cycles: exact-step visits %lld, super rounds %lld, window rounds %lld, end searches %lld, total %lld\n", rp_cyc[0],
+		       rp_cyc[1], rp_cyc[2], rp_cyc[3], clock64() - rp_start);
+#endif
 	}
 }
 
@@ -1609,8 +1730,17 @@ void dec_token_table(u32 *host_table)
 	}
 }
 
-int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b, int nchunks, cudaStream_t st, long long *launches)
+// Lineage passes cost the latency of one lone window walk each (~0.18 ms) whatever the stream size, and save exact resolver
+// steps in proportion to the stream's slow-to-synchronise regions.  Measured (single frame, coder stage): 8K photo
+// 5.50 / 4.75 / 4.29 / 3.92 / 3.63 ms for 0 / 1 / 2 / 3 / 5 passes, 4K photo 1.85 / 1.96 / 2.12 / 2.14 ms for 0 / 1 / 2 / 3.
+static int lineage_passes(u32 nwin)
 {
+	return nwin >= 32768u ? 3 : (nwin >= 20000u ? 1 : 0);
+}
+
+int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b_in, int nchunks, cudaStream_t st, long long *launches)
+{
+	DecBuffers b = b_in;
 	// windows of 128 slices give the one-thread-per-chain walk enough warps to hide its latencies at any stream size, and it
 	// decodes every token once: it is the default; the CTA-per-window kernel stays as the cross-check (scan_mode 1)
 	const bool serial = b.scan_mode != 1;
@@ -1619,6 +1749,24 @@ int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b, int nchunks, cu
 		                                                                  b.winX, b.winPT, b.winTT);
 	else
 		dec_scan_kernel<<<b.nwin, WS, 0, st>>>(b.stream, b.end_bits, b.toklut, b.E, b.P, b.TK, b.winX, b.winPT, b.winTT);
+	++*launches;
+	{
+		u32 *xin = b.winX, *xout = b.winX2;
+		unsigned char *cin = nullptr, *cout = b.chg;
+		static const int forced = getenv("DWT_LINEAGE") ? atoi(getenv("DWT_LINEAGE")) : -1; // tuning aid
+		const int passes = forced >= 0 ? forced : lineage_passes(b.nwin);
+		for (int pass = 0; pass < passes; ++pass) {
+			dec_scan_extend_kernel<<<(b.nwin + 127) / 128, 128, 0, st>>>(b.stream, b.end_bits, b.toklut, b.nwin, b.E, b.P, b.TK, xin,
+			                                                             xout, b.winPT, b.winTT, cin, cout);
+			++*launches;
+			u32 *t = xin;
+			xin = xout;
+			xout = t;
+			cin = cout;
+			cout = cout == b.chg ? b.chg + b.nwin : b.chg;
+		}
+		b.winX = xin; // the exits after the last pass
+	}
 	dec_link_kernel<<<(2 * b.nwin + 127) / 128, 128, 0, st>>>(b.stream, b.end_bits, b.nwin, b.E, b.P, b.TK, b.winX, b.winPT,
 	                                                           b.winTT, b.link);
 	dec_super_kernel<<<(b.nsuper + 3) / 4, 128, 0, st>>>(b.nwin, b.nsuper, b.link, b.super);
@@ -1629,7 +1777,7 @@ int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b, int nchunks, cu
 		const u32 want = b.nwin + 2u * (u32)nchunks, cap = (u32)sms * 64u;
 		dec_emit_kernel<<<want < cap ? want : cap, WS, 0, st>>>(b);
 	}
-	*launches += 6;
+	*launches += 5;
 	int depth_max = 0;
 	for (int c = 0; c < g.channels; ++c)
 		if (hs.planes[c] > depth_max)

@@ -32,6 +32,7 @@ struct dwt_ctx {
 	cudaEvent_t ev[9] = {};   // 0..3 stage timers, 4..7 caller slots, 8 cross-context waits
 	struct XferGate *gate = nullptr; // set by a pool: see ctx_copy
 	cudaEvent_t sync_ev = nullptr; // ctx_stream_sync: polled briefly, then waited for with the thread asleep
+	bool sleepy_wait = false;      // set for the contexts of a pool (many waiting threads); a lone context spins
 	cudaEvent_t xfer_ev[2] = {};   // completion of this context's latest gated copy, per direction
 
 	// geometry cache
@@ -91,9 +92,11 @@ struct XferGate {
 // copy on the context's stream and, if `wait`, wait for it.  Gated device -> host copies first wait for the stream's
 // kernels, so that the copies queued behind them in the chain are not held up by this context's compute.
 cudaError_t ctx_copy(dwt_ctx *c, void *dst, const void *src, size_t n, cudaMemcpyKind kind, bool wait);
-// wait for the context's stream: a short poll of an event (the common wait is a few microseconds), then a blocking
-// cudaEventSynchronize that leaves the core to other threads (a pool has more waiting threads than a GPU box has cores
-// per GPU).  DWT_SYNC=spin restores cudaStreamSynchronize, DWT_SPIN_US sets the poll time (default 20).
+// wait for the context's stream.  A lone context spins in cudaStreamSynchronize: a frame has three such waits and a
+// sleeping thread wakes up 100-300 us late (measured: 6.8 -> 10.1 ms per 8K round trip).  The contexts of a pool poll an
+// event for ~20 us and then sleep in cudaEventSynchronize (cudaEventBlockingSync): a pool has more waiting threads than a
+// GPU box has cores per GPU, and the other contexts keep the GPU busy meanwhile (measured: +4 % end to end at N = 1).
+// DWT_SYNC=spin / block forces one behaviour, DWT_SPIN_US sets the poll time.
 cudaError_t ctx_stream_sync(dwt_ctx *c);
 int ctx_upload_stream(dwt_ctx *c, const uint8_t *stream, size_t len, bool wait);
 const int *ctx_root_ll(dwt_ctx *c);      // device pointer to the planar root LL after ctx_forward_transform

@@ -246,7 +246,7 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		// per slice: E 4 B + P 16 B + TK 4 B; per window: X 4 B + PT 16 B + TT 4 B + two link records
 		const size_t nsuper = (nwin + DWT_DEC_SUPER - 1) / DWT_DEC_SUPER;
 		const size_t scan_bytes = nslice * 24 + nwin * (24 + 2 * sizeof(DecLink)) + nsuper * 2 * sizeof(DecSuper) +
-		                          (nsuper + (size_t)nchunks + 8) * sizeof(DecBulk) + 256;
+		                          (nsuper + (size_t)nchunks + 8) * sizeof(DecBulk) + nwin * 4 + round_up(2 * nwin, 16) + 256;
 		if (c->bs.ensure(bs_words * 4 + 64) || c->sig.ensure(sig_words * 4 + 64) || c->dstate.ensure(sizeof(DecState)) ||
 		    c->mem_pref.ensure(ntiles * 8 + 64) || c->ref_pref.ensure(ntiles * 8 + 64) ||
 		    c->ones_rank.ensure(rank_words * 8 + 64) || c->dec_scan.ensure(scan_bytes) ||
@@ -295,6 +295,10 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		b.winX = (u32 *)sp;
 		sp += nwin * 4;
 		b.winTT = (u32 *)sp;
+		sp += nwin * 4;
+		b.winX2 = (u32 *)sp;
+		sp += nwin * 4;
+		b.chg = (unsigned char *)sp;
 		b.seg = c->dec_seg.as<DecSeg>();
 		b.chunks = c->dec_chunks.as<DecChunk>();
 		b.tile_sums = c->mem_pref.as<u32>();
@@ -361,6 +365,17 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		stt->parse_windows = h_state->nseg;
 		stt->parse_jumps = h_state->slow_entries;
 		stt->parse_exact = h_state->exact_steps;
+		if (getenv("DWT_DEBUG"))
+			fprintf(stderr, "resolver: %u segments, %u bulk super-windows, %u exact-step entries, %u exact slice steps, %u super rounds, "
+			                "%u window rounds, %u end searches\n", h_state->nseg, h_state->nbulk, h_state->slow_entries,
+			        h_state->exact_steps, h_state->n_super, h_state->n_window, h_state->n_search);
+		if (getenv("DWT_DEBUG")) {
+			fprintf(stderr, "  exact steps per window visit (0,1,2,<=4,..,<=128 | joined):");
+			for (int t = 0; t < 10; ++t)
+				fprintf(stderr, " %u", h_state->dbg_hist[t]);
+			fprintf(stderr, "\n  entries: %u chunk starts, %u stray, %u end-before-join, %u window-not-joined\n", h_state->dbg_reason[0],
+			        h_state->dbg_reason[1], h_state->dbg_reason[2], h_state->dbg_reason[3]);
+		}
 	}
 	return 0;
 }
