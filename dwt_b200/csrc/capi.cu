@@ -11,6 +11,7 @@
 #include <thread>
 #include <vector>
 
+#include <sched.h>
 #include <string.h>
 
 
@@ -430,6 +431,10 @@ extern "C" dwt_pool *dwt_pool_create_multi(const int *devices, int n_devices, in
 	}
 	dwt_pool *p = new dwt_pool();
 	p->workers = workers;
+	// more waiting threads than cores for this GPU's share of the box: let them sleep instead of spin (ctx_stream_sync)
+	cpu_set_t cpus;
+	const int ncpu = sched_getaffinity(0, sizeof(cpus), &cpus) == 0 ? CPU_COUNT(&cpus) : 1;
+	const bool sleepy = workers > 1 && workers > ncpu / count;
 	if (!devices || n_devices <= 0) { // every visible device
 		for (int d = 0; d < count; ++d)
 			p->devices.push_back(d);
@@ -448,7 +453,7 @@ extern "C" dwt_pool *dwt_pool_create_multi(const int *devices, int n_devices, in
 				return nullptr;
 			}
 			c->in_flight = workers;
-			c->sleepy_wait = workers > 1;
+			c->sleepy_wait = sleepy;
 			c->gate = workers > 1 ? p->gate[d].get() : nullptr;
 			p->ctx.push_back(c);
 			p->devices[d] = c->device; // device < 0 resolved to the current device

@@ -1754,7 +1754,8 @@ int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b_in, int nchunks,
 		u32 *xin = b.winX, *xout = b.winX2;
 		unsigned char *cin = nullptr, *cout = b.chg;
 		static const int forced = getenv("DWT_LINEAGE") ? atoi(getenv("DWT_LINEAGE")) : -1; // tuning aid
-		const int passes = forced >= 0 ? forced : lineage_passes(b.nwin);
+		// several frames in flight: the resolver's latency hides behind the other frames' kernels, the passes are only work
+		const int passes = forced >= 0 ? forced : (b.in_flight >= 4 ? 0 : lineage_passes(b.nwin));
 		for (int pass = 0; pass < passes; ++pass) {
 			dec_scan_extend_kernel<<<(b.nwin + 127) / 128, 128, 0, st>>>(b.stream, b.end_bits, b.toklut, b.nwin, b.E, b.P, b.TK, xin,
 			                                                             xout, b.winPT, b.winTT, cin, cout);

@@ -10,6 +10,12 @@
 // the output is written as 32-coefficient groups, bit-sliced: one 32-bit word per bit-plane plus a sign
 // word, which is what the coder kernels consume.
 #include "hilbert.cuh"
+#include "bitslice.cuh"
+
+#include <cuda.h>
+
+#include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -415,6 +421,348 @@ __global__ void __launch_bounds__(256) reconstruct_kernel(const __grid_constant_
 	}
 }
 
+// ------------------------------------------------------------------------------------------------ TMA-staged full cells
+//
+// A full cell is a 32 x 32 x C box of the pyramid: exactly what the tensor memory accelerator moves.  One
+// cp.async.bulk.tensor per cell brings the box into shared memory (128-byte swizzle, so that the curve-ordered reads
+// below spread over the banks), an mbarrier tells the warp when it has landed, and the next cell's box is already in
+// flight in the warp's second buffer.  Lane k then owns the cell's k-th group of 32 curve-consecutive coefficients and
+// turns them into bit-plane words with a 16 x 16 bit-matrix transpose in registers (bitslice.cuh) instead of one warp
+// ballot per plane and group: ~6 instead of ~30 warp instructions per group and channel.  Every plane row of the cell
+// leaves as one 128-byte run.  The inverse (reconstruct) mirrors it and sends the cell back with a TMA store.
+// Requirements: rows 16-byte aligned in HBM (width % 4 == 0), at most 15 bit-planes; everything else takes the
+// ballot kernels above.
+
+constexpr int TMA_WARPS = 4;
+
+__device__ __forceinline__ u32 smem_addr(const void *p)
+{
+	return (u32)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(u64 *bar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{
+	asm volatile("{\n"
+	             ".reg .pred p;\n"
+	             "WAIT_%=:\n"
+	             "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	             "@p bra DONE_%=;\n"
+	             "bra WAIT_%=;\n"
+	             "DONE_%=:\n"
+	             "}" ::"r"(smem_addr(bar)),
+	             "r"(parity)
+	             : "memory");
+}
+
+__device__ __forceinline__ void tma_load_cell(void *dst, const CUtensorMap *map, int x, int y, u64 *bar)
+{
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+	                 smem_addr(dst)),
+	             "l"(reinterpret_cast<u64>(map)), "r"(x), "r"(y), "r"(0), "r"(smem_addr(bar))
+	             : "memory");
+}
+
+__device__ __forceinline__ void tma_store_cell(const CUtensorMap *map, int x, int y, const void *src)
+{
+	asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(reinterpret_cast<u64>(map)),
+	             "r"(x), "r"(y), "r"(0), "r"(smem_addr(src))
+	             : "memory");
+}
+
+struct TmaSmem { // carved out of the dynamic shared memory, cell buffers first (1024-byte aligned for the swizzle)
+	int *cells;            // [TMA_WARPS][2][NC][1024]
+	unsigned short *lut;   // [4][1024]
+	u64 *bars;             // [TMA_WARPS][2]
+};
+
+template <int NC>
+__device__ __forceinline__ TmaSmem tma_smem(unsigned char *raw, const unsigned short *__restrict__ tile_lut)
+{
+	TmaSmem s;
+	const u32 base = smem_addr(raw);
+	raw += (1024u - (base & 1023u)) & 1023u;
+	s.cells = reinterpret_cast<int *>(raw);
+	s.lut = reinterpret_cast<unsigned short *>(raw + (size_t)TMA_WARPS * 2 * NC * 4096);
+	s.bars = reinterpret_cast<u64 *>(s.lut + 4096);
+	for (int i = threadIdx.x; i < 2048; i += blockDim.x) // 8 KB of offsets, two per word
+		reinterpret_cast<u32 *>(s.lut)[i] = __ldg(reinterpret_cast<const u32 *>(tile_lut) + i);
+	if (threadIdx.x < TMA_WARPS * 2)
+		mbar_init(s.bars + threadIdx.x, 1);
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	__syncthreads();
+	return s;
+}
+
+template <int NC>
+constexpr size_t tma_smem_bytes()
+{
+	return (size_t)TMA_WARPS * 2 * NC * 4096 + 8192 + TMA_WARPS * 2 * 8 + 1024;
+}
+
+struct CellRef {
+	int ox, oy;   // cell origin in the pyramid
+	u32 orient;   // bit 0 transpose, bit 1 point reflection
+	u32 g0;       // first group of the cell inside its channel's group axis (level base included)
+	int s;        // rank of the cell's first position inside that group
+	int level;
+};
+
+__device__ __forceinline__ CellRef cell_ref(const HParams &P, u32 ent)
+{
+	const HLevel &L = P.lv[ent >> 28];
+	const u32 q = ent & 0x0fffffffu;
+	const u32 R0 = __ldg(P.cell_base + L.cell_off + q), info = __ldg(P.cell_info + L.cell_off + q);
+	CellRef c;
+	c.ox = (int)(info & 0xfffu) * 32;
+	c.oy = (int)((info >> 12) & 0xfffu) * 32;
+	c.orient = info >> 24;
+	c.g0 = (u32)L.gbase + (R0 >> 5);
+	c.s = (int)(R0 & 31u);
+	c.level = (int)(ent >> 28);
+	return c;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(TMA_WARPS * 32) linearize_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                        const __grid_constant__ HParams P,
+                                                                        const u32 *__restrict__ list, int nlist,
+                                                                        const unsigned short *__restrict__ tile_lut, u32 *bs)
+{
+	extern __shared__ unsigned char tma_raw[];
+	const TmaSmem sm = tma_smem<NC>(tma_raw, tile_lut);
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	int *mycells = sm.cells + (size_t)wid * 2 * NC * 1024;
+	u64 *mybar = sm.bars + wid * 2;
+	const int stride = gridDim.x * TMA_WARPS;
+	int item = blockIdx.x * TMA_WARPS + wid;
+	auto issue = [&](int it, int buf) { // lane 0: the cell's box into buffer `buf`
+		const CellRef c = cell_ref(P, __ldg(list + it));
+		mbar_expect_tx(mybar + buf, NC * 4096u);
+		tma_load_cell(mycells + (size_t)buf * NC * 1024, &tmap, c.ox, c.oy, mybar + buf);
+	};
+	if (item < nlist && lane == 0)
+		issue(item, 0);
+	u32 phases = 0;
+	int buf = 0;
+	for (; item < nlist; item += stride, buf ^= 1) {
+		if (item + stride < nlist && lane == 0)
+			issue(item + stride, buf ^ 1); // the other buffer was released by the __syncwarp that ended the last round
+		const CellRef c = cell_ref(P, __ldg(list + item));
+		mbar_wait(mybar + buf, (phases >> buf) & 1u);
+		phases ^= 1u << buf;
+		const int *cell = mycells + (size_t)buf * NC * 1024;
+		const unsigned short *lo = sm.lut + c.orient * 1024;
+		const int s = c.s;
+		// lane k owns the ranks 32 k - s .. 32 k - s + 31 of the cell (mod 1024: for s > 0 lane 0 holds the head of the cell's
+		// first group in its high bits and the tail of the cell's last group in its low bits)
+		u32 w[NC][16];
+#pragma unroll
+		for (int i = 0; i < 32; ++i) {
+			const int ip = (i - s) & 31;
+			const int kp = (lane - (i < s ? 1 : 0)) & 31;
+			const int off = lo[ip * 32 + kp];
+#pragma unroll
+			for (int ch = 0; ch < NC; ++ch) {
+				const u32 h = bitslice_half(cell[ch * 1024 + off]);
+				if (i < 16)
+					w[ch][i] = h;
+				else
+					w[ch][i - 16] |= h << 16;
+			}
+		}
+		const bool split = s != 0 && lane == 0;
+		const u32 lo_mask = (1u << s) - 1u; // ranks below s of lane 0's word belong to the group behind the cell's last whole one
+#pragma unroll
+		for (int ch = 0; ch < NC; ++ch) {
+			bitslice_transpose16(w[ch]);
+			const int planes = P.lay.planes[ch];
+			u32 *dst = bs + P.lay.bsbase[ch] + c.g0 + lane;
+#pragma unroll
+			for (int p = 0; p < 16; ++p) {
+				if (p < 15 && p >= planes)
+					continue;
+				const u32 v = w[ch][p];
+				u32 *d = dst + (long long)(p == 15 ? planes : p) * P.GT;
+				if (!split) {
+					*d = v;
+				} else {
+					if (v & ~lo_mask)
+						atomicOr(d, v & ~lo_mask);
+					if (v & lo_mask)
+						atomicOr(d + 32, v & lo_mask);
+				}
+			}
+		}
+		__syncwarp(); // every lane is done with the buffer before lane 0 lets the next box land in it
+	}
+}
+
+// The inverse has no box to wait for -- its input are the plane rows, fetched with plain loads -- so what hides the load
+// latency is the number of warps: one cell buffer per warp (the TMA store of cell n reads it while the warp is busy with
+// the loads and the transposes of cell n + 1), 8 warps per CTA, 2 CTAs per SM.
+constexpr int REC_WARPS = 8;
+
+template <int NC>
+constexpr size_t rec_smem_bytes()
+{
+	return (size_t)REC_WARPS * NC * 4096 + 8192 + 1024;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(REC_WARPS * 32, 2) reconstruct_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                             const __grid_constant__ HParams P,
+                                                                             const u32 *__restrict__ list, int nlist,
+                                                                             const unsigned short *__restrict__ tile_lut,
+                                                                             const u32 *__restrict__ bs,
+                                                                             const int *__restrict__ missing, int levels_used)
+{
+	extern __shared__ unsigned char tma_raw[];
+	unsigned char *raw = tma_raw;
+	raw += (1024u - (smem_addr(raw) & 1023u)) & 1023u;
+	int *cells = reinterpret_cast<int *>(raw);
+	unsigned short *lut = reinterpret_cast<unsigned short *>(raw + (size_t)REC_WARPS * NC * 4096);
+	for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+		reinterpret_cast<u32 *>(lut)[i] = __ldg(reinterpret_cast<const u32 *>(tile_lut) + i);
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	int *cell = cells + (size_t)wid * NC * 1024;
+	const int stride = gridDim.x * REC_WARPS;
+	for (int item = blockIdx.x * REC_WARPS + wid; item < nlist; item += stride) {
+		const CellRef c = cell_ref(P, __ldg(list + item));
+		if (c.level >= levels_used)
+			continue;
+		const unsigned short *lo = lut + c.orient * 1024;
+		const int s = c.s;
+		const bool split = s != 0 && lane == 0;
+		const u32 lo_mask = (1u << s) - 1u;
+		u32 w[NC][16];
+		int bias[NC];
+#pragma unroll
+		for (int ch = 0; ch < NC; ++ch) {
+			const int planes = P.lay.planes[ch];
+			const u32 *src = bs + P.lay.bsbase[ch] + c.g0 + lane;
+#pragma unroll
+			for (int p = 0; p < 16; ++p) {
+				u32 v = 0;
+				if (p == 15 || p < planes) {
+					const u32 *r = src + (long long)(p == 15 ? planes : p) * P.GT;
+					v = __ldg(r);
+					if (split)
+						v = (v & ~lo_mask) | (__ldg(r + 32) & lo_mask);
+				}
+				w[ch][p] = v;
+			}
+			const int m = missing[ch * 16 + c.level] - 2; // decode.c:51-58
+			bias[ch] = m >= 0 ? 1 << m : 0;
+		}
+#pragma unroll
+		for (int ch = 0; ch < NC; ++ch)
+			bitslice_transpose16(w[ch]);
+		// the TMA store of the previous cell must have finished reading the buffer
+		if (lane == 0)
+			asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+		__syncwarp();
+#pragma unroll
+		for (int i = 0; i < 32; ++i) {
+			const int ip = (i - s) & 31;
+			const int kp = (lane - (i < s ? 1 : 0)) & 31;
+			const int off = lo[ip * 32 + kp];
+#pragma unroll
+			for (int ch = 0; ch < NC; ++ch) {
+				int v = bitslice_value(i < 16 ? (w[ch][i] & 0xffffu) : (w[ch][i - 16] >> 16));
+				if (v != 0)
+					v += v < 0 ? -bias[ch] : bias[ch];
+				cell[ch * 1024 + off] = v;
+			}
+		}
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // my writes before the bulk copy reads them
+		__syncwarp();
+		if (lane == 0) {
+			tma_store_cell(&tmap, c.ox, c.oy, cell);
+			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+		}
+	}
+	if (lane == 0)
+		asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory must outlive the stores that read it
+	__syncwarp();
+}
+
+// 3-D tensor map of a planar int32 pyramid [C][H][W] with boxes of one cell: 32 x 32 x C, 128-byte swizzle
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+	static const EncodeTiledFn fn = [] {
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+			cudaGetLastError();
+			p = nullptr;
+		}
+		return reinterpret_cast<EncodeTiledFn>(p);
+	}();
+	return fn;
+}
+
+bool make_cell_map(CUtensorMap *map, const int *pyr, int W, int H, int C, long long chan_stride, int pitch)
+{
+	const EncodeTiledFn fn = encode_tiled_fn();
+	if (!fn || (pitch & 3) || (chan_stride & 3) || (reinterpret_cast<uintptr_t>(pyr) & 15) || W < 32 || H < 32)
+		return false;
+	const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C};
+	const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)chan_stride * 4};
+	const cuuint32_t box[3] = {32, 32, (cuuint32_t)C}, estr[3] = {1, 1, 1};
+	return fn(map, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, const_cast<int *>(pyr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool tma_wanted()
+{
+	const char *v = getenv("DWT_HILBERT"); // A/B and test aid: "ballot" sends full cells through the ballot kernels
+	return !(v && !strcmp(v, "ballot"));
+}
+
+bool planes_fit_tma(const Geom &g, const Sched &s)
+{
+	for (int c = 0; c < g.channels; ++c)
+		if (s.planes[c] > BITSLICE_MAX_PLANES)
+			return false;
+	return g.channels == 1 || g.channels == 3;
+}
+
+int tma_grid(int nlist)
+{
+	const int want = (nlist + TMA_WARPS - 1) / TMA_WARPS;
+	const int cap = dwt_device_sms() * 2; // two CTAs of ~105 KB fit an SM
+	return want < cap ? want : cap;
+}
+
+int rec_grid(int nlist)
+{
+	const int want = (nlist + REC_WARPS - 1) / REC_WARPS;
+	const int cap = dwt_device_sms() * 2;
+	return want < cap ? want : cap;
+}
+
+template <typename K>
+int tma_configure(K kernel, size_t bytes)
+{
+	CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+	return 0;
+}
+
 __global__ void unslice_kernel(Geom G, ChanLayout lay, const u32 *bs, int *planar, long long total)
 {
 	long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; // index inside the detail range
@@ -527,12 +875,33 @@ int hilbert_plan_build(const Geom &g, HilbertPlan *plan, cudaStream_t st, long l
 	}
 	plan->full_off[g.levels] = (int)h_full.size();
 	plan->part_off[g.levels] = (int)h_part.size();
-	const size_t words = 2 * ntot + h_full.size() + h_part.size() + 4;
+	// word offsets of the curve inside a TMA-staged cell, per orientation: entry [o][i][k] belongs to curve index 32 k + i;
+	// the box arrives with the 128-byte swizzle (16-byte chunk index XOR row mod 8)
+	std::vector<unsigned short> h_lut(4096);
+	for (u32 o = 0; o < 4; ++o)
+		for (int d = 0; d < 1024; ++d) {
+			int x, y;
+			hilbert_d2xy(32, (u32)d, x, y);
+			if (o & 1u) {
+				const int t = x;
+				x = y;
+				y = t;
+			}
+			if (o & 2u) {
+				x = 31 - x;
+				y = 31 - y;
+			}
+			const int off = y * 32 + ((((x >> 2) ^ (y & 7)) << 2) | (x & 3));
+			h_lut[o * 1024 + (d & 31) * 32 + (d >> 5)] = (unsigned short)off;
+		}
+	const size_t words = 2 * ntot + h_full.size() + h_part.size() + 4 + 2048;
 	plan->cell_base = nullptr;
 	CUDA_OK(cudaMalloc(&plan->cell_base, sizeof(u32) * words));
 	plan->cell_info = plan->cell_base + ntot;
 	plan->full_list = plan->cell_info + ntot;
 	plan->part_list = plan->full_list + h_full.size();
+	plan->tile_lut = reinterpret_cast<unsigned short *>(plan->part_list + h_part.size() + ((h_full.size() + h_part.size()) & 1) + 2);
+	CUDA_OK(cudaMemcpyAsync(plan->tile_lut, h_lut.data(), sizeof(unsigned short) * 4096, cudaMemcpyHostToDevice, st));
 	CUDA_OK(cudaMemcpyAsync(plan->cell_base, h_base.data(), sizeof(u32) * ntot, cudaMemcpyHostToDevice, st));
 	CUDA_OK(cudaMemcpyAsync(plan->cell_info, h_info.data(), sizeof(u32) * ntot, cudaMemcpyHostToDevice, st));
 	if (!h_full.empty())
@@ -565,7 +934,24 @@ int hilbert_linearize(const Geom &g, const HilbertPlan &plan, const Sched &s, co
 	const bool fast = planes_fit(g, s);
 	// lists are ordered by level: the first levels_used levels are a prefix
 	const int nfull = plan.full_off[levels_used], npart = plan.part_off[levels_used];
-	if (fast && nfull > 0) {
+	CUtensorMap tmap;
+	if (nfull > 0 && tma_wanted() && planes_fit_tma(g, s) &&
+	    make_cell_map(&tmap, pyr, g.w[g.levels], g.h[g.levels], g.channels, pyr_chan_stride, pyr_pitch)) {
+		// full cells through the tensor memory accelerator (see the TMA section above)
+		if (g.channels == 3) {
+			if (tma_configure(linearize_tma_kernel<3>, tma_smem_bytes<3>()))
+				return -1;
+			linearize_tma_kernel<3><<<tma_grid(nfull), TMA_WARPS * 32, tma_smem_bytes<3>(), st>>>(tmap, P, plan.full_list, nfull,
+			                                                                                   plan.tile_lut, bs);
+		} else {
+			if (tma_configure(linearize_tma_kernel<1>, tma_smem_bytes<1>()))
+				return -1;
+			linearize_tma_kernel<1><<<tma_grid(nfull), TMA_WARPS * 32, tma_smem_bytes<1>(), st>>>(tmap, P, plan.full_list, nfull,
+			                                                                                   plan.tile_lut, bs);
+		}
+		if (launches)
+			++*launches;
+	} else if (fast && nfull > 0) {
 		int np = 1;
 		for (int c = 0; c < g.channels; ++c)
 			if (s.planes[c] > np)
@@ -603,7 +989,25 @@ int hilbert_reconstruct(const Geom &g, const HilbertPlan &plan, const Sched &s, 
 	const HParams P = make_params(g, plan, s);
 	const bool fast = planes_fit(g, s);
 	const int nfull = plan.full_off[levels_used], npart = plan.part_off[levels_used];
-	if (fast && nfull > 0) {
+	CUtensorMap tmap;
+	if (nfull > 0 && tma_wanted() && planes_fit_tma(g, s) &&
+	    make_cell_map(&tmap, pyr, g.w[levels_used], g.h[levels_used], g.channels, pyr_chan_stride, pyr_pitch)) {
+		if (g.channels == 3) {
+			if (tma_configure(reconstruct_tma_kernel<3>, rec_smem_bytes<3>()))
+				return -1;
+			reconstruct_tma_kernel<3><<<rec_grid(nfull), REC_WARPS * 32, rec_smem_bytes<3>(), st>>>(tmap, P, plan.full_list, nfull,
+			                                                                                     plan.tile_lut, bs, missing_dev,
+			                                                                                     levels_used);
+		} else {
+			if (tma_configure(reconstruct_tma_kernel<1>, rec_smem_bytes<1>()))
+				return -1;
+			reconstruct_tma_kernel<1><<<rec_grid(nfull), REC_WARPS * 32, rec_smem_bytes<1>(), st>>>(tmap, P, plan.full_list, nfull,
+			                                                                                     plan.tile_lut, bs, missing_dev,
+			                                                                                     levels_used);
+		}
+		if (launches)
+			++*launches;
+	} else if (fast && nfull > 0) {
 		int np = 1;
 		for (int c = 0; c < g.channels; ++c)
 			if (s.planes[c] > np)

@@ -18,9 +18,11 @@ struct HilbertPlan {
 	int ncell[DWT_MAX_LEVELS];
 	int cs[DWT_MAX_LEVELS];
 	int full_off[DWT_MAX_LEVELS + 1], part_off[DWT_MAX_LEVELS + 1]; // list ranges per level
-	u32 *cell_base; // device (one allocation holds all four arrays)
+	u32 *cell_base; // device (one allocation holds all the arrays)
 	u32 *cell_info;
 	u32 *full_list, *part_list;
+	unsigned short *tile_lut; // 4 orientations x 1024: word offset of curve index 32 k + i inside a TMA-staged (128-byte
+	                          // swizzled) 32 x 32 cell, stored at [orientation][i][k] (hilbert.cu: the TMA kernels)
 };
 
 int hilbert_plan_build(const Geom &g, HilbertPlan *plan, cudaStream_t st, long long *launches);

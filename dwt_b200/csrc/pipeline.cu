@@ -135,7 +135,7 @@ extern "C" dwt_ctx *dwt_ctx_create(int device)
 cudaError_t ctx_stream_sync(dwt_ctx *c)
 {
 	static const int forced = !getenv("DWT_SYNC") ? 0 : (!strcmp(getenv("DWT_SYNC"), "spin") ? 1 : (!strcmp(getenv("DWT_SYNC"), "block") ? 2 : 0));
-	static const long spin_us = getenv("DWT_SPIN_US") ? atol(getenv("DWT_SPIN_US")) : 20;
+	static const long spin_us = getenv("DWT_SPIN_US") ? atol(getenv("DWT_SPIN_US")) : 100;
 	const bool sleepy = forced ? forced == 2 : c->sleepy_wait;
 	if (!sleepy || !c->sync_ev)
 		return cudaStreamSynchronize(c->st);

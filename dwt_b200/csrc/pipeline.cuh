@@ -93,9 +93,10 @@ struct XferGate {
 // kernels, so that the copies queued behind them in the chain are not held up by this context's compute.
 cudaError_t ctx_copy(dwt_ctx *c, void *dst, const void *src, size_t n, cudaMemcpyKind kind, bool wait);
 // wait for the context's stream.  A lone context spins in cudaStreamSynchronize: a frame has three such waits and a
-// sleeping thread wakes up 100-300 us late (measured: 6.8 -> 10.1 ms per 8K round trip).  The contexts of a pool poll an
-// event for ~20 us and then sleep in cudaEventSynchronize (cudaEventBlockingSync): a pool has more waiting threads than a
-// GPU box has cores per GPU, and the other contexts keep the GPU busy meanwhile (measured: +4 % end to end at N = 1).
+// sleeping thread wakes up 100-300 us late (measured: 6.8 -> 10.1 ms per 8K round trip).  The contexts of a pool with more workers
+// than this GPU's share of the box's cores poll an event for ~100 us and then sleep in cudaEventSynchronize
+// (cudaEventBlockingSync); the other contexts keep the GPU busy meanwhile.  (Sleeping always was measured too: +3 % end
+// to end on 8K frames, -15 % on batches of 1080p images whose waits are short, at 24 cores for one GPU.)
 // DWT_SYNC=spin / block forces one behaviour, DWT_SPIN_US sets the poll time.
 cudaError_t ctx_stream_sync(dwt_ctx *c);
 int ctx_upload_stream(dwt_ctx *c, const uint8_t *stream, size_t len, bool wait);

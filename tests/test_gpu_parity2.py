@@ -208,3 +208,29 @@ def test_multi_device_pool_and_batch_cli(oracle, tmp_path):
     assert r.returncode == 0, r.stderr
     for i, im in enumerate(imgs):
         assert (dec_dir / ("im%02d.pnm" % i)).read_bytes() == oracle.pnm_bytes(im)
+
+
+def test_hilbert_ballot_and_tma_paths_agree(codec, oracle):
+    """full 32x32 cells go through the TMA-staged kernels when rows are 16-byte aligned (width % 4 == 0) and through the ballot
+    kernels otherwise (or with DWT_HILBERT=ballot): both against the oracle, on aligned and unaligned widths, colour and gray"""
+    cases = [oracle.synth(640, 360, "photo", 3), oracle.synth(642, 361, "photo", 4), oracle.synth(1024, 1024, "noise", 5),
+             oracle.synth(516, 300, "photo", 6)[:, :, 1].copy(), oracle.synth(1001, 777, "photo", 13)]
+    want = [oracle.encode(im)[0] for im in cases]
+    old = os.environ.get("DWT_HILBERT")
+    try:
+        for mode in ("tma", "ballot"):
+            os.environ["DWT_HILBERT"] = mode
+            for im, w in zip(cases, want):
+                assert codec.encode(im) == w, (mode, im.shape)
+                assert np.array_equal(codec.decode(w), im), (mode, im.shape)
+                cut = w[: len(w) // 2]
+                a, b = codec.decode(cut), oracle.decode(cut)
+                assert a.shape == b.shape and np.array_equal(a, b), (mode, im.shape)
+                pyr, lin, planes = codec.front_end(im)
+                wpyr, wlin, wplanes = oracle.front_end(im)
+                assert np.array_equal(lin, wlin) and planes == wplanes, (mode, im.shape)
+    finally:
+        if old is None:
+            os.environ.pop("DWT_HILBERT", None)
+        else:
+            os.environ["DWT_HILBERT"] = old
