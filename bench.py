@@ -236,6 +236,32 @@ def reduce_max(values, device):
     return [float(v) for v in t]
 
 
+def staging_ceiling(device, barrier, seconds=0.4):
+    """host <-> device staging rate of this rank with every rank copying at the same time: pure cudaMemcpyAsync from / to
+    page-locked memory, both directions at once (what the end-to-end pass does), GB/s per direction"""
+    import torch
+    n = 1 << 28
+    h1 = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h2 = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d1 = torch.empty(n, dtype=torch.uint8, device=device)
+    d2 = torch.empty(n, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+
+    def run(reps):
+        torch.cuda.synchronize(device)
+        barrier()
+        t = time.perf_counter()
+        for _ in range(reps):
+            with torch.cuda.stream(s1):
+                d1.copy_(h1, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h2.copy_(d2, non_blocking=True)
+        torch.cuda.synchronize(device)
+        return reps * n / (time.perf_counter() - t) / 1e9
+    run(1)
+    return run(max(2, int(seconds * 25e9 / n)))
+
+
 def batch_seeds(rank, distinct):
     """BASELINE config 4: image i of the batch has seed i (0..4095); rank r owns the seeds r*512 .. r*512+511"""
     return [rank * 512 + i for i in range(distinct)]
@@ -553,6 +579,8 @@ def our_bench(args, rank, world, local):
     assert np.array_equal(jobs[4][-1], pin_img[(jobs[0] - 1) % F].reshape(-1)), "end-to-end round trip is not lossless"
     assert bytes(jobs[3][0][:stream_bytes]) == bytes(pin_out[0][:stream_bytes]), "end-to-end stream differs from the gate's"
     dpool.close()
+    # what the box's host <-> device path can carry with every rank copying at once (the end-to-end number's ceiling)
+    ceiling = staging_ceiling(torch.device("cuda", local), barrier)
     # the page-locked job buffers of the passes above (~8 GB) go back before the batch config takes its own
     del jobs, warm_jobs, pin_img, pin_out, pin_dec
     keep.clear()
@@ -580,6 +608,7 @@ def our_bench(args, rank, world, local):
         if batch:
             t_enc, t_dec = reduce_max(batch[:2], torch.device("cuda", local))
             batch = (t_enc, t_dec, batch[2])
+        ceiling = -reduce_max([-ceiling], torch.device("cuda", local))[0] * world   # slowest rank x ranks
     if rank != 0:
         if use_dist:
             dist.destroy_process_group()
@@ -650,6 +679,11 @@ def our_bench(args, rank, world, local):
                            parallelism="one frame stream per GPU, no collective; the %d frames of a step are coded concurrently "
                                        "on %d contexts (one CUDA stream and one host thread each)" % (F, F)),
                e2e=dict(value=round(e2e_value, 2), unit="Mpixel/s", ms_per_step=round(e2e_total / args.steps, 3),
+                        staging_gbs_per_direction=round(world * F * (img.size + stream_bytes) / (e2e_total / args.steps / 1e3) / 1e9, 1),
+                        staging_ceiling_gbs_per_direction=round(ceiling, 1),
+                        fraction_of_staging_ceiling=round(world * F * (img.size + stream_bytes) / (e2e_total / args.steps / 1e3) / 1e9 / ceiling, 3),
+                        staging_note="ceiling = pure cudaMemcpyAsync from / to page-locked memory, both directions at once on every rank "
+                                     "at the same time (slowest rank x ranks), measured in this run",
                         h2d_bytes_per_step=int(world * F * (img.size + stream_bytes)),
                         d2h_bytes_per_step=int(world * F * (stream_bytes + img.size)),
                         api="dwt_pool_run: dwt_encode_into of %d frames + dwt_decode_into of %d streams per step, interleaved on %d contexts, "

@@ -369,7 +369,7 @@ __device__ __forceinline__ bool next_item(const LiftLevel &p, const LiftSched &q
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 5) lift_fwd_kernel(const __grid_constant__ LiftLevel p,
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MODE == 2 ? 6 : 5) lift_fwd_kernel(const __grid_constant__ LiftLevel p,
                                                                             const __grid_constant__ LiftSched q)
 {
 	const int lane = threadIdx.x & 31;
