@@ -404,11 +404,23 @@ extern "C" const char *dwt_pool_last_error(const dwt_pool *p)
 
 // How many contexts the caller keeps busy on this device at the same time (default 1).  With several frames in flight the
 // library prefers kernels that do less total work over kernels that finish one frame sooner (decoder scan).
+// this GPU's share of the box's cores: more waiting threads than that should sleep, not spin (ctx_stream_sync)
+static bool oversubscribed(int threads_on_this_gpu)
+{
+	int count = 1;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1)
+		count = 1;
+	cpu_set_t cpus;
+	const int ncpu = sched_getaffinity(0, sizeof(cpus), &cpus) == 0 ? CPU_COUNT(&cpus) : 1;
+	return threads_on_this_gpu > 1 && threads_on_this_gpu > ncpu / count;
+}
+
 extern "C" int dwt_ctx_set_in_flight(dwt_ctx *c, int contexts)
 {
 	if (!c || contexts < 1)
 		return -1;
 	c->in_flight = contexts;
+	c->sleepy_wait = oversubscribed(contexts);
 	return 0;
 }
 
@@ -431,10 +443,7 @@ extern "C" dwt_pool *dwt_pool_create_multi(const int *devices, int n_devices, in
 	}
 	dwt_pool *p = new dwt_pool();
 	p->workers = workers;
-	// more waiting threads than cores for this GPU's share of the box: let them sleep instead of spin (ctx_stream_sync)
-	cpu_set_t cpus;
-	const int ncpu = sched_getaffinity(0, sizeof(cpus), &cpus) == 0 ? CPU_COUNT(&cpus) : 1;
-	const bool sleepy = workers > 1 && workers > ncpu / count;
+	const bool sleepy = oversubscribed(workers);
 	if (!devices || n_devices <= 0) { // every visible device
 		for (int d = 0; d < count; ++d)
 			p->devices.push_back(d);

@@ -636,48 +636,78 @@ __global__ void __launch_bounds__(128) dec_link_kernel(const u32 *__restrict__ s
 // tokens that start in the slice (a, b) from offset d with order k, against the member budget T.
 // Returns EV_NONE when the slice is left (d >= 64 then), otherwise the event that ends the pass.
 // lut: order-0 token table in shared memory (the resolver runs in one warp, so table and generic steps never diverge)
-__device__ __forceinline__ int walk_events(const u32 *lut, u64 a, u64 b, int avail, u64 T, int &d, int &k, u64 &cum, u32 &ones,
-                                           u32 &ev_pending)
+// 32 stream bits from offset `off` (0 .. 95) of the 128-bit pair (a, b)
+__device__ __forceinline__ u32 window_at(u64 a, u64 b, int off)
 {
-	const bool lut_ok = avail >= 64 + LUT_BITS + 4;
+	const u32 w0 = (u32)a, w1 = (u32)(a >> 32), w2 = (u32)b, w3 = (u32)(b >> 32);
+	const int i = off >> 5;
+	const u32 lo = i == 0 ? w0 : (i == 1 ? w1 : w2);
+	const u32 hi = i == 0 ? w1 : (i == 1 ? w2 : w3);
+	return __funnelshift_r(lo, hi, off & 31);
+}
+
+// The resolver's exact walk is one dependent chain per token, so what counts is the length of that chain: all state is
+// 32 bit (a chunk has fewer than 2^31 members, a run is below 2^32), the payload comes from a second 32-bit window instead
+// of 64-bit shifts, and the end-of-stream checks live in a separate variant that only runs within three slices of EOF.
+template <bool CHECKED>
+__device__ __forceinline__ int walk_events_t(const u32 *lut, u64 a, u64 b, int avail, u32 T, int &d, int &k, u32 &cum, u32 &ones,
+                                             u32 &ev_pending)
+{
+	const bool lut_ok = !CHECKED || avail >= 64 + LUT_BITS + 4;
 	for (;;) {
 		if (cum >= T)
 			return EV_COVERED; // every member has its symbol; the pass ends in front of the token at d
 		if (d >= 64)
 			return EV_NONE;
+		const u32 bits = window32(a, b, d);
 		if (k == 0 && lut_ok) { // several short tokens at once, as long as the pass cannot end inside them
-			const u32 t = lut[window32(a, b, d) & ((1u << LUT_BITS) - 1u)];
+			const u32 t = lut[bits & ((1u << LUT_BITS) - 1u)];
 			const u32 mem = t >> 11;
-			if ((t & 15u) && d + (int)((t >> 4) & 15u) < 64 && cum + mem < T) {
+			if ((t & 15u) && d + (int)((t >> 4) & 15u) < 64 && mem < T - cum) {
 				d += (int)(t & 15u);
 				ones += (t >> 8) & 7u;
 				cum += mem;
 				continue;
 			}
 		}
-		const u64 w = bits_from(a, b, d);
-		const u32 lo = (u32)w;
-		const int u = lo ? __ffs((int)lo) - 1 : 32;
+		const int u = bits ? __ffs((int)bits) - 1 : 32;
 		const int e = k + u;
 		const int L = u + 1 + e;
-		if (e > 31 || d + L > avail)
+		if (e > 31 || (CHECKED && d + L > avail))
 			return EV_STOP; // the token cannot be read completely (vli.h:88-95): decoding ends
-		const u32 payload = (u32)(w >> (u + 1)) & ((1u << e) - 1u);
-		const u64 n = (u64)((1u << e) - (1u << k)) + payload;
+		const u32 payload = window_at(a, b, d + u + 1) & ((1u << e) - 1u);
+		const u32 n = (1u << e) - (1u << k) + payload;
 		const int kn = e >= 2 ? e - 2 : 0;
-		if (cum + n >= T) { // the run reaches past this chunk's members (rle.h:74-76)
-			ev_pending = (u32)(n - (T - cum) + 1);
+		const u32 room = T - cum;
+		if (n >= room) { // the run reaches past this chunk's members (rle.h:74-76)
+			ev_pending = n - room + 1;
 			d += L;
 			k = kn;
 			return EV_PENDING;
 		}
 		++ones;
-		if (d + L + 1 > avail)
+		if (CHECKED && d + L + 1 > avail)
 			return EV_STOP; // sign bit beyond EOF: the magnitude bit stays (decode.c:80-86)
 		cum += n + 1;
 		d += L + 1;
 		k = kn;
 	}
+}
+
+// tokens that start in the slice (a, b) from offset d with order k, against the member budget T (cum < T on entry).
+// Returns EV_NONE when the slice is left (d >= 64 then), otherwise the event that ends the pass.
+// lut: order-0 token table in shared memory (the resolver runs in one warp, so table and generic steps never diverge)
+__device__ __forceinline__ int walk_events(const u32 *lut, u64 a, u64 b, int avail, u64 T64, int &d, int &k, u64 &cum64, u32 &ones,
+                                           u32 &ev_pending)
+{
+	if (cum64 >= T64)
+		return EV_COVERED;
+	const u32 T = (u32)T64; // T <= 2^31 (a level has fewer than 2^31 coefficients), cum < T
+	u32 cum = (u32)cum64;
+	const int r = avail >= 192 ? walk_events_t<false>(lut, a, b, avail, T, d, k, cum, ones, ev_pending)
+	                           : walk_events_t<true>(lut, a, b, avail, T, d, k, cum, ones, ev_pending);
+	cum64 = cum;
+	return r;
 }
 
 __device__ __forceinline__ u32 map_compose(u32 first, u32 second) // class maps: 2 bits per entry class 0 / 1
@@ -1731,11 +1761,11 @@ void dec_token_table(u32 *host_table)
 }
 
 // Lineage passes cost the latency of one lone window walk each (~0.18 ms) whatever the stream size, and save exact resolver
-// steps in proportion to the stream's slow-to-synchronise regions.  Measured (single frame, coder stage): 8K photo
-// 5.50 / 4.75 / 4.29 / 3.92 / 3.63 ms for 0 / 1 / 2 / 3 / 5 passes, 4K photo 1.85 / 1.96 / 2.12 / 2.14 ms for 0 / 1 / 2 / 3.
+// steps in proportion to the stream's slow-to-synchronise regions.  Measured (single frame, coder stage, B200): 8K photo
+// 5.02 / 4.44 / 4.05 / 3.77 / 3.55 / 3.74 ms for 0 / 1 / 2 / 3 / 5 / 8 passes, 4K photo 1.80 / 1.93 / 2.07 ms for 0 / 1 / 2.
 static int lineage_passes(u32 nwin)
 {
-	return nwin >= 32768u ? 3 : (nwin >= 20000u ? 1 : 0);
+	return nwin >= 32768u ? 5 : (nwin >= 20000u ? 1 : 0);
 }
 
 int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b_in, int nchunks, cudaStream_t st, long long *launches)
