@@ -20,7 +20,8 @@ struct EncInfo {                           // read back by the host
 	u64 total_bits;                        // header + prefix + payload, before padding
 	u32 opaque_tiles;
 	int error;
-	int jcut;                              // chunks j >= jcut certainly start behind the capacity: they are not coded at all
+	int jcut;                              // chunks j > jcut certainly start behind the capacity, and so do the tiles >= icut of
+	int icut;                              // chunk jcut: they are not coded at all (jcut == nchunks: nothing is cut)
 	u32 ref_cut;                           // refinement bits of the chunks < jcut (= tot_ref when nothing was cut)
 };
 
@@ -45,11 +46,14 @@ struct EncBuffers {
 };
 
 int enc_count(const Geom &g, const Sched &hs, const EncBuffers &b, cudaStream_t st, long long *launches);
-// prefix_bits: bits of header + root image + plane counts; limit_bits: 8 * capacity, 0 = unlimited.  Chunks whose first
-// bit provably lies behind limit_bits (lower bound: 2 bits per one, 1 per refinement bit) are dropped from the rest of
-// the pipeline -- the reference stops coding at the cap as well (encode.c:193,205,217 `goto end`, bytes.h:77-78)
+// prefix_bits: bits of header + root image + plane counts; limit_bits: 8 * capacity, 0 = unlimited.  Work whose first bit
+// provably lies behind limit_bits (lower bound: 2 bits per one, 1 per refinement bit; granularity: a tile of 256 groups of
+// a chunk) is dropped from the rest of the pipeline -- the reference stops coding at the cap as well (encode.c:193,205,217
+// `goto end`, bytes.h:77-78).  enc_token_bound / enc_ref_bound say how many tokens / refinement bits can survive the cut.
 int enc_scan_and_setup(const Geom &g, const Sched &hs, const EncBuffers &b, u64 prefix_bits, u64 limit_bits, cudaStream_t st,
                        long long *launches);
+u64 enc_token_bound(const Geom &g, const Sched &hs, u64 prefix_bits, u64 limit_bits);
+u64 enc_ref_bound(const Geom &g, const Sched &hs, u64 prefix_bits, u64 limit_bits);
 int enc_emit(const Geom &g, const Sched &hs, const EncBuffers &b, cudaStream_t st, long long *launches);
 // VLI order resolution + token bit lengths; k0 = order after the host-coded prefix
 int enc_vli_orders(const EncBuffers &b, int k0, cudaStream_t st, long long *launches);

@@ -161,28 +161,58 @@ __global__ void __launch_bounds__(1024) enc_scan_fix_kernel(u32 *ez, u32 *e1, u3
 constexpr u64 CUT_SLACK_BITS = 64;
 
 __global__ void __launch_bounds__(1024) enc_chunk_setup_kernel(const Sched *__restrict__ S, const u32 *ez, const u32 *e1,
-                                                                const u32 *er, EncChunks *C, EncInfo *info, u32 *Z,
+                                                                const u32 *er, int nent, EncChunks *C, EncInfo *info, u32 *Z,
                                                                 u32 *specbuf, u32 max_tokens, u64 prefix_bits, u64 limit_bits)
 {
 	__shared__ u64 ws[32];
-	__shared__ int s_jcut;
+	__shared__ int s_jcut, s_icut, s_ecut;
 	const int J = S->nchunks;
 	const int per = (J + 1 + 1023) / 1024;
 	const int b = threadIdx.x * per, e = min(b + per, J);
 	const u32 tz = (u32)info->tot_zero, t1 = (u32)info->tot_one, tr = (u32)info->tot_ref;
-	if (threadIdx.x == 0)
-		s_jcut = J;
-	__syncthreads();
-	// capacity cut: a one costs at least 2 bits (VLI >= 1 bit, sign), a refinement bit 1 -- the first chunk whose lower
-	// bound lies behind the capacity, and every chunk after it, cannot reach the output (bytes.h:77-78)
-	if (limit_bits) {
-		for (int j = b; j < e; ++j) {
-			const u64 lb = prefix_bits + 2ull * e1[S->ebase[j]] + er[S->ebase[j]];
-			if (lb >= limit_bits + CUT_SLACK_BITS) {
-				atomicMin(&s_jcut, j);
-				break;
+	if (threadIdx.x == 0) {
+		// capacity cut: a one costs at least 2 bits (VLI >= 1 bit, sign), a refinement bit 1, and the refinement block of a
+		// chunk lies behind all of its tokens -- so the first token of tile i of chunk j cannot start in front of
+		//     prefix + 2 * (ones in front of it) + (refinement bits of the chunks in front of j).
+		// The first (chunk, tile) entry whose bound lies behind the capacity, and everything after it, cannot reach the
+		// output (bytes.h:77-78).  The bound is non-decreasing along the entries: binary search, chunks first, then tiles.
+		const u64 L = limit_bits + CUT_SLACK_BITS;
+		int jc = J, ic = 0, lo = nent;
+		if (limit_bits) {
+			int a = 0, z = J; // first chunk whose first entry is bounded behind L (J: none)
+			while (a < z) {
+				const int mid = (a + z) >> 1;
+				const int em = S->ebase[mid];
+				if (prefix_bits + 2ull * e1[em] + er[em] >= L)
+					z = mid;
+				else
+					a = mid + 1;
+			}
+			const int jhi = a;
+			jc = jhi;
+			ic = 0;
+			lo = jhi < J ? S->ebase[jhi] : nent;
+			if (jhi > 0) { // the cut may fall inside the last chunk that starts in front of L
+				const int jp = jhi - 1, e0 = S->ebase[jp], en = S->ebase[jp + 1];
+				const u64 base = prefix_bits + er[e0];
+				int x = e0, y = en; // first entry of chunk jp bounded behind L (en: none)
+				while (x < y) {
+					const int mid = (x + y) >> 1;
+					if (base + 2ull * e1[mid] >= L)
+						y = mid;
+					else
+						x = mid + 1;
+				}
+				if (x < en) {
+					jc = jp;
+					ic = x - e0;
+					lo = x;
+				}
 			}
 		}
+		s_jcut = jc;
+		s_icut = ic;
+		s_ecut = lo;
 	}
 	u64 nf = 0;
 	for (int j = b; j < e; ++j) {
@@ -190,7 +220,7 @@ __global__ void __launch_bounds__(1024) enc_chunk_setup_kernel(const Sched *__re
 		nf += (r1 != r0);
 	}
 	u64 tot;
-	u64 F = block_exscan_u64(nf, ws, &tot); // syncs: s_jcut is final behind it
+	u64 F = block_exscan_u64(nf, ws, &tot); // syncs: the cut is known behind it
 	const int jcut = s_jcut;
 	for (int j = b; j < e; ++j) {
 		const int e0 = S->ebase[j];
@@ -211,7 +241,7 @@ __global__ void __launch_bounds__(1024) enc_chunk_setup_kernel(const Sched *__re
 			++F;
 		}
 	}
-	__syncthreads(); // tok_start / ref_start of chunk jcut (written by its owner) are read by thread 0
+	__syncthreads(); // tok_adj / ref_start of chunk jcut (written by its owner) are read by thread 0
 	if (threadIdx.x == 0) {
 		u32 tf = t1 + (u32)tot; // final rle_flush token (rle.h:37-40)
 		u32 zf = tz;
@@ -219,12 +249,14 @@ __global__ void __launch_bounds__(1024) enc_chunk_setup_kernel(const Sched *__re
 		C->tok_adj[J] = (u32)tot;
 		C->ref_start[J] = tr;
 		info->jcut = jcut;
+		info->icut = s_icut;
 		info->ref_cut = tr;
 		if (jcut < J) {
-			// the token list ends in front of chunk jcut; its last entry stands for "whatever follows": it is placed
-			// behind the capacity, so its bits never reach the output (enc_scatter clips at the capacity)
-			tf = C->tok_start[jcut];
-			zf = ez[S->ebase[jcut]];
+			// the token list ends in front of tile icut of chunk jcut; its last entry stands for "whatever follows": it is
+			// placed behind the capacity, so its bits never reach the output (enc_scatter clips at the capacity).  The
+			// refinement block of chunk jcut lies behind all of its tokens, hence behind the capacity as well.
+			tf = e1[s_ecut] + C->tok_adj[jcut];
+			zf = ez[s_ecut];
 			info->ref_cut = C->ref_start[jcut];
 		}
 		Z[0] = 0;
@@ -251,9 +283,15 @@ __global__ void __launch_bounds__(TG) enc_emit_kernel(const __grid_constant__ Ge
 	int c, l, i;
 	tile_coords(G, blockIdx.x, c, l, i);
 	const int P = S->planes[c];
-	const int jcut = info->jcut; // chunks from here on lie behind the capacity (enc_chunk_setup_kernel)
-	if (P == 0 || S->chunk_of[c][l][P - 1] >= jcut)
-		return; // the planes of a (channel, level) are coded top down: nothing of this tile is needed
+	// chunks behind jcut, and the tiles from icut on of chunk jcut, lie behind the capacity (enc_chunk_setup_kernel)
+	const int jcut = info->jcut, icut = info->icut;
+	if (P == 0)
+		return;
+	{
+		const int jtop = S->chunk_of[c][l][P - 1];
+		if (jtop > jcut || (jtop == jcut && i >= icut))
+			return; // the planes of a (channel, level) are coded top down: nothing of this tile is needed
+	}
 	const int g = i * TG + threadIdx.x;
 	const u32 vm = group_valid_mask(G, l, g);
 	const u32 *base = bs + S->bsbase[c] + G.gbase[l] + g;
@@ -265,7 +303,7 @@ __global__ void __launch_bounds__(TG) enc_emit_kernel(const __grid_constant__ Ge
 		u32 ones = B & member, zeros = member & ~B;
 		u32 n1 = __popc(ones), nz = __popc(zeros), nr = __popc(sig);
 		const int j = S->chunk_of[c][l][p];
-		if (j >= jcut)
+		if (j > jcut || (j == jcut && i >= icut))
 			break; // block-uniform: this plane and the ones below it are cut
 		u64 packed = (u64)nz | ((u64)n1 << 21) | ((u64)nr << 42), tot;
 		u64 ex = block_exscan_u64(packed, ws, &tot);
@@ -285,7 +323,7 @@ __global__ void __launch_bounds__(TG) enc_emit_kernel(const __grid_constant__ Ge
 			}
 			bits_or(signbuf, tb, sb, (int)n1);
 		}
-		if (nr) {
+		if (nr && j < jcut) { // the refinement block of chunk jcut lies behind all of its tokens: behind the cut
 			u32 rb = er[e] + (u32)(ex >> 42);
 			bits_or(refbuf, rb, bit_compress(B, sig), (int)nr);
 		}
@@ -649,11 +687,37 @@ int enc_scan_and_setup(const Geom &g, const Sched &hs, const EncBuffers &b, u64 
 	enc_scan_local_kernel<<<nb, 1024, 0, st>>>(b.ent_z, b.ent_1, b.ent_r, b.nent, bsum);
 	enc_scan_fix_kernel<<<nb, 1024, 0, st>>>(b.ent_z, b.ent_1, b.ent_r, b.nent, bsum, b.info);
 	++*launches;
-	enc_chunk_setup_kernel<<<1, 1024, 0, st>>>(b.sched, b.ent_z, b.ent_1, b.ent_r, b.chunks, b.info, b.Z, b.specbuf,
+	enc_chunk_setup_kernel<<<1, 1024, 0, st>>>(b.sched, b.ent_z, b.ent_1, b.ent_r, b.nent, b.chunks, b.info, b.Z, b.specbuf,
 	                                           b.max_tokens, prefix_bits, limit_bits);
 	*launches += 2;
 	CUDA_OK(cudaGetLastError());
 	return 0;
+}
+
+// Tokens / refinement bits that can survive a capacity of limit_bits (0: no limit): every entry in front of the cut has
+// a lower bound below limit + slack, i.e. fewer than (limit + slack) / 2 ones and (limit + slack) refinement bits in front of
+// it; the entry itself adds at most a tile of ones, the flush candidates one token per chunk, and the refinement block of
+// the last whole chunk at most one level's worth of bits.
+u64 enc_token_bound(const Geom &g, const Sched &hs, u64 prefix_bits, u64 limit_bits)
+{
+	(void)g;
+	if (!limit_bits)
+		return ~0ull;
+	const u64 room = limit_bits + CUT_SLACK_BITS > prefix_bits ? limit_bits + CUT_SLACK_BITS - prefix_bits : 0;
+	return room / 2 + (u64)TG * 32 + (u64)hs.nchunks + 2;
+}
+
+u64 enc_ref_bound(const Geom &g, const Sched &hs, u64 prefix_bits, u64 limit_bits)
+{
+	(void)hs;
+	if (!limit_bits)
+		return ~0ull;
+	u64 biggest = 0;
+	for (int l = 0; l < g.levels; ++l)
+		if ((u64)g.num[l] > biggest)
+			biggest = (u64)g.num[l];
+	const u64 room = limit_bits + CUT_SLACK_BITS > prefix_bits ? limit_bits + CUT_SLACK_BITS - prefix_bits : 0;
+	return room + biggest + 64;
 }
 
 int enc_emit(const Geom &g, const Sched &hs, const EncBuffers &b, cudaStream_t st, long long *launches)

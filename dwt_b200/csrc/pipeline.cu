@@ -603,14 +603,19 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 		}
 		EncBuffers b;
 		memset(&b, 0, sizeof(b));
-		b.max_tokens = (u32)max_tok_ll;
+		// a capacity bounds how many tokens and refinement bits can reach the output (enc_chunk_setup_kernel cuts the rest):
+		// the buffers that are zeroed per frame and the token-tile grids are sized by what can survive
+		const u64 limit_bits = capacity > 0 ? 8ull * (u64)capacity : 0ull;
+		const u64 tok_cap = enc_token_bound(g, S, prefix_bits, limit_bits);
+		b.max_tokens = (u32)((u64)max_tok_ll < tok_cap ? (u64)max_tok_ll : tok_cap);
 		const size_t tok_room = round_up(b.max_tokens, DWT_TOK_TILE) + 32;
 		const size_t ntile_max = tok_room / DWT_TOK_TILE + 1;
 		b.nent = S.ebase[S.nchunks];
 		long long ref_bound = 0;
 		for (int ch = 0; ch < C; ++ch)
 			ref_bound += ndet * (planes[ch] > 1 ? planes[ch] - 1 : 0);
-		const size_t ref_words = (size_t)(ref_bound / 32) + 4;
+		const u64 ref_cap = enc_ref_bound(g, S, prefix_bits, limit_bits);
+		const size_t ref_words = (size_t)(((u64)ref_bound < ref_cap ? (u64)ref_bound : ref_cap) / 32) + 4;
 		const size_t bit_words = tok_room / 32 + 4;
 		if (c->ent.ensure((size_t)b.nent * 12 + 64 + (size_t)(b.nent / 4096 + 2) * 24) || // + block totals of the scan
 		    c->Z.ensure(tok_room * 4 + 64) ||
@@ -636,7 +641,6 @@ extern "C" int dwt_ctx_encode_resident(dwt_ctx *c, int capacity, struct dwt_stat
 		b.chunks = c->chunks.as<EncChunks>();
 		b.info = c->info.as<EncInfo>();
 		b.sched = c->dsched.as<Sched>();
-		const u64 limit_bits = capacity > 0 ? 8ull * (u64)capacity : 0ull;
 		if (enc_count(g, S, b, st, &c->launches) || enc_scan_and_setup(g, S, b, prefix_bits, limit_bits, st, &c->launches) ||
 		    enc_emit(g, S, b, st, &c->launches) || enc_vli_orders(b, k0, st, &c->launches))
 			return -1;
