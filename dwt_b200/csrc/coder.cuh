@@ -63,6 +63,7 @@ int enc_scatter(const Sched &hs, const EncBuffers &b, u64 prefix_bits, u64 tot_r
 // ---------------------------------------------------------------------------------------------- decoder
 
 #define DWT_DEC_WS 128            // stream slices (64 bits each) per scan window (1 KB of stream)
+#define DWT_DEC_MAX_LINEAGE 16    // lineage passes a decode can run
 #define DWT_DEC_SUPER 32          // windows per super-window (the resolver's second level)
 
 struct DecState {                 // device-resident cursor of the serial parse (decode.c:187-243); read back by the host
@@ -144,6 +145,8 @@ struct DecBuffers {
 	u32 *winX;            // per window: exit states of the two classes
 	u32 *winX2;           // second copy for the lineage passes (they read one and write the other)
 	unsigned char *chg;   // 2 * nwin flags: windows whose class-1 chain a lineage pass replaced
+	u32 *ext_count;       // DWT_DEC_MAX_LINEAGE counters (zeroed per decode): windows a lineage pass has to walk
+	uint2 *ext_list;      // nwin entries: (window, entry state) of those windows
 	ulonglong2 *winPT;    // per window: member totals
 	u32 *winTT;           // per window: token totals
 	DecLink *link;        // [window][class]

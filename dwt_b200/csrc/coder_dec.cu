@@ -34,6 +34,7 @@ constexpr int WS = DWT_DEC_WS;
 constexpr u32 PDEAD = 0xffffu;    // a chain that cannot continue (EOF inside a token, impossible order)
 constexpr int LINK_CAP = DWT_DEC_WS; // exact slice steps the link pass spends on one (window, chain): the whole window
 constexpr u32 LINK_OPEN = 0xfffeu;  // link record: the chain had not joined after LINK_CAP slices
+constexpr int EXACT_FIRST = 4;     // resolver: slices of a chunk start that are stepped with full bookkeeping before it changes gear
 constexpr u64 DEATH = 1ull << 48; // member count charged to a slice in which a canonical chain dies: more than any chunk holds
 
 enum { EV_NONE = 0, EV_COVERED = 1, EV_PENDING = 2, EV_STOP = 3 };
@@ -490,53 +491,99 @@ __global__ void __launch_bounds__(128) dec_scan_serial_kernel(const u32 *__restr
 // regions are left alone: there the continuation joins at once.
 constexpr int EXTEND_JOIN_SLICES = 6;
 
-__global__ void __launch_bounds__(128) dec_scan_extend_kernel(const u32 *__restrict__ stream, u64 end_bits,
-                                                               const u32 *__restrict__ toklut, u32 nwin, u32 *E, ulonglong2 *P,
-                                                               u32 *TK, const u32 *__restrict__ winX_in, u32 *winX_out,
-                                                               ulonglong2 *winPT, u32 *winTT, const unsigned char *changed_in,
-                                                               unsigned char *changed_out)
+// part 1, one thread per window: does the chain that leaves window w - 1 on class 1 fall onto one of w's chains within a
+// few slices?  If not, w goes on the list of windows whose class-1 chain is to be replaced by that continuation.
+__global__ void __launch_bounds__(128) dec_extend_find_kernel(const u32 *__restrict__ stream, u64 end_bits, u32 nwin,
+                                                               const u32 *__restrict__ E, const u32 *__restrict__ winX_in,
+                                                               u32 *winX_out, const unsigned char *changed_in,
+                                                               unsigned char *changed_out, u32 *list_count, uint2 *list)
+{
+	const u32 w = blockIdx.x * 128 + threadIdx.x;
+	if (w >= nwin)
+		return;
+	winX_out[w] = winX_in[w];
+	changed_out[w] = 0;
+	if (w < 1 || (changed_in && !changed_in[w - 1]))
+		return;
+	const u32 st = winX_in[w - 1] >> 16; // where the class-1 chain of the window in front ends
+	if (st == PDEAD)
+		return;
+	const u64 gs0 = (u64)w * WS;
+	u32 s = st;
+	for (int i = 0; i < EXTEND_JOIN_SLICES; ++i) { // no table: a handful of tokens
+		const u32 e = E[gs0 + i];
+		if (s == (e & 0xffffu) || s == (e >> 16))
+			return;
+		u64 a, b;
+		load_slice(stream, end_bits, gs0 + i, a, b);
+		s = slice_exit(a, b, clamp_avail(end_bits, (gs0 + i) << 6), s);
+		if (s == PDEAD)
+			return; // a chain that dies here is not worth keeping
+	}
+	list[atomicAdd(list_count, 1u)] = make_uint2(w, st);
+}
+
+// part 2, one CTA per listed window.  A lone thread that walks a window with full bookkeeping needs ~0.18 ms; here thread 0
+// only follows the token POSITIONS from slice to slice (a few instructions per token) and leaves every slice's entry state
+// in shared memory, then all 128 threads count what their slice consumes from its entry state, and a block scan turns the
+// counts into the chain's tables.  Same tables as walk_window_chain, a fraction of its latency.
+__global__ void __launch_bounds__(WS) dec_extend_walk_kernel(const u32 *__restrict__ stream, u64 end_bits,
+                                                              const u32 *__restrict__ toklut, u32 *E, ulonglong2 *P, u32 *TK,
+                                                              u32 *winX_out, ulonglong2 *winPT, u32 *winTT,
+                                                              unsigned char *changed_out, const u32 *__restrict__ list_count,
+                                                              const uint2 *__restrict__ list)
 {
 	__shared__ u32 lut[1 << LUT_BITS];
-	const u32 w = blockIdx.x * 128 + threadIdx.x;
-	bool replace = false;
-	u32 st = PDEAD;
-	if (w < nwin) {
-		const u32 xin = winX_in[w];
-		winX_out[w] = xin;
-		changed_out[w] = 0;
-		if (w >= 1 && (!changed_in || changed_in[w - 1])) {
-			st = winX_in[w - 1] >> 16; // where the class-1 chain of the window in front ends
-			if (st != PDEAD) {
-				// does it fall onto one of this window's chains within a few slices?  (no table: a handful of tokens)
-				const u64 gs0 = (u64)w * WS;
-				u32 s = st;
-				replace = true;
-				for (int i = 0; i < EXTEND_JOIN_SLICES; ++i) {
-					const u32 e = E[gs0 + i];
-					if (s == (e & 0xffffu) || s == (e >> 16)) {
-						replace = false;
-						break;
-					}
-					u64 a, b;
-					load_slice(stream, end_bits, gs0 + i, a, b);
-					s = slice_exit(a, b, clamp_avail(end_bits, (gs0 + i) << 6), s);
-					if (s == PDEAD) {
-						replace = false; // a chain that dies here is not worth keeping
-						break;
-					}
-				}
+	__shared__ u64 sw[WS + 1];
+	__shared__ unsigned short sentry[WS];
+	__shared__ u64 ws[32];
+	const u32 count = *list_count;
+	if (blockIdx.x >= count)
+		return;
+	const int tid = threadIdx.x;
+	for (int i = tid; i < (1 << LUT_BITS); i += WS)
+		lut[i] = __ldg(toklut + i);
+	unsigned short *E16 = reinterpret_cast<unsigned short *>(E), *TK16 = reinterpret_cast<unsigned short *>(TK);
+	u64 *P64 = reinterpret_cast<u64 *>(P);
+	for (u32 item = blockIdx.x; item < count; item += gridDim.x) {
+		const uint2 it = list[item];
+		const u32 w = it.x;
+		const u64 gs0 = (u64)w * WS;
+		__syncthreads(); // the table is staged; the previous item's shared arrays are no longer read
+		for (int i = tid; i < WS + 1; i += WS)
+			sw[i] = ((gs0 + i) << 6) < end_bits + 128 ? __ldg((const u64 *)stream + gs0 + i) : 0ull;
+		__syncthreads();
+		if (tid == 0) { // the serial part: positions only
+			u32 state = it.y;
+			for (int t = 0; t < WS; ++t) {
+				sentry[t] = (unsigned short)state;
+				const u64 b2 = ((gs0 + t) << 6) < end_bits + 64 ? sw[t + 1] : 0ull; // load_slice's rule for the second word
+				const u32 x = slice_exit_lut(lut, sw[t], b2, clamp_avail(end_bits, (gs0 + t) << 6), state);
+				state = x == PDEAD ? 1u : x; // a dead chain restarts at class 1's seed offset with order 0 (dec_scan_kernel)
 			}
 		}
+		__syncthreads();
+		const u64 gs = gs0 + tid;
+		const u32 entry = sentry[tid];
+		u64 mem;
+		u32 tok;
+		const u64 b2 = (gs << 6) < end_bits + 64 ? sw[tid + 1] : 0ull;
+		const u32 x = slice_walk_lut(lut, sw[tid], b2, clamp_avail(end_bits, gs << 6), entry, mem, tok);
+		if (x == PDEAD)
+			mem += DEATH;
+		u64 tot_m, tot_t;
+		const u64 pm = block_exscan_u64(mem, ws, &tot_m);
+		const u64 pt = block_exscan_u64((u64)tok, ws, &tot_t);
+		E16[2 * gs + 1] = (unsigned short)entry;
+		P64[2 * gs + 1] = pm;
+		TK16[2 * gs + 1] = (unsigned short)pt;
+		if (tid == WS - 1) {
+			reinterpret_cast<unsigned short *>(winX_out)[2 * w + 1] = (unsigned short)x;
+			reinterpret_cast<u64 *>(winPT)[2 * w + 1] = tot_m;
+			reinterpret_cast<unsigned short *>(winTT)[2 * w + 1] = (unsigned short)tot_t;
+			changed_out[w] = 1;
+		}
 	}
-	if (!__syncthreads_or(replace))
-		return;
-	for (int i = threadIdx.x; i < (1 << LUT_BITS); i += 128)
-		lut[i] = __ldg(toklut + i);
-	__syncthreads();
-	if (!replace)
-		return;
-	walk_window_chain(stream, end_bits, lut, w, 1u, (int)(st & 63u), (int)(st >> 6), E, P, TK, winX_out, winPT, winTT);
-	changed_out[w] = 1;
 }
 
 // ---------------------------------------------------------------------------------------------- link
@@ -932,6 +979,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 			dead_link(pfL0);
 			dead_link(pfL1);
 			u32 guard = 0;
+			bool long_walk = false; // the walk has already crossed a window without joining: no point in careful first steps
 			++slow_entries;
 			++reason[0];
 			while (event == EV_NONE) {
@@ -984,8 +1032,43 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 							mp = B.P[mgs];
 							mtk = B.TK[mgs];
 						}
-						for (int t = 0; t < nb; ++t) {
-							const u64 a = shfl_u64(ma, t), b = shfl_u64(mb, t);
+						// Most visits join within a slice or two: those slices are stepped with full bookkeeping right away.
+						// A walk that is still going after EXACT_FIRST slices (a region where the canonical chains are slow to
+						// fall onto the token grid: long runs, high Rice orders) changes gear: the serial part only follows the
+						// token POSITIONS (offset and order from slice to slice: a few instructions per token) until the chain
+						// joins or a token cannot be read; what the slices consume is then counted by all lanes at once, one
+						// slice each, from the entry states the walk left behind; a scan finds the slice in which the members
+						// run out, and only that slice is stepped with full bookkeeping.
+						const int avail_l = clamp_avail(end_bits, mgs << 6);
+						int t0 = 0;
+						if (i == i0 && !long_walk) {
+							for (; t0 < nb && t0 < EXACT_FIRST; ++t0) {
+								const u32 e = __shfl_sync(FULL, me, t0);
+								const u32 state = (u32)d | ((u32)k << 6);
+								if (state == (e & 0xffffu) || state == (e >> 16)) {
+									m = i + t0;
+									qm = state == (e & 0xffffu) ? 0 : 1;
+									pm = shfl_u64(qm ? mp.y : mp.x, t0);
+									tkm = __shfl_sync(FULL, mtk, t0);
+									break;
+								}
+								const u64 a = shfl_u64(ma, t0), b = shfl_u64(mb, t0);
+								++exact_steps;
+								const u64 sgs = (u64)cw * WS + i + t0;
+								event = walk_events(lut, a, b, __shfl_sync(FULL, avail_l, t0), T, d, k, cum, ones, f_pending);
+								if (event != EV_NONE) {
+									f_pos = (sgs << 6) + (u64)d;
+									f_k = k;
+									break;
+								}
+								d -= 64;
+							}
+							if (event != EV_NONE || m != WS)
+								break;
+						}
+						u32 my_entry = PDEAD;
+						int nwalk = 0, stop_t = -1;
+						for (int t = t0; t < nb; ++t) {
 							const u32 e = __shfl_sync(FULL, me, t);
 							const u32 state = (u32)d | ((u32)k << 6);
 							if (state == (e & 0xffffu) || state == (e >> 16)) {
@@ -995,15 +1078,65 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 								tkm = __shfl_sync(FULL, mtk, t);
 								break;
 							}
-							++exact_steps;
-							const u64 sgs = (u64)cw * WS + i + t;
-							event = walk_events(lut, a, b, clamp_avail(end_bits, sgs << 6), T, d, k, cum, ones, f_pending);
-							if (event != EV_NONE) {
-								f_pos = (sgs << 6) + (u64)d;
-								f_k = k;
+							const u64 a = shfl_u64(ma, t), b = shfl_u64(mb, t);
+							if (lane == t)
+								my_entry = state;
+							const u32 x = slice_exit_lut(lut, a, b, __shfl_sync(FULL, avail_l, t), state);
+							++nwalk;
+							if (x == PDEAD) {
+								stop_t = t; // a token of this slice cannot be read completely: the exact step below says why
 								break;
 							}
-							d -= 64;
+							d = (int)(x & 63u);
+							k = (int)(x >> 6);
+						}
+						exact_steps += (u32)nwalk;
+						if (nwalk > 0) {
+							const bool mine = lane >= t0 && lane < t0 + nwalk;
+							u64 lmem = 0;
+							u32 ltok = 0;
+							if (mine)
+								slice_walk_lut(lut, ma, mb, avail_l, my_entry, lmem, ltok);
+							u64 incm = lmem;
+							u32 inct = ltok;
+#pragma unroll
+							for (int dd = 1; dd < 32; dd <<= 1) {
+								const u64 tm = shfl_u64(incm, max(lane - dd, 0));
+								const u32 tt = __shfl_up_sync(FULL, inct, dd);
+								if (lane >= dd) {
+									incm += tm;
+									inct += tt;
+								}
+							}
+							const u32 crossed = __ballot_sync(FULL, mine && cum + incm >= T);
+							int xt = crossed ? __ffs((int)crossed) - 1 : -1;
+							if (xt < 0)
+								xt = stop_t;
+							if (xt >= 0) {
+								// the pass ends (or the stream does) inside slice i + xt: members and ones in front of it, then
+								// the exact step from the slice's entry state
+								cum += shfl_u64(incm - lmem, xt);
+								ones += __shfl_sync(FULL, inct - ltok, xt);
+								const u32 en = __shfl_sync(FULL, my_entry, xt);
+								const u64 a = shfl_u64(ma, xt), b = shfl_u64(mb, xt);
+								const u64 sgs = (u64)cw * WS + i + xt;
+								d = (int)(en & 63u);
+								k = (int)(en >> 6);
+								event = walk_events(lut, a, b, clamp_avail(end_bits, sgs << 6), T, d, k, cum, ones, f_pending);
+								if (event == EV_NONE && cum >= T)
+									event = EV_COVERED; // the pass ends exactly with the slice's last token
+								if (event == EV_NONE) {
+									event = EV_STOP; // cannot happen: the scan saw the members run out or a token fail here
+									tripped = 3;
+								}
+								f_pos = (sgs << 6) + (u64)d;
+								f_k = k;
+								m = WS; // the pass ended in front of a join the position walk may have seen further on
+								qm = 0;
+								break;
+							}
+							cum += shfl_u64(incm, t0 + nwalk - 1);
+							ones += __shfl_sync(FULL, inct, t0 + nwalk - 1);
 						}
 						i += nb;
 					}
@@ -1032,6 +1165,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 					if (event != EV_NONE)
 						break;
 					if (m == WS) { // the window ended before the chain joined: go on exactly in the next one
+						long_walk = true;
 						++reason[3];
 						gs = ((u64)cw + 1) * WS;
 						continue;
@@ -1760,12 +1894,16 @@ void dec_token_table(u32 *host_table)
 	}
 }
 
-// Lineage passes cost the latency of one lone window walk each (~0.18 ms) whatever the stream size, and save exact resolver
-// steps in proportion to the stream's slow-to-synchronise regions.  Measured (single frame, coder stage, B200): 8K photo
-// 5.02 / 4.44 / 4.05 / 3.77 / 3.55 / 3.74 ms for 0 / 1 / 2 / 3 / 5 / 8 passes, 4K photo 1.80 / 1.93 / 2.07 ms for 0 / 1 / 2.
-static int lineage_passes(u32 nwin)
+// A lineage pass costs ~0.13 ms of latency whatever the stream size (one window's positions walked by one thread) and
+// saves exact resolver steps in proportion to the stream's slow-to-synchronise regions -- the top planes of the big
+// levels, which every stream of a large image starts with.  Measured (single frame, coder stage, B200): 8K photo 4.35 /
+// 4.04 / 3.80 / 3.62 / 3.43 / 3.57 / 3.61 ms for 0 / 1 / 2 / 3 / 5 / 8 / 12 passes; its first 1 MiB 3.26 / 2.57 / 2.19 / 2.24 ms
+// for 0 / 2 / 4 / 8; 4K photo 1.82 / 1.83 / 1.97 ms for 0 / 1 / 2.
+static int lineage_passes(const Geom &g, u32 nwin)
 {
-	return nwin >= 32768u ? 5 : (nwin >= 20000u ? 1 : 0);
+	if (g.pix[g.levels] < 20000000LL || nwin < 512u)
+		return 0;
+	return nwin >= 8192u ? 5 : 4;
 }
 
 int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b_in, int nchunks, cudaStream_t st, long long *launches)
@@ -1785,11 +1923,17 @@ int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b_in, int nchunks,
 		unsigned char *cin = nullptr, *cout = b.chg;
 		static const int forced = getenv("DWT_LINEAGE") ? atoi(getenv("DWT_LINEAGE")) : -1; // tuning aid
 		// several frames in flight: the resolver's latency hides behind the other frames' kernels, the passes are only work
-		const int passes = forced >= 0 ? forced : (b.in_flight >= 4 ? 0 : lineage_passes(b.nwin));
+		int passes = forced >= 0 ? forced : (b.in_flight >= 4 ? 0 : lineage_passes(g, b.nwin));
+		if (passes > DWT_DEC_MAX_LINEAGE)
+			passes = DWT_DEC_MAX_LINEAGE;
+		const unsigned ext_grid = (unsigned)(b.nwin < 4u * (u32)dwt_device_sms() ? b.nwin : 4u * (u32)dwt_device_sms());
 		for (int pass = 0; pass < passes; ++pass) {
-			dec_scan_extend_kernel<<<(b.nwin + 127) / 128, 128, 0, st>>>(b.stream, b.end_bits, b.toklut, b.nwin, b.E, b.P, b.TK, xin,
-			                                                             xout, b.winPT, b.winTT, cin, cout);
-			++*launches;
+			u32 *cnt = b.ext_count + pass; // one counter per pass, zeroed by the caller
+			dec_extend_find_kernel<<<(b.nwin + 127) / 128, 128, 0, st>>>(b.stream, b.end_bits, b.nwin, b.E, xin, xout, cin, cout, cnt,
+			                                                             b.ext_list);
+			dec_extend_walk_kernel<<<ext_grid, WS, 0, st>>>(b.stream, b.end_bits, b.toklut, b.E, b.P, b.TK, xout, b.winPT, b.winTT, cout,
+			                                                cnt, b.ext_list);
+			*launches += 2;
 			u32 *t = xin;
 			xin = xout;
 			xout = t;

@@ -246,7 +246,7 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		// per slice: E 4 B + P 16 B + TK 4 B; per window: X 4 B + PT 16 B + TT 4 B + two link records
 		const size_t nsuper = (nwin + DWT_DEC_SUPER - 1) / DWT_DEC_SUPER;
 		const size_t scan_bytes = nslice * 24 + nwin * (24 + 2 * sizeof(DecLink)) + nsuper * 2 * sizeof(DecSuper) +
-		                          (nsuper + (size_t)nchunks + 8) * sizeof(DecBulk) + nwin * 4 + round_up(2 * nwin, 16) + 256;
+		                          (nsuper + (size_t)nchunks + 8) * sizeof(DecBulk) + nwin * 4 + round_up(2 * nwin, 16) + nwin * 8 + 64 + 16 + 256;
 		if (c->bs.ensure(bs_words * 4 + 64) || c->sig.ensure(sig_words * 4 + 64) || c->dstate.ensure(sizeof(DecState)) ||
 		    c->mem_pref.ensure(ntiles * 8 + 64) || c->ref_pref.ensure(ntiles * 8 + 64) ||
 		    c->ones_rank.ensure(rank_words * 8 + 64) || c->dec_scan.ensure(scan_bytes) ||
@@ -299,6 +299,12 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		b.winX2 = (u32 *)sp;
 		sp += nwin * 4;
 		b.chg = (unsigned char *)sp;
+		sp += round_up(2 * nwin, 16);
+		sp = (char *)(((uintptr_t)sp + 15) & ~(uintptr_t)15); // the u32 arrays above leave it 4-byte aligned
+		b.ext_list = (uint2 *)sp;
+		sp += nwin * 8;
+		b.ext_count = (u32 *)sp;
+		CUDA_OK(cudaMemsetAsync(b.ext_count, 0, 64, st));
 		b.seg = c->dec_seg.as<DecSeg>();
 		b.chunks = c->dec_chunks.as<DecChunk>();
 		b.tile_sums = c->mem_pref.as<u32>();
