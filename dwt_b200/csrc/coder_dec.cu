@@ -879,7 +879,8 @@ __device__ __forceinline__ void load_super(const DecSuper *src, DecSuper &S)
 __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__ Geom G, int nchunks,
                                                           const __grid_constant__ DecBuffers B)
 {
-	static_assert(WS == 128, "the end search loads four slices per lane");
+	static_assert(WS % 32 == 0 && WS >= 32 && WS <= 256, "the end search loads WS / 32 slices per lane");
+	constexpr int NPL = WS / 32;
 #ifdef DWT_RESOLVE_PROFILE
 	long long rp_cyc[5] = {0, 0, 0, 0, 0};
 	const long long rp_start = clock64();
@@ -1384,42 +1385,54 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 				}
 				if (search) {
 					// ---- the pass ends on class sq of window sw at or behind slice sm: smallest slice i >= sm with
-					// cum + P(i + 1) - P(sm) >= T.  A window has 128 slices: every lane fetches the tables and the stream
-					// words of four of them in one go, a ballot finds the slice, and that slice is stepped exactly.
+					// cum + P(i + 1) - P(sm) >= T.  Every lane fetches the tables and the stream words of its WS / 32 slices
+					// in one go, a ballot finds the slice, and that slice is stepped exactly.
 					search = false;
 					++n_search;
 					RP_BEGIN();
 					const u64 wbase = (u64)sw * WS;
-					const u64 g4 = wbase + 4u * (u32)lane;
-					ulonglong2 p4[4];
+					const u64 g4 = wbase + (u32)(NPL * lane);
+					u64 pv[NPL + 1]; // members of class sq before my slices and before the slice behind them
+					u32 tk4[NPL], en4[NPL];
+					u64 s5[NPL + 1]; // stream words of my slices and the one behind them
 #pragma unroll
-					for (int t = 0; t < 4; ++t)
-						p4[t] = B.P[g4 + t];
-					const uint4 e4 = *reinterpret_cast<const uint4 *>(B.E + g4);
-					const uint4 t4 = *reinterpret_cast<const uint4 *>(B.TK + g4);
-					u64 s5[5]; // stream words of my four slices and the one behind them
+					for (int t = 0; t < NPL; ++t) {
+						const ulonglong2 p2 = B.P[g4 + t];
+						pv[t] = sq ? p2.y : p2.x;
+						en4[t] = B.E[g4 + t];
+						tk4[t] = B.TK[g4 + t];
+					}
 #pragma unroll
-					for (int t = 0; t < 5; ++t)
+					for (int t = 0; t < NPL + 1; ++t)
 						s5[t] = ((g4 + t) << 6) < end_bits + 128 ? __ldg((const u64 *)stream + g4 + t) : 0ull;
 					const ulonglong2 pt2 = B.winPT[sw];
 					const u64 ptot = sq ? pt2.y : pt2.x;
-					u64 pv[5]; // members of class sq before my four slices and before the slice behind them
-#pragma unroll
-					for (int t = 0; t < 4; ++t)
-						pv[t] = sq ? p4[t].y : p4[t].x;
-					pv[4] = shfl_u64(pv[0], min(lane + 1, 31));
+					pv[NPL] = shfl_u64(pv[0], min(lane + 1, 31));
 					if (lane == 31)
-						pv[4] = ptot;
-					const u32 tk4[4] = {t4.x, t4.y, t4.z, t4.w};
-					const u32 en4[4] = {e4.x, e4.y, e4.z, e4.w};
+						pv[NPL] = ptot;
+					// the value a lane holds for its t-th slice, t uniform across the warp
+					auto pick64 = [&](const u64 *v, int t) {
+						u64 r = v[0];
+#pragma unroll
+						for (int q2 = 1; q2 < NPL + 1; ++q2)
+							r = t == q2 ? v[q2] : r;
+						return r;
+					};
+					auto pick32 = [&](const u32 *v, int t) {
+						u32 r = v[0];
+#pragma unroll
+						for (int q2 = 1; q2 < NPL; ++q2)
+							r = t == q2 ? v[q2] : r;
+						return r;
+					};
 					// P and TK at the start slice sm
-					const int sm_lane = sm >> 2, sm_k = sm & 3;
-					const u64 pm = shfl_u64(sm_k == 0 ? pv[0] : (sm_k == 1 ? pv[1] : (sm_k == 2 ? pv[2] : pv[3])), sm_lane);
-					const u32 tkm = __shfl_sync(FULL, sm_k == 0 ? tk4[0] : (sm_k == 1 ? tk4[1] : (sm_k == 2 ? tk4[2] : tk4[3])), sm_lane);
+					const int sm_lane = sm / NPL, sm_k = sm % NPL;
+					const u64 pm = shfl_u64(pick64(pv, sm_k), sm_lane);
+					const u32 tkm = __shfl_sync(FULL, pick32(tk4, sm_k), sm_lane);
 					u32 hit = 0;
 #pragma unroll
-					for (int t = 0; t < 4; ++t) {
-						const int idx = 4 * lane + t;
+					for (int t = 0; t < NPL; ++t) {
+						const int idx = NPL * lane + t;
 						if (idx >= sm && cum + (pv[t + 1] - pm) >= T)
 							hit |= 1u << t;
 					}
@@ -1431,13 +1444,13 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 					}
 					const int fl = __ffs((int)bal) - 1;
 					const int fk = __ffs((int)__shfl_sync(FULL, hit, fl)) - 1;
-					const int lo = 4 * fl + fk;
+					const int lo = NPL * fl + fk;
 					const u64 egs = wbase + lo;
-					const u64 pi = shfl_u64(fk == 0 ? pv[0] : (fk == 1 ? pv[1] : (fk == 2 ? pv[2] : pv[3])), fl);
-					const u32 tki = __shfl_sync(FULL, fk == 0 ? tk4[0] : (fk == 1 ? tk4[1] : (fk == 2 ? tk4[2] : tk4[3])), fl);
-					const u32 e2 = __shfl_sync(FULL, fk == 0 ? en4[0] : (fk == 1 ? en4[1] : (fk == 2 ? en4[2] : en4[3])), fl);
-					const u64 a = shfl_u64(fk == 0 ? s5[0] : (fk == 1 ? s5[1] : (fk == 2 ? s5[2] : s5[3])), fl);
-					u64 b = shfl_u64(fk == 0 ? s5[1] : (fk == 1 ? s5[2] : (fk == 2 ? s5[3] : s5[4])), fl);
+					const u64 pi = shfl_u64(pick64(pv, fk), fl);
+					const u32 tki = __shfl_sync(FULL, pick32(tk4, fk), fl);
+					const u32 e2 = __shfl_sync(FULL, pick32(en4, fk), fl);
+					const u64 a = shfl_u64(pick64(s5, fk), fl);
+					u64 b = shfl_u64(pick64(s5, fk + 1), fl);
 					if (((egs + 1) << 6) >= end_bits + 64)
 						b = 0ull; // load_slice's rule for the second word
 					const u32 e = (e2 >> (16 * sq)) & 0xffffu;
