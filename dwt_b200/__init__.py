@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdwt_b200.so")
+LIB_PATH = os.environ.get("DWT_B200_LIB") or os.path.join(HERE, "libdwt_b200.so")  # the override is an A/B aid for builds with other flags
 
 # every symbol include/dwt_b200.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = [
