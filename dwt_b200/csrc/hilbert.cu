@@ -472,10 +472,10 @@ __device__ __forceinline__ void tma_load_cell(void *dst, const CUtensorMap *map,
 	             : "memory");
 }
 
-__device__ __forceinline__ void tma_store_cell(const CUtensorMap *map, int x, int y, const void *src)
+__device__ __forceinline__ void tma_store_cell(const CUtensorMap *map, int x, int y, int z, const void *src)
 {
 	asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(reinterpret_cast<u64>(map)),
-	             "r"(x), "r"(y), "r"(0), "r"(smem_addr(src))
+	             "r"(x), "r"(y), "r"(z), "r"(smem_addr(src))
 	             : "memory");
 }
 
@@ -608,88 +608,112 @@ __global__ void __launch_bounds__(TMA_WARPS * 32) linearize_tma_kernel(const __g
 }
 
 // The inverse has no box to wait for -- its input are the plane rows, fetched with plain loads -- so what hides the load
-// latency is the number of warps: one cell buffer per warp (the TMA store of cell n reads it while the warp is busy with
-// the loads and the transposes of cell n + 1), 8 warps per CTA, 2 CTAs per SM.
+// latency is the number of warps.  A warp therefore works on ONE channel of a cell at a time: a 4 KB cell buffer per warp
+// instead of 12 KB and 16 plane words in registers instead of 48, which lets 32 warps share an SM (the three-channel
+// version fitted 16 and spent 77 % of its stall samples waiting for the plane rows).  The TMA store of channel c reads
+// the buffer while the warp loads and transposes the planes of channel c + 1; the cell descriptors (list entry ->
+// rank / origin words, two dependent loads) are fetched one and two cells ahead.
 constexpr int REC_WARPS = 8;
+constexpr int REC_CTAS_PER_SM = 4;
 
-template <int NC>
 constexpr size_t rec_smem_bytes()
 {
-	return (size_t)REC_WARPS * NC * 4096 + 8192 + 1024;
+	return (size_t)REC_WARPS * 4096 + 8192 + 1024;
 }
 
 template <int NC>
-__global__ void __launch_bounds__(REC_WARPS * 32, 2) reconstruct_tma_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                                             const __grid_constant__ HParams P,
-                                                                             const u32 *__restrict__ list, int nlist,
-                                                                             const unsigned short *__restrict__ tile_lut,
-                                                                             const u32 *__restrict__ bs,
-                                                                             const int *__restrict__ missing, int levels_used)
+__global__ void __launch_bounds__(REC_WARPS * 32, REC_CTAS_PER_SM) reconstruct_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                                           const __grid_constant__ HParams P,
+                                                                                           const u32 *__restrict__ list, int nlist,
+                                                                                           const unsigned short *__restrict__ tile_lut,
+                                                                                           const u32 *__restrict__ bs,
+                                                                                           const int *__restrict__ missing,
+                                                                                           int levels_used)
 {
 	extern __shared__ unsigned char tma_raw[];
 	unsigned char *raw = tma_raw;
 	raw += (1024u - (smem_addr(raw) & 1023u)) & 1023u;
 	int *cells = reinterpret_cast<int *>(raw);
-	unsigned short *lut = reinterpret_cast<unsigned short *>(raw + (size_t)REC_WARPS * NC * 4096);
+	unsigned short *lut = reinterpret_cast<unsigned short *>(raw + (size_t)REC_WARPS * 4096);
 	for (int i = threadIdx.x; i < 2048; i += blockDim.x)
 		reinterpret_cast<u32 *>(lut)[i] = __ldg(reinterpret_cast<const u32 *>(tile_lut) + i);
 	__syncthreads();
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	int *cell = cells + (size_t)wid * NC * 1024;
+	int *cell = cells + (size_t)wid * 1024;
 	const int stride = gridDim.x * REC_WARPS;
-	for (int item = blockIdx.x * REC_WARPS + wid; item < nlist; item += stride) {
-		const CellRef c = cell_ref(P, __ldg(list + item));
-		if (c.level >= levels_used)
+	int item = blockIdx.x * REC_WARPS + wid;
+	// descriptor pipeline: `ent` belongs to the cell after the next, (R0, info) to the next cell
+	auto entry_of = [&](int it) { return it < nlist ? __ldg(list + it) : 0u; };
+	u32 ent0 = entry_of(item), ent1 = entry_of(item + stride);
+	u32 R0 = 0, info = 0;
+	if (item < nlist) {
+		const HLevel &L = P.lv[ent0 >> 28];
+		R0 = __ldg(P.cell_base + L.cell_off + (ent0 & 0x0fffffffu));
+		info = __ldg(P.cell_info + L.cell_off + (ent0 & 0x0fffffffu));
+	}
+	for (; item < nlist; item += stride) {
+		const int level = (int)(ent0 >> 28);
+		const int ox = (int)(info & 0xfffu) * 32, oy = (int)((info >> 12) & 0xfffu) * 32;
+		const u32 orient = info >> 24;
+		const u32 g0 = (u32)P.lv[level].gbase + (R0 >> 5);
+		const int s = (int)(R0 & 31u);
+		// next cell's descriptor words, and the list entry behind it
+		ent0 = ent1;
+		ent1 = entry_of(item + 2 * stride);
+		if (item + stride < nlist) {
+			const HLevel &L = P.lv[ent0 >> 28];
+			R0 = __ldg(P.cell_base + L.cell_off + (ent0 & 0x0fffffffu));
+			info = __ldg(P.cell_info + L.cell_off + (ent0 & 0x0fffffffu));
+		}
+		if (level >= levels_used)
 			continue;
-		const unsigned short *lo = lut + c.orient * 1024;
-		const int s = c.s;
+		const unsigned short *lo = lut + orient * 1024;
 		const bool split = s != 0 && lane == 0;
 		const u32 lo_mask = (1u << s) - 1u;
-		u32 w[NC][16];
-		int bias[NC];
-#pragma unroll
+#pragma unroll 1
 		for (int ch = 0; ch < NC; ++ch) {
+			u32 w[16];
 			const int planes = P.lay.planes[ch];
-			const u32 *src = bs + P.lay.bsbase[ch] + c.g0 + lane;
+			const u32 *src = bs + P.lay.bsbase[ch] + g0 + lane;
+			// every plane row is requested before the first one is used; the second word of a cell that starts inside a
+			// group (s != 0: lane 0 owns the head of the first group and the tail of the last) is a pass of its own behind
+			// a warp-uniform branch -- merged into the loop above, each plane's load waited for the one in front
 #pragma unroll
-			for (int p = 0; p < 16; ++p) {
-				u32 v = 0;
-				if (p == 15 || p < planes) {
-					const u32 *r = src + (long long)(p == 15 ? planes : p) * P.GT;
-					v = __ldg(r);
+			for (int p = 0; p < 16; ++p)
+				w[p] = (p == 15 || p < planes) ? __ldg(src + (long long)(p == 15 ? planes : p) * P.GT) : 0u;
+			if (s != 0) {
+				u32 t[16];
+#pragma unroll
+				for (int p = 0; p < 16; ++p)
+					t[p] = (split && (p == 15 || p < planes)) ? __ldg(src + (long long)(p == 15 ? planes : p) * P.GT + 32) : 0u;
+#pragma unroll
+				for (int p = 0; p < 16; ++p)
 					if (split)
-						v = (v & ~lo_mask) | (__ldg(r + 32) & lo_mask);
-				}
-				w[ch][p] = v;
+						w[p] = (w[p] & ~lo_mask) | (t[p] & lo_mask);
 			}
-			const int m = missing[ch * 16 + c.level] - 2; // decode.c:51-58
-			bias[ch] = m >= 0 ? 1 << m : 0;
-		}
+			const int m = missing[ch * 16 + level] - 2; // decode.c:51-58
+			const int bias = m >= 0 ? 1 << m : 0;
+			bitslice_transpose16(w);
+			// the TMA store of the previous channel must have finished reading the buffer
+			if (lane == 0)
+				asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+			__syncwarp();
 #pragma unroll
-		for (int ch = 0; ch < NC; ++ch)
-			bitslice_transpose16(w[ch]);
-		// the TMA store of the previous cell must have finished reading the buffer
-		if (lane == 0)
-			asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-		__syncwarp();
-#pragma unroll
-		for (int i = 0; i < 32; ++i) {
-			const int ip = (i - s) & 31;
-			const int kp = (lane - (i < s ? 1 : 0)) & 31;
-			const int off = lo[ip * 32 + kp];
-#pragma unroll
-			for (int ch = 0; ch < NC; ++ch) {
-				int v = bitslice_value(i < 16 ? (w[ch][i] & 0xffffu) : (w[ch][i - 16] >> 16));
+			for (int i = 0; i < 32; ++i) {
+				const int ip = (i - s) & 31;
+				const int kp = (lane - (i < s ? 1 : 0)) & 31;
+				const int off = lo[ip * 32 + kp];
+				int v = bitslice_value(i < 16 ? (w[i] & 0xffffu) : (w[i - 16] >> 16));
 				if (v != 0)
-					v += v < 0 ? -bias[ch] : bias[ch];
-				cell[ch * 1024 + off] = v;
+					v += v < 0 ? -bias : bias;
+				cell[off] = v;
 			}
-		}
-		asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // my writes before the bulk copy reads them
-		__syncwarp();
-		if (lane == 0) {
-			tma_store_cell(&tmap, c.ox, c.oy, cell);
-			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // my writes before the bulk copy reads them
+			__syncwarp();
+			if (lane == 0) {
+				tma_store_cell(&tmap, ox, oy, ch, cell);
+				asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+			}
 		}
 	}
 	if (lane == 0)
@@ -716,14 +740,14 @@ EncodeTiledFn encode_tiled_fn()
 	return fn;
 }
 
-bool make_cell_map(CUtensorMap *map, const int *pyr, int W, int H, int C, long long chan_stride, int pitch)
+bool make_cell_map(CUtensorMap *map, const int *pyr, int W, int H, int C, long long chan_stride, int pitch, int box_c)
 {
 	const EncodeTiledFn fn = encode_tiled_fn();
 	if (!fn || (pitch & 3) || (chan_stride & 3) || (reinterpret_cast<uintptr_t>(pyr) & 15) || W < 32 || H < 32)
 		return false;
 	const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C};
 	const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)chan_stride * 4};
-	const cuuint32_t box[3] = {32, 32, (cuuint32_t)C}, estr[3] = {1, 1, 1};
+	const cuuint32_t box[3] = {32, 32, (cuuint32_t)box_c}, estr[3] = {1, 1, 1};
 	return fn(map, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, const_cast<int *>(pyr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
 	          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -752,7 +776,7 @@ int tma_grid(int nlist)
 int rec_grid(int nlist)
 {
 	const int want = (nlist + REC_WARPS - 1) / REC_WARPS;
-	const int cap = dwt_device_sms() * 2;
+	const int cap = dwt_device_sms() * REC_CTAS_PER_SM;
 	return want < cap ? want : cap;
 }
 
@@ -936,7 +960,7 @@ int hilbert_linearize(const Geom &g, const HilbertPlan &plan, const Sched &s, co
 	const int nfull = plan.full_off[levels_used], npart = plan.part_off[levels_used];
 	CUtensorMap tmap;
 	if (nfull > 0 && tma_wanted() && planes_fit_tma(g, s) &&
-	    make_cell_map(&tmap, pyr, g.w[g.levels], g.h[g.levels], g.channels, pyr_chan_stride, pyr_pitch)) {
+	    make_cell_map(&tmap, pyr, g.w[g.levels], g.h[g.levels], g.channels, pyr_chan_stride, pyr_pitch, g.channels)) {
 		// full cells through the tensor memory accelerator (see the TMA section above)
 		if (g.channels == 3) {
 			if (tma_configure(linearize_tma_kernel<3>, tma_smem_bytes<3>()))
@@ -991,19 +1015,19 @@ int hilbert_reconstruct(const Geom &g, const HilbertPlan &plan, const Sched &s, 
 	const int nfull = plan.full_off[levels_used], npart = plan.part_off[levels_used];
 	CUtensorMap tmap;
 	if (nfull > 0 && tma_wanted() && planes_fit_tma(g, s) &&
-	    make_cell_map(&tmap, pyr, g.w[levels_used], g.h[levels_used], g.channels, pyr_chan_stride, pyr_pitch)) {
+	    make_cell_map(&tmap, pyr, g.w[levels_used], g.h[levels_used], g.channels, pyr_chan_stride, pyr_pitch, 1)) {
 		if (g.channels == 3) {
-			if (tma_configure(reconstruct_tma_kernel<3>, rec_smem_bytes<3>()))
+			if (tma_configure(reconstruct_tma_kernel<3>, rec_smem_bytes()))
 				return -1;
-			reconstruct_tma_kernel<3><<<rec_grid(nfull), REC_WARPS * 32, rec_smem_bytes<3>(), st>>>(tmap, P, plan.full_list, nfull,
-			                                                                                     plan.tile_lut, bs, missing_dev,
-			                                                                                     levels_used);
+			reconstruct_tma_kernel<3><<<rec_grid(nfull), REC_WARPS * 32, rec_smem_bytes(), st>>>(tmap, P, plan.full_list, nfull,
+			                                                                                  plan.tile_lut, bs, missing_dev,
+			                                                                                  levels_used);
 		} else {
-			if (tma_configure(reconstruct_tma_kernel<1>, rec_smem_bytes<1>()))
+			if (tma_configure(reconstruct_tma_kernel<1>, rec_smem_bytes()))
 				return -1;
-			reconstruct_tma_kernel<1><<<rec_grid(nfull), REC_WARPS * 32, rec_smem_bytes<1>(), st>>>(tmap, P, plan.full_list, nfull,
-			                                                                                     plan.tile_lut, bs, missing_dev,
-			                                                                                     levels_used);
+			reconstruct_tma_kernel<1><<<rec_grid(nfull), REC_WARPS * 32, rec_smem_bytes(), st>>>(tmap, P, plan.full_list, nfull,
+			                                                                                  plan.tile_lut, bs, missing_dev,
+			                                                                                  levels_used);
 		}
 		if (launches)
 			++*launches;
