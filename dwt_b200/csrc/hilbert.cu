@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(256) reconstruct_kernel(const __grid_constant_
 // Requirements: rows 16-byte aligned in HBM (width % 4 == 0), at most 15 bit-planes; everything else takes the
 // ballot kernels above.
 
-constexpr int TMA_WARPS = 4;
+constexpr int TMA_WARPS = 8;
 
 __device__ __forceinline__ u32 smem_addr(const void *p)
 {
@@ -464,11 +464,11 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
 	             : "memory");
 }
 
-__device__ __forceinline__ void tma_load_cell(void *dst, const CUtensorMap *map, int x, int y, u64 *bar)
+__device__ __forceinline__ void tma_load_cell(void *dst, const CUtensorMap *map, int x, int y, int z, u64 *bar)
 {
 	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
 	                 smem_addr(dst)),
-	             "l"(reinterpret_cast<u64>(map)), "r"(x), "r"(y), "r"(0), "r"(smem_addr(bar))
+	             "l"(reinterpret_cast<u64>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_addr(bar))
 	             : "memory");
 }
 
@@ -479,20 +479,19 @@ __device__ __forceinline__ void tma_store_cell(const CUtensorMap *map, int x, in
 	             : "memory");
 }
 
-struct TmaSmem { // carved out of the dynamic shared memory, cell buffers first (1024-byte aligned for the swizzle)
-	int *cells;            // [TMA_WARPS][2][NC][1024]
+struct TmaSmem { // carved out of the dynamic shared memory, box buffers first (1024-byte aligned for the swizzle)
+	int *cells;            // [TMA_WARPS][2][1024]
 	unsigned short *lut;   // [4][1024]
 	u64 *bars;             // [TMA_WARPS][2]
 };
 
-template <int NC>
 __device__ __forceinline__ TmaSmem tma_smem(unsigned char *raw, const unsigned short *__restrict__ tile_lut)
 {
 	TmaSmem s;
 	const u32 base = smem_addr(raw);
 	raw += (1024u - (base & 1023u)) & 1023u;
 	s.cells = reinterpret_cast<int *>(raw);
-	s.lut = reinterpret_cast<unsigned short *>(raw + (size_t)TMA_WARPS * 2 * NC * 4096);
+	s.lut = reinterpret_cast<unsigned short *>(raw + (size_t)TMA_WARPS * 2 * 4096);
 	s.bars = reinterpret_cast<u64 *>(s.lut + 4096);
 	for (int i = threadIdx.x; i < 2048; i += blockDim.x) // 8 KB of offsets, two per word
 		reinterpret_cast<u32 *>(s.lut)[i] = __ldg(reinterpret_cast<const u32 *>(tile_lut) + i);
@@ -503,95 +502,94 @@ __device__ __forceinline__ TmaSmem tma_smem(unsigned char *raw, const unsigned s
 	return s;
 }
 
-template <int NC>
 constexpr size_t tma_smem_bytes()
 {
-	return (size_t)TMA_WARPS * 2 * NC * 4096 + 8192 + TMA_WARPS * 2 * 8 + 1024;
+	return (size_t)TMA_WARPS * 2 * 4096 + 8192 + TMA_WARPS * 2 * 8 + 1024;
 }
 
-struct CellRef {
-	int ox, oy;   // cell origin in the pyramid
-	u32 orient;   // bit 0 transpose, bit 1 point reflection
-	u32 g0;       // first group of the cell inside its channel's group axis (level base included)
-	int s;        // rank of the cell's first position inside that group
-	int level;
-};
-
-__device__ __forceinline__ CellRef cell_ref(const HParams &P, u32 ent)
-{
-	const HLevel &L = P.lv[ent >> 28];
-	const u32 q = ent & 0x0fffffffu;
-	const u32 R0 = __ldg(P.cell_base + L.cell_off + q), info = __ldg(P.cell_info + L.cell_off + q);
-	CellRef c;
-	c.ox = (int)(info & 0xfffu) * 32;
-	c.oy = (int)((info >> 12) & 0xfffu) * 32;
-	c.orient = info >> 24;
-	c.g0 = (u32)L.gbase + (R0 >> 5);
-	c.s = (int)(R0 & 31u);
-	c.level = (int)(ent >> 28);
-	return c;
-}
+// The unit of work is ONE channel of a cell (a 32 x 32 x 1 box, 4 KB): two boxes per warp are in flight or in use, 8
+// warps per CTA and 3 CTAs per SM keep 24 warps on an SM (whole three-channel cells of 12 KB allowed 8: the kernel then
+// ran at two warps per scheduler and 38 % issue utilisation).  The cell descriptors (list entry -> rank / origin words:
+// two dependent loads) are fetched one and two cells ahead.
+constexpr int LIN_CTAS_PER_SM = 3;
 
 template <int NC>
-__global__ void __launch_bounds__(TMA_WARPS * 32) linearize_tma_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                                        const __grid_constant__ HParams P,
-                                                                        const u32 *__restrict__ list, int nlist,
-                                                                        const unsigned short *__restrict__ tile_lut, u32 *bs)
+__global__ void __launch_bounds__(TMA_WARPS * 32, LIN_CTAS_PER_SM) linearize_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                                         const __grid_constant__ HParams P,
+                                                                                         const u32 *__restrict__ list, int nlist,
+                                                                                         const unsigned short *__restrict__ tile_lut,
+                                                                                         u32 *bs)
 {
 	extern __shared__ unsigned char tma_raw[];
-	const TmaSmem sm = tma_smem<NC>(tma_raw, tile_lut);
+	const TmaSmem sm = tma_smem(tma_raw, tile_lut);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	int *mycells = sm.cells + (size_t)wid * 2 * NC * 1024;
+	int *mycells = sm.cells + (size_t)wid * 2 * 1024;
 	u64 *mybar = sm.bars + wid * 2;
 	const int stride = gridDim.x * TMA_WARPS;
 	int item = blockIdx.x * TMA_WARPS + wid;
-	auto issue = [&](int it, int buf) { // lane 0: the cell's box into buffer `buf`
-		const CellRef c = cell_ref(P, __ldg(list + it));
-		mbar_expect_tx(mybar + buf, NC * 4096u);
-		tma_load_cell(mycells + (size_t)buf * NC * 1024, &tmap, c.ox, c.oy, mybar + buf);
+	if (item >= nlist)
+		return;
+	auto entry_of = [&](int it) { return it < nlist ? __ldg(list + it) : 0u; };
+	auto words_of = [&](u32 ent, u32 &R0, u32 &info) {
+		const HLevel &L = P.lv[ent >> 28];
+		R0 = __ldg(P.cell_base + L.cell_off + (ent & 0x0fffffffu));
+		info = __ldg(P.cell_info + L.cell_off + (ent & 0x0fffffffu));
 	};
-	if (item < nlist && lane == 0)
-		issue(item, 0);
+	auto issue = [&](u32 info, int ch, int buf) { // lane 0: channel ch of the cell with origin word `info` into buffer `buf`
+		mbar_expect_tx(mybar + buf, 4096u);
+		tma_load_cell(mycells + (size_t)buf * 1024, &tmap, (int)(info & 0xfffu) * 32, (int)((info >> 12) & 0xfffu) * 32, ch,
+		              mybar + buf);
+	};
+	// descriptors: the current cell, the next one, and the list entry of the one after
+	u32 ent_c = entry_of(item), R0_c, info_c;
+	words_of(ent_c, R0_c, info_c);
+	u32 ent_n = entry_of(item + stride), R0_n = 0, info_n = 0;
+	if (item + stride < nlist)
+		words_of(ent_n, R0_n, info_n);
+	u32 ent_nn = entry_of(item + 2 * stride);
+	if (lane == 0)
+		issue(info_c, 0, 0);
 	u32 phases = 0;
 	int buf = 0;
-	for (; item < nlist; item += stride, buf ^= 1) {
-		if (item + stride < nlist && lane == 0)
-			issue(item + stride, buf ^ 1); // the other buffer was released by the __syncwarp that ended the last round
-		const CellRef c = cell_ref(P, __ldg(list + item));
-		mbar_wait(mybar + buf, (phases >> buf) & 1u);
-		phases ^= 1u << buf;
-		const int *cell = mycells + (size_t)buf * NC * 1024;
-		const unsigned short *lo = sm.lut + c.orient * 1024;
-		const int s = c.s;
-		// lane k owns the ranks 32 k - s .. 32 k - s + 31 of the cell (mod 1024: for s > 0 lane 0 holds the head of the cell's
-		// first group in its high bits and the tail of the cell's last group in its low bits)
-		u32 w[NC][16];
-#pragma unroll
-		for (int i = 0; i < 32; ++i) {
-			const int ip = (i - s) & 31;
-			const int kp = (lane - (i < s ? 1 : 0)) & 31;
-			const int off = lo[ip * 32 + kp];
-#pragma unroll
-			for (int ch = 0; ch < NC; ++ch) {
-				const u32 h = bitslice_half(cell[ch * 1024 + off]);
-				if (i < 16)
-					w[ch][i] = h;
-				else
-					w[ch][i - 16] |= h << 16;
-			}
-		}
+	for (; item < nlist; item += stride) {
+		const u32 g0 = (u32)P.lv[ent_c >> 28].gbase + (R0_c >> 5);
+		const int s = (int)(R0_c & 31u);
+		const unsigned short *lo = sm.lut + (info_c >> 24) * 1024;
 		const bool split = s != 0 && lane == 0;
 		const u32 lo_mask = (1u << s) - 1u; // ranks below s of lane 0's word belong to the group behind the cell's last whole one
+#pragma unroll 1
+		for (int ch = 0; ch < NC; ++ch, buf ^= 1) {
+			// the next unit's box goes into the other buffer, which the __syncwarp at the end of the last round released
+			if (lane == 0) {
+				if (ch + 1 < NC)
+					issue(info_c, ch + 1, buf ^ 1);
+				else if (item + stride < nlist)
+					issue(info_n, 0, buf ^ 1);
+			}
+			mbar_wait(mybar + buf, (phases >> buf) & 1u);
+			phases ^= 1u << buf;
+			const int *cell = mycells + (size_t)buf * 1024;
+			// lane k owns the ranks 32 k - s .. 32 k - s + 31 of the cell (mod 1024: for s > 0 lane 0 holds the head of the cell's
+			// first group in its high bits and the tail of the cell's last group in its low bits)
+			u32 w[16];
 #pragma unroll
-		for (int ch = 0; ch < NC; ++ch) {
-			bitslice_transpose16(w[ch]);
+			for (int i = 0; i < 32; ++i) {
+				const int ip = (i - s) & 31;
+				const int kp = (lane - (i < s ? 1 : 0)) & 31;
+				const u32 h = bitslice_half(cell[lo[ip * 32 + kp]]);
+				if (i < 16)
+					w[i] = h;
+				else
+					w[i - 16] |= h << 16;
+			}
+			bitslice_transpose16(w);
 			const int planes = P.lay.planes[ch];
-			u32 *dst = bs + P.lay.bsbase[ch] + c.g0 + lane;
+			u32 *dst = bs + P.lay.bsbase[ch] + g0 + lane;
 #pragma unroll
 			for (int p = 0; p < 16; ++p) {
 				if (p < 15 && p >= planes)
 					continue;
-				const u32 v = w[ch][p];
+				const u32 v = w[p];
 				u32 *d = dst + (long long)(p == 15 ? planes : p) * P.GT;
 				if (!split) {
 					*d = v;
@@ -602,8 +600,15 @@ __global__ void __launch_bounds__(TMA_WARPS * 32) linearize_tma_kernel(const __g
 						atomicOr(d + 32, v & lo_mask);
 				}
 			}
+			__syncwarp(); // every lane is done with the buffer before lane 0 lets the next box land in it
 		}
-		__syncwarp(); // every lane is done with the buffer before lane 0 lets the next box land in it
+		ent_c = ent_n;
+		R0_c = R0_n;
+		info_c = info_n;
+		ent_n = ent_nn;
+		if (item + 2 * stride < nlist)
+			words_of(ent_n, R0_n, info_n);
+		ent_nn = entry_of(item + 3 * stride);
 	}
 }
 
@@ -769,7 +774,7 @@ bool planes_fit_tma(const Geom &g, const Sched &s)
 int tma_grid(int nlist)
 {
 	const int want = (nlist + TMA_WARPS - 1) / TMA_WARPS;
-	const int cap = dwt_device_sms() * 2; // two CTAs of ~105 KB fit an SM
+	const int cap = dwt_device_sms() * LIN_CTAS_PER_SM; // CTAs of ~73 KB
 	return want < cap ? want : cap;
 }
 
@@ -960,18 +965,18 @@ int hilbert_linearize(const Geom &g, const HilbertPlan &plan, const Sched &s, co
 	const int nfull = plan.full_off[levels_used], npart = plan.part_off[levels_used];
 	CUtensorMap tmap;
 	if (nfull > 0 && tma_wanted() && planes_fit_tma(g, s) &&
-	    make_cell_map(&tmap, pyr, g.w[g.levels], g.h[g.levels], g.channels, pyr_chan_stride, pyr_pitch, g.channels)) {
+	    make_cell_map(&tmap, pyr, g.w[g.levels], g.h[g.levels], g.channels, pyr_chan_stride, pyr_pitch, 1)) {
 		// full cells through the tensor memory accelerator (see the TMA section above)
 		if (g.channels == 3) {
-			if (tma_configure(linearize_tma_kernel<3>, tma_smem_bytes<3>()))
+			if (tma_configure(linearize_tma_kernel<3>, tma_smem_bytes()))
 				return -1;
-			linearize_tma_kernel<3><<<tma_grid(nfull), TMA_WARPS * 32, tma_smem_bytes<3>(), st>>>(tmap, P, plan.full_list, nfull,
-			                                                                                   plan.tile_lut, bs);
+			linearize_tma_kernel<3><<<tma_grid(nfull), TMA_WARPS * 32, tma_smem_bytes(), st>>>(tmap, P, plan.full_list, nfull,
+			                                                                                plan.tile_lut, bs);
 		} else {
-			if (tma_configure(linearize_tma_kernel<1>, tma_smem_bytes<1>()))
+			if (tma_configure(linearize_tma_kernel<1>, tma_smem_bytes()))
 				return -1;
-			linearize_tma_kernel<1><<<tma_grid(nfull), TMA_WARPS * 32, tma_smem_bytes<1>(), st>>>(tmap, P, plan.full_list, nfull,
-			                                                                                   plan.tile_lut, bs);
+			linearize_tma_kernel<1><<<tma_grid(nfull), TMA_WARPS * 32, tma_smem_bytes(), st>>>(tmap, P, plan.full_list, nfull,
+			                                                                                plan.tile_lut, bs);
 		}
 		if (launches)
 			++*launches;
