@@ -48,6 +48,36 @@ __device__ __forceinline__ u32 group_valid_mask(const Geom &G, int l, int g)
 	return rem >= 32 ? 0xffffffffu : ((1u << (int)rem) - 1u);
 }
 
+// exclusive scan over the 256 threads of a tile of two counts packed as lo | hi << 16 (tile totals < 2^16): one warp
+// shuffle scan, the eight warp totals through shared memory, ONE block barrier (`ws` holds two sets of warp totals used
+// alternately by consecutive calls: a warp can only be one call ahead of the slowest).  The generic 64-bit
+// block_exscan_u64 cost a quarter of enc_emit's instructions.
+__device__ __forceinline__ u32 tile_exscan_2x16(u32 v, u32 (*ws)[8], int parity)
+{
+	static_assert(TG == 256, "eight warps per tile");
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	u32 inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const u32 t = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= d)
+			inc += t;
+	}
+	if (lane == 31)
+		ws[parity][wid] = inc;
+	__syncthreads();
+	const uint4 a = *reinterpret_cast<const uint4 *>(&ws[parity][0]), b = *reinterpret_cast<const uint4 *>(&ws[parity][4]);
+	u32 base = 0;
+	base += wid > 0 ? a.x : 0u;
+	base += wid > 1 ? a.y : 0u;
+	base += wid > 2 ? a.z : 0u;
+	base += wid > 3 ? a.w : 0u;
+	base += wid > 4 ? b.x : 0u;
+	base += wid > 5 ? b.y : 0u;
+	base += wid > 6 ? b.z : 0u;
+	return base + inc - v;
+}
+
 // ------------------------------------------------------------------------------------------------ count
 
 __global__ void __launch_bounds__(TG) enc_count_kernel(const __grid_constant__ Geom G, const Sched *__restrict__ S,
@@ -64,8 +94,10 @@ __global__ void __launch_bounds__(TG) enc_count_kernel(const __grid_constant__ G
 	const u32 vm = group_valid_mask(G, l, g);
 	const u32 *base = bs + S->bsbase[c] + G.gbase[l] + g;
 	u32 sig = 0;
+	u32 Bn = vm && P > 0 ? __ldg(base + (long long)(P - 1) * G.GT) : 0u; // the next plane's word is always one plane ahead
 	for (int p = P - 1; p >= 0; --p) {
-		u32 B = vm ? __ldg(base + (long long)p * G.GT) : 0u;
+		const u32 B = Bn;
+		Bn = vm && p > 0 ? __ldg(base + (long long)(p - 1) * G.GT) : 0u;
 		u32 member = vm & ~sig;
 		u32 n1 = __popc(B & member), nz = __popc(member) - n1, nr = __popc(sig);
 		nz = __reduce_add_sync(0xffffffffu, nz);
@@ -279,7 +311,7 @@ __global__ void __launch_bounds__(TG) enc_emit_kernel(const __grid_constant__ Ge
                                                        const EncChunks *__restrict__ C, const EncInfo *__restrict__ info, u32 *Z,
                                                        u32 *signbuf, u32 *refbuf)
 {
-	__shared__ u64 ws[32];
+	__shared__ __align__(16) u32 ws[2][8];
 	int c, l, i;
 	tile_coords(G, blockIdx.x, c, l, i);
 	const int P = S->planes[c];
@@ -297,20 +329,24 @@ __global__ void __launch_bounds__(TG) enc_emit_kernel(const __grid_constant__ Ge
 	const u32 *base = bs + S->bsbase[c] + G.gbase[l] + g;
 	const u32 sgn = vm ? __ldg(base + (long long)P * G.GT) : 0u;
 	u32 sig = 0;
+	u32 Bn = vm ? __ldg(base + (long long)(P - 1) * G.GT) : 0u; // the next plane's word is always one plane ahead
 	for (int p = P - 1; p >= 0; --p) {
-		u32 B = vm ? __ldg(base + (long long)p * G.GT) : 0u;
+		const u32 B = Bn;
+		Bn = vm && p > 0 ? __ldg(base + (long long)(p - 1) * G.GT) : 0u;
 		u32 member = vm & ~sig;
 		u32 ones = B & member, zeros = member & ~B;
 		u32 n1 = __popc(ones), nz = __popc(zeros), nr = __popc(sig);
 		const int j = S->chunk_of[c][l][p];
 		if (j > jcut || (j == jcut && i >= icut))
 			break; // block-uniform: this plane and the ones below it are cut
-		u64 packed = (u64)nz | ((u64)n1 << 21) | ((u64)nr << 42), tot;
-		u64 ex = block_exscan_u64(packed, ws, &tot);
+		// zeros and ones before this group inside the tile; the refinement bits follow from them: the groups in front of a
+		// valid group are all full, so zeros + ones + refinement bits in front of it = 32 per group
+		const u32 ex = tile_exscan_2x16(nz | (n1 << 16), ws, p & 1);
+		const u32 ex_z = ex & 0xffffu, ex_1 = ex >> 16, ex_r = 32u * threadIdx.x - ex_z - ex_1;
 		const int e = S->ebase[j] + i;
 		if (n1) {
-			u32 zb = ez[e] + (u32)(ex & 0x1fffffu);
-			u32 tb = e1[e] + C->tok_adj[j] + (u32)((ex >> 21) & 0x1fffffu);
+			u32 zb = ez[e] + ex_z;
+			u32 tb = e1[e] + C->tok_adj[j] + ex_1;
 			// the signs of the ones, in token order: gathered in the walk over the ones (cheaper than a parallel-suffix
 			// compress of the sign word for the two or three ones a group has per plane)
 			u32 o = ones, t = tb, sb = 0;
@@ -324,7 +360,7 @@ __global__ void __launch_bounds__(TG) enc_emit_kernel(const __grid_constant__ Ge
 			bits_or(signbuf, tb, sb, (int)n1);
 		}
 		if (nr && j < jcut) { // the refinement block of chunk jcut lies behind all of its tokens: behind the cut
-			u32 rb = er[e] + (u32)(ex >> 42);
+			u32 rb = er[e] + ex_r;
 			bits_or(refbuf, rb, bit_compress(B, sig), (int)nr);
 		}
 		sig |= B;
