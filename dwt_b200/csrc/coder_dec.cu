@@ -1733,9 +1733,9 @@ __device__ __forceinline__ u32 group_valid_mask(const Geom &G, int l, int g)
 
 __device__ __forceinline__ int level_of_tile(const Geom &G, int tile)
 {
-	int l = 0;
-	while (l + 1 < G.levels && G.tbase[l + 1] <= tile)
-		++l;
+	int l = G.levels - 1; // from the top: three quarters of the tiles belong to the finest level
+	while (l > 0 && G.tbase[l] > tile)
+		--l;
 	return l;
 }
 
@@ -1817,7 +1817,7 @@ __global__ void __launch_bounds__(1024) dec_tilescan_kernel(const __grid_constan
 __global__ void __launch_bounds__(TG) dec_deposit_kernel(const __grid_constant__ Geom G, const __grid_constant__ DecBuffers B,
                                                           int nchunks, int depth)
 {
-	__shared__ u64 ws[32];
+	__shared__ __align__(16) u32 ws[2][8];
 	__shared__ u32 acc[2];
 	const int c = blockIdx.y, tile = blockIdx.x;
 	const int l = level_of_tile(G, tile);
@@ -1836,8 +1836,8 @@ __global__ void __launch_bounds__(TG) dec_deposit_kernel(const __grid_constant__
 	const u32 s = vm ? sig[gi] : 0u;
 	const u32 member = vm & ~s;
 	const u32 nm = __popc(member), nr = __popc(s);
-	u64 tot;
-	const u64 ex = block_exscan_u64((u64)nm | ((u64)nr << 32), ws, &tot); // syncs: acc is initialised behind it
+	const u32 ex2 = tile_exscan_2x16(nm | (nr << 16), ws, 0); // syncs: acc is initialised behind it
+	const u64 ex = (u64)(ex2 & 0xffffu) | ((u64)(ex2 >> 16) << 32);
 	const size_t ti = 2 * ((size_t)c * G.tbase[G.levels] + tile);
 	u32 Bw = 0;
 	if (vm) {

@@ -214,4 +214,34 @@ __device__ __forceinline__ u64 block_exscan_u64(u64 v, u64 *warp_sums, u64 *tota
 	return base + inc - v;
 }
 
+// exclusive scan over the 256 threads of a tile of two counts packed as lo | hi << 16 (tile totals < 2^16): one warp
+// shuffle scan, the eight warp totals through shared memory, ONE block barrier (`ws` holds two sets of warp totals used
+// alternately by consecutive calls: a warp can only be one call ahead of the slowest).  The generic 64-bit
+// block_exscan_u64 cost a quarter of enc_emit's instructions.
+__device__ __forceinline__ u32 tile_exscan_2x16(u32 v, u32 (*ws)[8], int parity)
+{
+	static_assert(DWT_TILE_GROUPS == 256, "eight warps per tile");
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	u32 inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const u32 t = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= d)
+			inc += t;
+	}
+	if (lane == 31)
+		ws[parity][wid] = inc;
+	__syncthreads();
+	const uint4 a = *reinterpret_cast<const uint4 *>(&ws[parity][0]), b = *reinterpret_cast<const uint4 *>(&ws[parity][4]);
+	u32 base = 0;
+	base += wid > 0 ? a.x : 0u;
+	base += wid > 1 ? a.y : 0u;
+	base += wid > 2 ? a.z : 0u;
+	base += wid > 3 ? a.w : 0u;
+	base += wid > 4 ? b.x : 0u;
+	base += wid > 5 ? b.y : 0u;
+	base += wid > 6 ? b.z : 0u;
+	return base + inc - v;
+}
+
 #endif // __CUDACC__
