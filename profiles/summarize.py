@@ -1,7 +1,8 @@
-"""Turn ncu exports into the tables of profiles/r01_summary.md (run here, no GPU needed).
+"""Turn ncu exports into the tables of profiles/rNN_summary.md (run here, no GPU needed).
 
     python profiles/summarize.py launches gpurun_out/r01_launches.csv [frames_total]
     ncu -i gpurun_out/r01_top.ncu-rep --page raw --csv > /tmp/top_raw.csv && python profiles/summarize.py kernels /tmp/top_raw.csv
+    python profiles/summarize.py traffic /tmp/top_raw.csv "<source note>" > profiles/traffic.json   # DRAM bytes per stage
 """
 import collections
 import csv
@@ -77,8 +78,41 @@ def kernels(path):
         print("| %s %s | %s |" % (short(r[ik]), r[ig] if ig >= 0 else "", " | ".join(cells)))
 
 
+def stage_of(name):
+    n = short(name)
+    for prefix, stage in (("lift_fwd", "lift_fwd"), ("lift_tail_fwd", "lift_fwd"), ("lift_inv", "lift_inv"), ("lift_tail_inv", "lift_inv"),
+                          ("linearize", "linearize"), ("reconstruct", "reconstruct"), ("enc_", "enc_coder"), ("dec_", "dec_coder")):
+        if n.startswith(prefix):
+            return stage
+    return None
+
+
+def traffic(path, note):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the launches of one frame (raw page of ONE encode + decode), per stage"""
+    import json
+    rows = list(csv.reader(open(path)))
+    hdr, unit_row = rows[0], rows[1]
+    ik = hdr.index("Kernel Name")
+    out = collections.OrderedDict()
+    for r in rows[2:]:
+        st = stage_of(r[ik])
+        if not st:
+            continue
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(key)
+            v = float(r[i].replace(",", ""))
+            tot += v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit_row[i], 1.0)
+        out[st] = out.get(st, 0.0) + tot
+    d = collections.OrderedDict((k, int(v)) for k, v in out.items())
+    d["source"] = note
+    print(json.dumps(d, indent=1))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], float(sys.argv[3]) if len(sys.argv) > 3 else 1.0)
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
     else:
         kernels(sys.argv[2])
