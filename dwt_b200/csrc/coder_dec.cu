@@ -53,6 +53,12 @@ __device__ __forceinline__ void load_slice(const u32 *__restrict__ stream, u64 e
 	w1 = lo < end_bits + 64 ? __ldg((const u64 *)stream + slice + 1) : 0ull;
 }
 
+__device__ __forceinline__ u64 shfl_up_u64(u64 v, int d)
+{
+	const u32 lo = __shfl_up_sync(0xffffffffu, (u32)v, d), hi = __shfl_up_sync(0xffffffffu, (u32)(v >> 32), d);
+	return (u64)lo | ((u64)hi << 32);
+}
+
 __device__ __forceinline__ u64 bits_from(u64 a, u64 b, int d) // 64 stream bits from offset d (0..63) of the pair
 {
 	return d ? (a >> d) | (b << (64 - d)) : a;
@@ -523,37 +529,45 @@ __global__ void __launch_bounds__(128) dec_extend_find_kernel(const u32 *__restr
 	list[atomicAdd(list_count, 1u)] = make_uint2(w, st);
 }
 
-// part 2, one CTA per listed window.  A lone thread that walks a window with full bookkeeping needs ~0.18 ms; here thread 0
-// only follows the token POSITIONS from slice to slice (a few instructions per token) and leaves every slice's entry state
-// in shared memory, then all 128 threads count what their slice consumes from its entry state, and a block scan turns the
-// counts into the chain's tables.  Same tables as walk_window_chain, a fraction of its latency.
-__global__ void __launch_bounds__(WS) dec_extend_walk_kernel(const u32 *__restrict__ stream, u64 end_bits,
-                                                              const u32 *__restrict__ toklut, u32 *E, ulonglong2 *P, u32 *TK,
-                                                              u32 *winX_out, ulonglong2 *winPT, u32 *winTT,
-                                                              unsigned char *changed_out, const u32 *__restrict__ list_count,
-                                                              const uint2 *__restrict__ list)
+// part 2, one WARP per listed window.  A lone thread that walks a window with full bookkeeping needs ~0.18 ms; here lane 0
+// only follows the token POSITIONS from slice to slice (a few instructions per token, ~17 us per window) and leaves every
+// slice's entry state in shared memory, then the 32 lanes count what four slices each consume from their entry states, and
+// a warp scan turns the counts into the chain's tables.  Same tables as walk_window_chain.  The serial walk is the
+// latency of a pass, so what matters is how many windows are walked at the same time: a warp per window keeps up to 64 of
+// them on an SM (a CTA per window, the first version, kept 4 and a pass took 85 - 290 us).
+constexpr int XW_WARPS = 8;
+
+__global__ void __launch_bounds__(XW_WARPS * 32) dec_extend_walk_kernel(const u32 *__restrict__ stream, u64 end_bits,
+                                                                        const u32 *__restrict__ toklut, u32 *E, ulonglong2 *P,
+                                                                        u32 *TK, u32 *winX_out, ulonglong2 *winPT, u32 *winTT,
+                                                                        unsigned char *changed_out,
+                                                                        const u32 *__restrict__ list_count,
+                                                                        const uint2 *__restrict__ list)
 {
+	static_assert(WS == 128, "four slices per lane");
 	__shared__ u32 lut[1 << LUT_BITS];
-	__shared__ u64 sw[WS + 1];
-	__shared__ unsigned short sentry[WS];
-	__shared__ u64 ws[32];
+	__shared__ u64 sw_all[XW_WARPS][WS + 1];
+	__shared__ unsigned short sentry_all[XW_WARPS][WS];
 	const u32 count = *list_count;
-	if (blockIdx.x >= count)
+	if (blockIdx.x * XW_WARPS >= count)
 		return;
-	const int tid = threadIdx.x;
-	for (int i = tid; i < (1 << LUT_BITS); i += WS)
+	for (int i = threadIdx.x; i < (1 << LUT_BITS); i += XW_WARPS * 32)
 		lut[i] = __ldg(toklut + i);
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	u64 *sw = sw_all[wid];
+	unsigned short *sentry = sentry_all[wid];
 	unsigned short *E16 = reinterpret_cast<unsigned short *>(E), *TK16 = reinterpret_cast<unsigned short *>(TK);
 	u64 *P64 = reinterpret_cast<u64 *>(P);
-	for (u32 item = blockIdx.x; item < count; item += gridDim.x) {
+	for (u32 item = blockIdx.x * XW_WARPS + wid; item < count; item += gridDim.x * XW_WARPS) {
 		const uint2 it = list[item];
 		const u32 w = it.x;
 		const u64 gs0 = (u64)w * WS;
-		__syncthreads(); // the table is staged; the previous item's shared arrays are no longer read
-		for (int i = tid; i < WS + 1; i += WS)
+		__syncwarp(); // the previous item's shared arrays are no longer read
+		for (int i = lane; i < WS + 1; i += 32)
 			sw[i] = ((gs0 + i) << 6) < end_bits + 128 ? __ldg((const u64 *)stream + gs0 + i) : 0ull;
-		__syncthreads();
-		if (tid == 0) { // the serial part: positions only
+		__syncwarp();
+		if (lane == 0) { // the serial part: positions only
 			u32 state = it.y;
 			for (int t = 0; t < WS; ++t) {
 				sentry[t] = (unsigned short)state;
@@ -562,25 +576,47 @@ __global__ void __launch_bounds__(WS) dec_extend_walk_kernel(const u32 *__restri
 				state = x == PDEAD ? 1u : x; // a dead chain restarts at class 1's seed offset with order 0 (dec_scan_kernel)
 			}
 		}
-		__syncthreads();
-		const u64 gs = gs0 + tid;
-		const u32 entry = sentry[tid];
-		u64 mem;
-		u32 tok;
-		const u64 b2 = (gs << 6) < end_bits + 64 ? sw[tid + 1] : 0ull;
-		const u32 x = slice_walk_lut(lut, sw[tid], b2, clamp_avail(end_bits, gs << 6), entry, mem, tok);
-		if (x == PDEAD)
-			mem += DEATH;
-		u64 tot_m, tot_t;
-		const u64 pm = block_exscan_u64(mem, ws, &tot_m);
-		const u64 pt = block_exscan_u64((u64)tok, ws, &tot_t);
-		E16[2 * gs + 1] = (unsigned short)entry;
-		P64[2 * gs + 1] = pm;
-		TK16[2 * gs + 1] = (unsigned short)pt;
-		if (tid == WS - 1) {
-			reinterpret_cast<unsigned short *>(winX_out)[2 * w + 1] = (unsigned short)x;
-			reinterpret_cast<u64 *>(winPT)[2 * w + 1] = tot_m;
-			reinterpret_cast<unsigned short *>(winTT)[2 * w + 1] = (unsigned short)tot_t;
+		__syncwarp();
+		// lane l counts slices 4 l .. 4 l + 3 from their entry states
+		u64 mem[4], msum = 0;
+		u32 tok[4], tsum = 0, xlast = 0;
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const int t = 4 * lane + q;
+			const u64 gs = gs0 + t;
+			const u64 b2 = (gs << 6) < end_bits + 64 ? sw[t + 1] : 0ull;
+			xlast = slice_walk_lut(lut, sw[t], b2, clamp_avail(end_bits, gs << 6), (u32)sentry[t], mem[q], tok[q]);
+			if (xlast == PDEAD)
+				mem[q] += DEATH;
+			msum += mem[q];
+			tsum += tok[q];
+		}
+		u64 minc = msum;
+		u32 tinc = tsum;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const u64 tm = shfl_up_u64(minc, d);
+			const u32 tt = __shfl_up_sync(0xffffffffu, tinc, d);
+			if (lane >= d) {
+				minc += tm;
+				tinc += tt;
+			}
+		}
+		u64 pm = minc - msum;
+		u32 pt = tinc - tsum;
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const u64 gs = gs0 + 4 * lane + q;
+			E16[2 * gs + 1] = sentry[4 * lane + q];
+			P64[2 * gs + 1] = pm;
+			TK16[2 * gs + 1] = (unsigned short)pt;
+			pm += mem[q];
+			pt += tok[q];
+		}
+		if (lane == 31) {
+			reinterpret_cast<unsigned short *>(winX_out)[2 * w + 1] = (unsigned short)xlast;
+			reinterpret_cast<u64 *>(winPT)[2 * w + 1] = minc;
+			reinterpret_cast<unsigned short *>(winTT)[2 * w + 1] = (unsigned short)tinc;
 			changed_out[w] = 1;
 		}
 	}
@@ -871,9 +907,15 @@ __device__ __forceinline__ void load_super(const DecSuper *src, DecSuper &S)
 #ifdef DWT_RESOLVE_PROFILE
 #define RP_BEGIN() const long long rp_t0 = clock64()
 #define RP_END(slot) rp_cyc[slot] += clock64() - rp_t0
+#define RP_STAT(stmt) stmt
+#define RP_HIST(t) hist[t]
+#define RP_REASON(t) reason[t]
 #else
 #define RP_BEGIN()
 #define RP_END(slot)
+#define RP_STAT(stmt)
+#define RP_HIST(t) 0u
+#define RP_REASON(t) 0u
 #endif
 
 __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__ Geom G, int nchunks,
@@ -914,7 +956,9 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 	bool stopped = false;
 	u64 rank_base = 0;
 	u32 nseg = 0, nbulk = 0, slow_entries = 0, exact_steps = 0, n_super = 0, n_window = 0, n_search = 0;
+#ifdef DWT_RESOLVE_PROFILE
 	u32 hist[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, reason[4] = {0, 0, 0, 0};
+#endif
 	int tripped = 0;
 	// every pass of the loops below moves on by at least one window or ends the chunk; the guard only exists so that a
 	// bug can never hang the device
@@ -982,7 +1026,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 			u32 guard = 0;
 			bool long_walk = false; // the walk has already crossed a window without joining: no point in careful first steps
 			++slow_entries;
-			++reason[0];
+			RP_STAT(++reason[0]);
 			while (event == EV_NONE) {
 				if (++guard > guard_max) {
 					tripped = 1;
@@ -1017,7 +1061,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 					}
 					const u32 seg_state = (u32)d | ((u32)k << 6);
 					const u64 seg_cum0 = cum;
-					const u32 steps0 = exact_steps;
+					RP_STAT(const u32 steps0 = exact_steps;)
 					int i = i0, m = WS, qm = 0;
 					u64 pm = 0;   // members of class qm before the join slice
 					u32 tkm = 0;  // tokens of both classes before the join slice
@@ -1155,6 +1199,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 					}
 					++nseg;
 					RP_END(0);
+#ifdef DWT_RESOLVE_PROFILE
 					{
 						const u32 n = exact_steps - steps0;
 						const int b = n <= 2 ? (int)n : (n <= 4 ? 3 : (n <= 8 ? 4 : (n <= 16 ? 5 : (n <= 32 ? 6 : (n <= 64 ? 7 : 8)))));
@@ -1163,11 +1208,12 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 							hist[t] += b == t;
 						hist[9] += m < WS;
 					}
+#endif
 					if (event != EV_NONE)
 						break;
 					if (m == WS) { // the window ended before the chain joined: go on exactly in the next one
 						long_walk = true;
-						++reason[3];
+						RP_STAT(++reason[3]);
 						gs = ((u64)cw + 1) * WS;
 						continue;
 					}
@@ -1348,7 +1394,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 						d = (int)(carry_state & 63u);
 						k = (int)(carry_state >> 6);
 						++slow_entries;
-						++reason[1];
+						RP_STAT(++reason[1]);
 						continue;
 					}
 					const u32 m_f = __shfl_sync(FULL, (u32)my.m, f), qm_f = __shfl_sync(FULL, (u32)my.qm, f);
@@ -1360,7 +1406,7 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 						d = (int)(entry_f & 63u);
 						k = (int)(entry_f >> 6);
 						++slow_entries;
-						++reason[2];
+						RP_STAT(++reason[2]);
 						continue;
 					}
 					if (lane == 0) {
@@ -1536,9 +1582,9 @@ __global__ void __launch_bounds__(32) dec_resolve_kernel(const __grid_constant__
 		st->n_window = n_window;
 		st->n_search = n_search;
 		for (int t = 0; t < 10; ++t)
-			st->dbg_hist[t] = hist[t];
+			st->dbg_hist[t] = RP_HIST(t);
 		for (int t = 0; t < 4; ++t)
-			st->dbg_reason[t] = reason[t];
+			st->dbg_reason[t] = RP_REASON(t);
 		st->guard_tripped = tripped;
 #ifdef DWT_RESOLVE_PROFILE
 		printf("resolver cycles: exact-step visits %lld, super rounds %lld, window rounds %lld, end searches %lld, total %lld\n", rp_cyc[0],
@@ -1939,12 +1985,14 @@ int dec_run(const Geom &g, const Sched &hs, const DecBuffers &b_in, int nchunks,
 		int passes = forced >= 0 ? forced : (b.in_flight >= 4 ? 0 : lineage_passes(g, b.nwin));
 		if (passes > DWT_DEC_MAX_LINEAGE)
 			passes = DWT_DEC_MAX_LINEAGE;
-		const unsigned ext_grid = (unsigned)(b.nwin < 4u * (u32)dwt_device_sms() ? b.nwin : 4u * (u32)dwt_device_sms());
+		// a warp per listed window, eight per CTA; CTAs without a window leave at once
+		const u32 ext_want = (b.nwin + XW_WARPS - 1) / XW_WARPS, ext_cap = 8u * (u32)dwt_device_sms();
+		const unsigned ext_grid = (unsigned)(ext_want < ext_cap ? ext_want : ext_cap);
 		for (int pass = 0; pass < passes; ++pass) {
 			u32 *cnt = b.ext_count + pass; // one counter per pass, zeroed by the caller
 			dec_extend_find_kernel<<<(b.nwin + 127) / 128, 128, 0, st>>>(b.stream, b.end_bits, b.nwin, b.E, xin, xout, cin, cout, cnt,
 			                                                             b.ext_list);
-			dec_extend_walk_kernel<<<ext_grid, WS, 0, st>>>(b.stream, b.end_bits, b.toklut, b.E, b.P, b.TK, xout, b.winPT, b.winTT, cout,
+			dec_extend_walk_kernel<<<ext_grid, XW_WARPS * 32, 0, st>>>(b.stream, b.end_bits, b.toklut, b.E, b.P, b.TK, xout, b.winPT, b.winTT, cout,
 			                                                cnt, b.ext_list);
 			*launches += 2;
 			u32 *t = xin;

@@ -234,3 +234,43 @@ def test_hilbert_ballot_and_tma_paths_agree(codec, oracle):
             os.environ.pop("DWT_HILBERT", None)
         else:
             os.environ["DWT_HILBERT"] = old
+
+
+def test_lineage_passes_on_small_streams(oracle):
+    """the decoder's lineage passes (dec_extend_find / dec_extend_walk: one warp per window) only run on images of 20 Mpixel
+    and more by default; DWT_LINEAGE forces them (read once per process, hence the child process), so that small streams --
+    sparse images with long runs, noise, truncated and corrupted streams -- exercise them against the oracle as well"""
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import dwt_b200 as D
+from oracle import pyoracle as O
+cod = D.Codec()
+rng = np.random.default_rng(7)
+bad = 0
+for (w, h, kind, seed) in [(1920, 1080, "photo", 1), (1024, 1024, "noise", 2), (1500, 900, "sparse", 3), (640, 360, "smooth", 4)]:
+    if kind == "sparse":    # long zero runs, high Rice orders: where seeded chains synchronise slowly
+        img = (rng.integers(0, 256, (h, w, 3)) * (rng.random((h, w, 3)) < 0.03)).astype(np.uint8)
+    elif kind == "smooth":  # streams that are mostly refinement bits
+        img = np.clip(np.cumsum(rng.integers(-2, 3, (h, w, 3)), axis=1) + 128, 0, 255).astype(np.uint8)
+    else:
+        img = O.synth(w, h, kind, seed)
+    s, _ = O.encode(img)
+    for cut in (len(s), len(s) // 2, len(s) // 7, 4096):
+        t = s[:cut]
+        a, b = cod.decode(t), O.decode(t)
+        ok = (a is None and b is None) or (a is not None and b is not None and a.shape == b.shape and np.array_equal(a, b))
+        bad += not ok
+    t = bytearray(s)
+    for _ in range(20):
+        t[int(rng.integers(64, len(t)))] ^= 1 << int(rng.integers(0, 8))
+    a, b = cod.decode(bytes(t)), O.decode(bytes(t))
+    ok = (a is None and b is None) or (a is not None and b is not None and a.shape == b.shape and np.array_equal(a, b))
+    bad += not ok
+print("BAD", bad)
+''' % ROOT
+    for passes in ("3", "6"):
+        env = dict(os.environ, DWT_LINEAGE=passes)
+        r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert "BAD 0" in r.stdout, (passes, r.stdout[-500:], r.stderr[-500:])
