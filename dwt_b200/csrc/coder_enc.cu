@@ -363,6 +363,12 @@ __device__ __forceinline__ void load_tokens(const u32 *__restrict__ Z, const u32
 	const u32 spec = (specbuf[t0 >> 5] >> (t0 & 31)) & 0xffu;
 	if (signbuf)
 		T.signs = (signbuf[t0 >> 5] >> (t0 & 31)) & 0xffu;
+	if (spec == 0 && t0 + TPT < ntok) { // eight ordinary tokens (a one and its sign each): what all but ~300 threads of a frame hold
+#pragma unroll
+		for (int k = 0; k < TPT; ++k)
+			T.v[k] = z[k + 1] - z[k];
+		return;
+	}
 #pragma unroll
 	for (int k = 0; k < TPT; ++k) {
 		u32 t = t0 + k;
@@ -375,9 +381,27 @@ __device__ __forceinline__ void load_tokens(const u32 *__restrict__ Z, const u32
 }
 
 // run the tokens of one thread from order k; returns the order after them and adds their bit lengths
-__device__ __forceinline__ int run_tokens(const Tok &T, int k, u32 *bits)
+__device__ __forceinline__ int run_tokens(const Tok &T, int k, u32 *bits, u32 *longest = nullptr)
 {
 	u32 sum = 0;
+	if (T.kinds == 0) { // ordinary tokens only: no kind to look at
+		u32 mx = 0;
+#pragma unroll
+		for (int i = 0; i < TPT; ++i) {
+			const int e = vli_e(T.v[i], k);
+			const u32 len = (u32)(2 * e - k + 2);
+			sum += len;
+			mx = max(mx, len);
+			k = vli_next(e);
+		}
+		if (bits)
+			*bits = sum;
+		if (longest)
+			*longest = mx;
+		return k;
+	}
+	if (longest)
+		*longest = 64;
 #pragma unroll
 	for (int i = 0; i < TPT; ++i) {
 		u32 kind = (T.kinds >> (2 * i)) & 3u;
@@ -576,8 +600,8 @@ __global__ void __launch_bounds__(256) enc_scatter_kernel(const u32 *__restrict_
 	Tok T;
 	load_tokens(Z, specbuf, signbuf, ntok, t0, T);
 	int k = thr_state[(size_t)tile * 256 + threadIdx.x];
-	u32 mybits;
-	run_tokens(T, k, &mybits);
+	u32 mybits, longest;
+	run_tokens(T, k, &mybits, &longest);
 	u64 tot;
 	u64 off = prefix_bits + tile_bitbase[tile] + block_exscan_u64(mybits, ws, &tot);
 	// chunk of the tile's first token: one binary search per block, the threads only walk forward from it
@@ -594,6 +618,34 @@ __global__ void __launch_bounds__(256) enc_scatter_kernel(const u32 *__restrict_
 		next_start = j < J ? C->tok_start[j + 1] : 0xffffffffu;
 	}
 	u64 ref_start = C->ref_start[j];
+	if (T.kinds == 0 && longest <= 24 && (j >= J || t0 + TPT <= next_start)) {
+		// the common case: eight ordinary tokens of one chunk, no code longer than 24 bits.  Their codes are contiguous in
+		// the stream: a 64-bit shift register, one atomic per 32-bit word that fills up
+		const u64 pos = off + ref_start;
+		u64 w = pos >> 5;
+		int fill = (int)(pos & 31);
+		u64 acc = 0;
+#pragma unroll
+		for (int i = 0; i < TPT; ++i) {
+			const u32 x = T.v[i] + (1u << k); // vli.h:67-84 in closed form: e - k zeros, a one, the e low bits of x, then the sign
+			const int e = ilog2_u32(x);
+			const int nz = e - k;
+			const u32 code = ((((x ^ (1u << e)) << 1) | 1u) << nz) | (((T.signs >> i) & 1u) << (nz + 1 + e));
+			acc |= (u64)code << fill;
+			fill += nz + e + 2;
+			k = vli_next(e);
+			if (fill >= 32) {
+				if ((w << 5) < limit_bits && (u32)acc)
+					atomicOr(out + w, (u32)acc);
+				acc >>= 32;
+				fill -= 32;
+				++w;
+			}
+		}
+		if (fill > 0 && (w << 5) < limit_bits && (u32)acc)
+			atomicOr(out + w, (u32)acc);
+		return;
+	}
 	// the codes of a thread's tokens are contiguous in the stream (except across a chunk's refinement block): they are
 	// gathered in a 64-bit window and sent with one atomic per 32-bit word instead of one or two per token
 	u64 acc = 0, acc_pos = 0;
