@@ -219,8 +219,8 @@ __device__ __forceinline__ u32 slice_walk_lut(const u32 *lut, u64 a, u64 b, int 
 			mem += msum;
 			return PDEAD;
 		}
-		const u64 w = bits_from(a, b, d);
-		const u32 payload = (u32)(w >> (u + 1)) & ((1u << e) - 1u);
+		// the payload lies inside the 32-bit window for all but the long runs: no 64-bit shifts then
+		const u32 payload = (L <= 32 ? bits >> (u + 1) : (u32)(bits_from(a, b, d) >> (u + 1))) & ((1u << e) - 1u);
 		mem += (u64)((1u << e) - (1u << k)) + payload + 1ull;
 		++ntok;
 		k = e >= 2 ? e - 2 : 0;
@@ -430,8 +430,8 @@ __device__ __forceinline__ void walk_window_chain(const u32 *__restrict__ stream
 			if (e > 31 || d + L > avail) {
 				dead = true;
 			} else {
-				const u64 wv = bits_from(a, b, d);
-				const u32 payload = (u32)(wv >> (u + 1)) & ((1u << e) - 1u);
+				// the payload lies inside the 32-bit window for all but the long runs: no 64-bit shifts then
+				const u32 payload = (L <= 32 ? bits >> (u + 1) : (u32)(bits_from(a, b, d) >> (u + 1))) & ((1u << e) - 1u);
 				m += (u64)((1u << e) - (1u << k)) + payload + 1ull;
 				++n;
 				k = e >= 2 ? e - 2 : 0;
@@ -1638,80 +1638,61 @@ __global__ void __launch_bounds__(128) dec_bulk_kernel(const __grid_constant__ D
 // ---------------------------------------------------------------------------------------------- emit
 
 // rank-space bits of consecutive tokens mostly fall into the same 32-bit word: they are collected in registers and
-// sent with one atomic per word
+// sent with one atomic per word.  All of a slice's bookkeeping is 32 bit: a chunk has fewer than 2^31 members, ranks are
+// kept relative to the word the chunk's rank space starts in (the callers pass the two bit vectors already offset by that
+// word), and a token that fits a 32-bit stream window together with its sign bit (all but the long runs) is taken apart
+// without 64-bit shifts.
 struct RankAcc {
-	u64 word;
+	u32 word; // relative to the chunk's first rank word
 	u32 ones, signs;
 };
 
-__device__ __forceinline__ void acc_flush(RankAcc &A, u32 *ones_rank, u32 *sign_rank)
+__device__ __forceinline__ void acc_flush(RankAcc &A, u32 *ones_w, u32 *sign_w)
 {
 	if (A.ones)
-		atomicOr(ones_rank + A.word, A.ones);
+		atomicOr(ones_w + A.word, A.ones);
 	if (A.signs)
-		atomicOr(sign_rank + A.word, A.signs);
+		atomicOr(sign_w + A.word, A.signs);
 	A.ones = A.signs = 0;
 }
 
-// OR a 16-bit member mask (ones / signs) into rank space at rank rk
-__device__ __forceinline__ void acc_mask(RankAcc &A, u64 rk, u32 ones, u32 signs, u32 *ones_rank, u32 *sign_rank)
+// ones and signs of the tokens that start in one slice; false when the chain ends here.  T = members the chunk's own
+// tokens cover, cum (< T on entry) = members consumed so far, r0 = bit of the chunk's first rank inside its word.
+// (A table-driven walk like the scan's was measured here and lost: staging 32 KB per CTA and the divergence between
+// table and generic steps cost more than the per-token work they save.)
+__device__ __forceinline__ bool emit_slice(u64 a, u64 b, int avail, u32 T, u32 r0, int &d, int &k, u32 &cum, RankAcc &A,
+                                           u32 *ones_w, u32 *sign_w)
 {
-	const u64 w = rk >> 5;
-	const int sh = (int)(rk & 31);
-	if (w != A.word) {
-		acc_flush(A, ones_rank, sign_rank);
-		A.word = w;
-	}
-	A.ones |= ones << sh;
-	A.signs |= signs << sh;
-	if (sh > 16 && (ones >> (32 - sh))) { // the mask runs over into the next word
-		acc_flush(A, ones_rank, sign_rank);
-		A.word = w + 1;
-		A.ones = ones >> (32 - sh);
-		A.signs = signs >> (32 - sh);
-	}
-}
-
-// ones and signs of the tokens that start in one slice; false when the chain ends here.
-// lut: the order-0 token table (both words) or nullptr
-__device__ __forceinline__ bool emit_slice(const u32 *lut, u64 a, u64 b, int avail, u64 T, u64 base, int &d, int &k, u64 &cum,
-                                           RankAcc &A, u32 *ones_rank, u32 *sign_rank)
-{
-	const bool lut_ok = lut != nullptr && avail >= 64 + LUT_BITS + 4;
 	while (d < 64) {
-		if (k == 0 && lut_ok) {
-			const u32 idx = window32(a, b, d) & ((1u << LUT_BITS) - 1u);
-			const u32 t = lut[idx];
-			const u32 mem = t >> 11;
-			if ((t & 15u) && d + (int)((t >> 4) & 15u) < 64 && cum + mem <= T) { // all of them ones of this chunk
-				const u32 mk = lut[(1 << LUT_BITS) + idx];
-				acc_mask(A, base + cum, mk & 0xffffu, mk >> 16, ones_rank, sign_rank);
-				cum += mem;
-				d += (int)(t & 15u);
-				continue;
-			}
-		}
-		const u64 w = bits_from(a, b, d);
-		const u32 lo = (u32)w;
+		const u32 lo = window32(a, b, d);
 		const int u = lo ? __ffs((int)lo) - 1 : 32;
 		const int e = k + u;
 		const int L = u + 1 + e;
 		if (e > 31 || d + L > avail)
 			return false;
-		const u32 payload = (u32)(w >> (u + 1)) & ((1u << e) - 1u);
-		const u64 one = cum + (u64)((1u << e) - (1u << k)) + payload;
-		if (one >= T)
-			return false;
-		const u64 rk = base + one;
-		if ((rk >> 5) != A.word) {
-			acc_flush(A, ones_rank, sign_rank);
-			A.word = rk >> 5;
+		u32 payload, sign;
+		if (L < 32) {
+			payload = (lo >> (u + 1)) & ((1u << e) - 1u);
+			sign = (lo >> L) & 1u;
+		} else {
+			const u64 w = bits_from(a, b, d);
+			payload = (u32)(w >> (u + 1)) & ((1u << e) - 1u);
+			sign = (u32)(w >> L) & 1u;
 		}
-		const u32 bit = 1u << (rk & 31);
+		const u32 n = (1u << e) - (1u << k) + payload; // the run in front of this one (< 2^32)
+		if (n >= T - cum)
+			return false;
+		const u32 one = cum + n;
+		const u32 rel = r0 + one;
+		if ((rel >> 5) != A.word) {
+			acc_flush(A, ones_w, sign_w);
+			A.word = rel >> 5;
+		}
+		const u32 bit = 1u << (rel & 31);
 		A.ones |= bit;
 		if (d + L + 1 > avail)
 			return false;
-		if ((w >> L) & 1ull)
+		if (sign)
 			A.signs |= bit;
 		cum = one + 1;
 		d += L + 1;
@@ -1722,47 +1703,49 @@ __device__ __forceinline__ bool emit_slice(const u32 *lut, u64 a, u64 b, int ava
 
 __global__ void __launch_bounds__(WS) dec_emit_kernel(const __grid_constant__ DecBuffers B)
 {
-	// (a table-driven walk like the scan's was measured here and lost: staging 32 KB per CTA and the divergence between
-	// table and generic steps cost more than the per-token work they save; emit_slice still takes a table pointer)
-	const u32 *lut = nullptr;
 	const u32 nseg = B.state->nseg;
 	const int i = threadIdx.x;
 	for (u32 sidx = blockIdx.x; sidx < nseg; sidx += gridDim.x) {
 		const DecSeg s = B.seg[sidx];
 		const DecChunk ck = B.chunks[s.j];
 		const int m = s.m;
-		const u64 T = ck.T;
+		const u32 T = ck.T;
 		const u64 base = ck.rank_base + ck.r0;
+		const u32 r0 = (u32)(base & 31u);
+		u32 *ones_w = B.ones_rank + (base >> 5), *sign_w = B.sign_rank + (base >> 5);
 		const u64 wbase = (u64)s.w * WS;
 		if (i == s.i0 && m > i) {
 			// exact steps through the slices in front of the join
 			int d = (int)(s.state & 63u), k = (int)(s.state >> 6);
-			u64 cum = s.cum0;
-			RankAcc A = {~0ull, 0u, 0u};
-			for (int ii = i; ii < m; ++ii) {
-				u64 a, b;
-				const u64 gs = wbase + ii;
-				load_slice(B.stream, B.end_bits, gs, a, b);
-				if (!emit_slice(lut, a, b, clamp_avail(B.end_bits, gs << 6), T, base, d, k, cum, A, B.ones_rank, B.sign_rank))
-					break;
-				d -= 64;
+			u32 cum = s.cum0;
+			RankAcc A = {~0u, 0u, 0u};
+			if (cum < T) {
+				for (int ii = i; ii < m; ++ii) {
+					u64 a, b;
+					const u64 gs = wbase + ii;
+					load_slice(B.stream, B.end_bits, gs, a, b);
+					if (!emit_slice(a, b, clamp_avail(B.end_bits, gs << 6), T, r0, d, k, cum, A, ones_w, sign_w))
+						break;
+					d -= 64;
+				}
 			}
-			acc_flush(A, B.ones_rank, B.sign_rank);
+			acc_flush(A, ones_w, sign_w);
 		} else if (i >= m) {
 			const u64 gs = wbase + i;
 			const u32 e = (B.E[gs] >> (16 * s.qm)) & 0xffffu;
 			if (e == PDEAD)
 				continue;
 			const ulonglong2 pi = B.P[gs], pm = B.P[wbase + m];
-			u64 cum = (u64)s.cum_m + (s.qm ? pi.y - pm.y : pi.x - pm.x);
-			if (cum >= T)
+			const u64 cum64 = (u64)s.cum_m + (s.qm ? pi.y - pm.y : pi.x - pm.x);
+			if (cum64 >= T)
 				continue;
+			u32 cum = (u32)cum64;
 			u64 a, b;
 			load_slice(B.stream, B.end_bits, gs, a, b);
 			int d = (int)(e & 63u), k = (int)(e >> 6);
-			RankAcc A = {~0ull, 0u, 0u};
-			emit_slice(lut, a, b, clamp_avail(B.end_bits, gs << 6), T, base, d, k, cum, A, B.ones_rank, B.sign_rank);
-			acc_flush(A, B.ones_rank, B.sign_rank);
+			RankAcc A = {~0u, 0u, 0u};
+			emit_slice(a, b, clamp_avail(B.end_bits, gs << 6), T, r0, d, k, cum, A, ones_w, sign_w);
+			acc_flush(A, ones_w, sign_w);
 		}
 	}
 }
