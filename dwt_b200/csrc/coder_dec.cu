@@ -569,11 +569,41 @@ __global__ void __launch_bounds__(XW_WARPS * 32) dec_extend_walk_kernel(const u3
 		__syncwarp();
 		if (lane == 0) { // the serial part: positions only
 			u32 state = it.y;
-			for (int t = 0; t < WS; ++t) {
-				sentry[t] = (unsigned short)state;
-				const u64 b2 = ((gs0 + t) << 6) < end_bits + 64 ? sw[t + 1] : 0ull; // load_slice's rule for the second word
-				const u32 x = slice_exit_lut(lut, sw[t], b2, clamp_avail(end_bits, (gs0 + t) << 6), state);
-				state = x == PDEAD ? 1u : x; // a dead chain restarts at class 1's seed offset with order 0 (dec_scan_kernel)
+			if (((gs0 + WS + 4) << 6) < end_bits) {
+				// The window and everything a token of it can touch lie inside the stream.  The walk is ONE dependent chain
+				// (measured: ~700 tokens and 125 000 cycles per listed window, 180 cycles per token through slice_exit_lut),
+				// so it is written for the length of that chain: the slice's words in registers, a token's length straight
+				// from the unary prefix (u zeros, the one, e = k + u payload bits, the sign: 2u + k + 2 bits), no end-of-stream
+				// bookkeeping, no table (the listed windows are the ones with orders well above 0).
+				const u32 *w32 = reinterpret_cast<const u32 *>(sw);
+				int d = (int)(state & 63u), k = (int)(state >> 6);
+				u32 w0 = w32[0], w1 = w32[1];
+				for (int t = 0; t < WS; ++t) {
+					const u32 w2 = w32[2 * t + 2], w3 = w32[2 * t + 3]; // the next slice's words (independent of the chain)
+					sentry[t] = (unsigned short)((u32)d | ((u32)k << 6));
+					do {
+						const u32 bits = __funnelshift_r(d < 32 ? w0 : w1, d < 32 ? w1 : w2, d);
+						const int u = __ffs((int)bits) - 1; // -1: no one within 32 bits
+						const int e = k + u;
+						if (bits == 0u || e > 31) { // dead: restart at class 1's seed offset with order 0 in the next slice
+							d = 64 + 1;
+							k = 0;
+							break;
+						}
+						d += 2 * u + k + 2;
+						k = max(e - 2, 0);
+					} while (d < 64);
+					d -= 64;
+					w0 = w2;
+					w1 = w3;
+				}
+			} else {
+				for (int t = 0; t < WS; ++t) {
+					sentry[t] = (unsigned short)state;
+					const u64 b2 = ((gs0 + t) << 6) < end_bits + 64 ? sw[t + 1] : 0ull; // load_slice's rule for the second word
+					const u32 x = slice_exit_lut(lut, sw[t], b2, clamp_avail(end_bits, (gs0 + t) << 6), state);
+					state = x == PDEAD ? 1u : x; // a dead chain restarts at class 1's seed offset with order 0 (dec_scan_kernel)
+				}
 			}
 		}
 		__syncwarp();

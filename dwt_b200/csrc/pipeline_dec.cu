@@ -318,6 +318,15 @@ extern "C" int dwt_ctx_decode_resident(dwt_ctx *c, int pixels_max, struct dwt_st
 		CUDA_OK(cudaMemcpyAsync(h_state, c->dstate.p, sizeof(DecState), cudaMemcpyDeviceToHost, st));
 		CUDA_OK(cudaEventRecord(c->ev[1], st));
 		CUDA_OK(ctx_stream_sync(c));
+		if (getenv("DWT_DEBUG")) { // windows each lineage pass walked
+			u32 cnt[16];
+			if (cudaMemcpy(cnt, b.ext_count, sizeof(cnt), cudaMemcpyDeviceToHost) == cudaSuccess) {
+				fprintf(stderr, "lineage: windows walked per pass:");
+				for (int t = 0; t < 16; ++t)
+					fprintf(stderr, " %u", cnt[t]);
+				fprintf(stderr, " (of %zu)\n", nwin);
+			}
+		}
 		if (h_state->guard_tripped) {
 			dwt_set_error("decoder: the resolver's iteration guard fired (code %d): internal error", h_state->guard_tripped);
 			return -1;
