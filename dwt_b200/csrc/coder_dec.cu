@@ -788,7 +788,8 @@ __device__ __forceinline__ int walk_events_t(const u32 *lut, u64 a, u64 b, int a
 		const int L = u + 1 + e;
 		if (e > 31 || (CHECKED && d + L > avail))
 			return EV_STOP; // the token cannot be read completely (vli.h:88-95): decoding ends
-		const u32 payload = window_at(a, b, d + u + 1) & ((1u << e) - 1u);
+		// the payload lies inside the first window for all but the long runs (u + 1 + e <= 32)
+		const u32 payload = (L <= 32 ? bits >> (u + 1) : window_at(a, b, d + u + 1)) & ((1u << e) - 1u);
 		const u32 n = (1u << e) - (1u << k) + payload;
 		const int kn = e >= 2 ? e - 2 : 0;
 		const u32 room = T - cum;
