@@ -15,7 +15,6 @@
 #include "lift.cuh"
 
 #include <atomic>
-#include <stdlib.h>
 #include <type_traits>
 
 namespace {
