@@ -33,21 +33,6 @@ __device__ __forceinline__ int clamp_u8(int x) // clamp to 0..255 in one instruc
 	return __vimin_s32_relu(x, 255);
 }
 
-// x - (a + b) / 2 and x - (a + b) / 4 with C's truncating division (cdf53.h:12-16, 49-55).  Truncation is symmetric, so the
-// quotient of the NEGATED sum is added instead: the shift then rides on the add (LEA.HI.SX32), one instruction less per
-// sample than subtracting the quotient of the sum.
-__device__ __forceinline__ int sub_half(int x, int a, int b)
-{
-	const int n = -a - b;
-	return x + ((n + (int)((u32)n >> 31)) >> 1);
-}
-
-__device__ __forceinline__ int sub_quarter(int x, int a, int b)
-{
-	const int n = -a - b;
-	return x + ((n + (int)((u32)(n >> 31) >> 30)) >> 2);
-}
-
 template <int MODE>
 struct FwdTraits {
 	static constexpr int NC = MODE == 0 ? 3 : 1;
@@ -167,8 +152,8 @@ __device__ __forceinline__ void fwd_hlift(int (&v)[NC][4], const HPred &hp)
 	for (int c = 0; c < NC; ++c) {
 		const int X0 = v[c][0], X1 = v[c][1], X2 = v[c][2], X3 = v[c][3];
 		const int X4 = __shfl_down_sync(FULLMASK, X0, 1);
-		const int d1 = hp.d1_int ? sub_half(X1, X0, X2) : X1 - X0; // x+1 == N-1 (N even); garbage beyond the row
-		const int d3 = hp.d3_int ? sub_half(X3, X2, X4) : X3 - X2;
+		const int d1 = hp.d1_int ? X1 - (X0 + X2) / 2 : X1 - X0; // x+1 == N-1 (N even); garbage beyond the row
+		const int d3 = hp.d3_int ? X3 - (X2 + X4) / 2 : X3 - X2;
 		const int dm1 = __shfl_up_sync(FULLMASK, d3, 1);
 		// x == 0: first sample; x == N-1 (N odd): the tail even sample is not updated (cdf53.h:21)
 		const int s0 = hp.s0_first ? X0 + d1 / 2 : (hp.s0_upd ? X0 + (dm1 + d1) / 4 : X0);
@@ -204,36 +189,31 @@ __device__ __forceinline__ void fwd_body(const LiftLevel &p, const int y0, const
 	hp.s0_upd = HI || x + 1 <= W - 1;
 	hp.s2_upd = HI || x + 3 <= W - 1;
 
-	// vertical window: e = row-lifted current even row, dp = vertical detail of the odd row above.
-	// Every row the item starts with -- the two halo rows above, its first row, and the four rows of the prefetch
-	// window (r+1, r+2 in no / ne, r+3, r+4 in no2 / ne2) -- is requested before the first of them is used: an item then
-	// waits for memory once.  (Requested one after the other, each behind the arithmetic of the row in front, the item
-	// start cost four DRAM latencies: 29 % of the level-1 kernel's stall samples.)  Rows are clamped to the image, so the
-	// halo loads of the first segment are harmless.
+	// vertical window: e = row-lifted current even row, dp = vertical detail of the odd row above
 	int e[NC][4], dp[NC][4];
-	Raw<MODE> raw, rm2, rm1, no, ne, no2, ne2;
-	fwd_load<MODE>(p, ch, y0 - 2, x, fast, rm2);
-	fwd_load<MODE>(p, ch, y0 - 1, x, fast, rm1);
+	Raw<MODE> raw;
 	fwd_load<MODE>(p, ch, y0, x, fast, raw);
-	fwd_load<MODE>(p, ch, y0 + 1, x, fast, no);
-	fwd_load<MODE>(p, ch, y0 + 2, x, fast, ne);
-	fwd_load<MODE>(p, ch, y0 + 3, x, fast, no2);
-	fwd_load<MODE>(p, ch, y0 + 4, x, fast, ne2);
 	fwd_expand<MODE>(raw, e);
 	fwd_hlift<NC>(e, hp);
-	{
-		// computed for the first segment as well (from clamped rows) and dropped there: a branch around it would let the
-		// compiler sink the two halo loads into the branch, behind the first row's arithmetic
+	if (y0 > 0) {
 		int m2[NC][4], m1[NC][4];
-		fwd_expand<MODE>(rm2, m2);
+		fwd_load<MODE>(p, ch, y0 - 2, x, fast, raw);
+		fwd_expand<MODE>(raw, m2);
 		fwd_hlift<NC>(m2, hp);
-		fwd_expand<MODE>(rm1, m1);
+		fwd_load<MODE>(p, ch, y0 - 1, x, fast, raw);
+		fwd_expand<MODE>(raw, m1);
 		fwd_hlift<NC>(m1, hp);
 #pragma unroll
 		for (int c = 0; c < NC; ++c)
 #pragma unroll
 			for (int k = 0; k < 4; ++k)
-				dp[c][k] = y0 > 0 ? sub_half(m1[c][k], m2[c][k], e[c][k]) : 0; // y0-1 is an interior odd row
+				dp[c][k] = m1[c][k] - (m2[c][k] + e[c][k]) / 2; // y0-1 is an interior odd row
+	} else {
+#pragma unroll
+		for (int c = 0; c < NC; ++c)
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				dp[c][k] = 0;
 	}
 	int mx[NC];
 #pragma unroll
@@ -241,6 +221,13 @@ __device__ __forceinline__ void fwd_body(const LiftLevel &p, const int y0, const
 		mx[c] = 0;
 
 	const int xl = x >> 1, xh = w2 + (x >> 1);
+	// raw rows are fetched two iterations ahead (r+1, r+2 in no / ne, r+3, r+4 in no2 / ne2): one iteration of
+	// distance left the first use of a row waiting on DRAM for half of all stall samples
+	Raw<MODE> no, ne, no2, ne2;
+	fwd_load<MODE>(p, ch, y0 + 1, x, fast, no);
+	fwd_load<MODE>(p, ch, y0 + 2, x, fast, ne);
+	fwd_load<MODE>(p, ch, y0 + 3, x, fast, no2);
+	fwd_load<MODE>(p, ch, y0 + 4, x, fast, ne2);
 	// one row pair.  STEADY (interior strips only): not the first pair, rows r+3 / r+4 exist and are prefetched --
 	// no clamp, no boundary rule, no branch in the body; this is what almost every iteration runs
 	auto step = [&](const int r, auto steady_tag) {
@@ -266,7 +253,7 @@ __device__ __forceinline__ void fwd_body(const LiftLevel &p, const int y0, const
 			if (v_int) {
 #pragma unroll
 				for (int k = 0; k < 4; ++k) {
-					D[k] = sub_half(o[c][k], e[c][k], f[c][k]);
+					D[k] = o[c][k] - (e[c][k] + f[c][k]) / 2;
 					S[k] = e[c][k] + (dp[c][k] + D[k]) / 4;
 				}
 			} else {
@@ -319,66 +306,13 @@ __device__ __forceinline__ void fwd_body(const LiftLevel &p, const int y0, const
 			}
 		}
 	};
-	int r = y0;
-	if constexpr (HI) {
-		// Interior strips.  The first row pair of the image is the only one in front of the steady ones.  Steady row pairs
-		// run two at a time with the roles of the rotating windows written out -- the pair (e, dp) feeds (f, D), which feeds
-		// (e, dp) again, and each half refills the raw rows it has just expanded (rows r + 5, r + 6) -- so nothing is moved
-		// between registers, stores are predicated instead of branched around, and max |detail| is kept as a running
-		// max and min instead of an abs per sample.
-		if (r == 0 && r < y1) {
+#pragma unroll 1
+	for (int r = y0; r < y1; r += 2) {
+		if (HI && r > 0 && r + 6 < H)
+			step(r, std::true_type());
+		else
 			step(r, std::false_type());
-			r += 2;
-		}
-		int f[NC][4], D[NC][4], hi[NC], lo[NC];
-#pragma unroll
-		for (int c = 0; c < NC; ++c)
-			hi[c] = lo[c] = 0;
-		auto half = [&](const int rr, int(&ei)[NC][4], int(&dpi)[NC][4], int(&eo)[NC][4], int(&dpo)[NC][4], Raw<MODE> &ro,
-		                Raw<MODE> &re) {
-			int o[NC][4];
-			fwd_expand<MODE>(ro, o);
-			fwd_expand<MODE>(re, eo);
-			fwd_load<MODE, true>(p, ch, rr + 5, x, true, ro);
-			fwd_load<MODE, true>(p, ch, rr + 6, x, true, re);
-			fwd_hlift<NC>(o, hp);
-			fwd_hlift<NC>(eo, hp);
-			const size_t lo_row = (size_t)(rr >> 1), hi_row = (size_t)(h2 + (rr >> 1));
-#pragma unroll
-			for (int c = 0; c < NC; ++c) {
-				const int cc = MODE == 2 ? ch : c;
-				int S[4];
-#pragma unroll
-				for (int k = 0; k < 4; ++k) {
-					dpo[c][k] = sub_half(o[c][k], ei[c][k], eo[c][k]);
-					S[k] = ei[c][k] + (dpi[c][k] + dpo[c][k]) / 4;
-				}
-				int *ll = (int *)p.out + (size_t)cc * p.out_chan_stride + lo_row * p.out_pitch;
-				int *pl = p.pyr + (size_t)cc * p.pyr_chan_stride + lo_row * p.pyr_pitch;
-				int *ph = p.pyr + (size_t)cc * p.pyr_chan_stride + hi_row * p.pyr_pitch;
-				if (full) {
-					*reinterpret_cast<int2 *>(ll + xl) = make_int2(S[0], S[2]);                 // LL
-					*reinterpret_cast<int2 *>(pl + xh) = make_int2(S[1], S[3]);                 // HL
-					*reinterpret_cast<int2 *>(ph + xl) = make_int2(dpo[c][0], dpo[c][2]);       // LH
-					*reinterpret_cast<int2 *>(ph + xh) = make_int2(dpo[c][1], dpo[c][3]);       // HH
-				}
-				hi[c] = max(max(hi[c], max(S[1], S[3])), max(max(dpo[c][0], dpo[c][1]), max(dpo[c][2], dpo[c][3])));
-				lo[c] = min(min(lo[c], min(S[1], S[3])), min(min(dpo[c][0], dpo[c][1]), min(dpo[c][2], dpo[c][3])));
-			}
-		};
-#pragma unroll 1
-		for (; r + 2 < y1 && r + 8 < H; r += 4) {
-			half(r, e, dp, f, D, no, ne);
-			half(r + 2, f, D, e, dp, no2, ne2);
-		}
-		// the halo lanes compute garbage in their outer columns: only lanes that store count
-#pragma unroll
-		for (int c = 0; c < NC; ++c)
-			mx[c] = max(mx[c], full ? max(hi[c], -lo[c]) : 0);
 	}
-#pragma unroll 1
-	for (; r < y1; r += 2)
-		step(r, std::false_type());
 #pragma unroll
 	for (int c = 0; c < NC; ++c) {
 		const int m = __reduce_max_sync(FULLMASK, mx[c]);
