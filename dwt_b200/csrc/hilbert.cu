@@ -423,13 +423,13 @@ __global__ void __launch_bounds__(256) reconstruct_kernel(const __grid_constant_
 
 // ------------------------------------------------------------------------------------------------ TMA-staged full cells
 //
-// A full cell is a 32 x 32 x C box of the pyramid: exactly what the tensor memory accelerator moves.  One
-// cp.async.bulk.tensor per cell brings the box into shared memory (128-byte swizzle, so that the curve-ordered reads
-// below spread over the banks), an mbarrier tells the warp when it has landed, and the next cell's box is already in
+// One channel of a full cell is a 32 x 32 x 1 box of the pyramid: exactly what the tensor memory accelerator moves.  One
+// cp.async.bulk.tensor per (cell, channel) brings the box into shared memory (128-byte swizzle, so that the curve-ordered
+// reads below spread over the banks), an mbarrier tells the warp when it has landed, and the next box is already in
 // flight in the warp's second buffer.  Lane k then owns the cell's k-th group of 32 curve-consecutive coefficients and
 // turns them into bit-plane words with a 16 x 16 bit-matrix transpose in registers (bitslice.cuh) instead of one warp
 // ballot per plane and group: ~6 instead of ~30 warp instructions per group and channel.  Every plane row of the cell
-// leaves as one 128-byte run.  The inverse (reconstruct) mirrors it and sends the cell back with a TMA store.
+// leaves as one 128-byte run.  The inverse (reconstruct) mirrors it and sends each box back with a TMA store.
 // Requirements: rows 16-byte aligned in HBM (width % 4 == 0), at most 15 bit-planes; everything else takes the
 // ballot kernels above.
 
