@@ -20,6 +20,7 @@ def table(mode, gz, *extra):
 d = json.load(open(os.path.join(P, "r02_bench_n1.json")))
 s0 = json.load(open(os.path.join(P, "r02_start_bench_n1.json")))
 n8 = json.load(open(os.path.join(P, "r02_bench_n8.json")))
+n2 = json.load(open(os.path.join(P, "r02_bench_n2.json")))
 ref = json.load(open(os.path.join(P, "r02_bench_reference_arm.json")))
 L = table("launches", "r02_launches_bench_steps2.csv.gz", "29")
 K = table("kernels", "r02_ncu_top_raw.csv.gz")
@@ -55,6 +56,7 @@ config says otherwise.  Artefacts in this directory (gpurun calls `tools/gpu_rou
 * `r02_ncu_top_raw.csv.gz` -- `ncu --set full --clock-control none`, raw page, every kernel of one encode + decode
   (`python tests/gpu_dec_once.py 7680 4320 1`, commit `58d9376`; later commits changed `dec_extend_walk_kernel`, `dec_resolve_kernel`
   and `lift_fwd_kernel` only); `traffic.json` -- DRAM bytes per stage summed from it (`summarize.py traffic`);
+* `r02_bench_n2.json` -- the bench under `torch.distributed.run` on 2 GPUs of one box at the final commit;
 * `r02_bench_n8.json` -- the bench under `torch.distributed.run` on the 8 GPUs of one box (session start commit `097101a`: what it
   shows is a host property, see below);
 * `r02_sass_tma.txt` -- SASS excerpt of the TMA kernels (`UTMALDG.3D`, `UTMASTG.3D`, `SYNCS.ARRIVE.TRANS64`, `SYNCS.PHASECHK`);
@@ -96,6 +98,12 @@ around them.  Lifting against BASELINE.json's target (>= 0.50): forward **{d['li
 | 512 images of 1920x1080 through `dwt_pool`, host buffers | {c('batch_1080p','encode_images_s','decode_images_s','encode_mpx_s','decode_mpx_s')} |
 
 A capped encode no longer costs a lossless one: coder stage {cfg['8k_cap_64KiB']['encode_coder_ms']:.2f} ms at 64 KiB against {d['stages']['enc_coder']['ms']:.2f} ms lossless (the reference also stops at the cap).
+
+## N = 2 (one box, final commit, `r02_bench_n2.json`)
+
+Device resident {n2['value']:.0f} Mpixel/s = **{n2['value']/d['value']/2:.2f}** of 2 x the N = 1 value; end to end {n2['e2e']['value']:.0f} Mpixel/s =
+{n2['e2e']['staging_gbs_per_direction']} GB/s per direction = {n2['e2e']['fraction_of_staging_ceiling']} of that box's staging ceiling ({n2['e2e']['staging_ceiling_gbs_per_direction']} GB/s per direction for both GPUs
+together, measured in the run; 24 vCPUs).  Batch of 1024 images of 1920x1080: encode {n2['configs']['batch_1080p']['encode_images_s']:.0f}, decode {n2['configs']['batch_1080p']['decode_images_s']:.0f} images/s.
 
 ## N = 8 (one box, `r02_bench_n8.json`)
 
