@@ -84,6 +84,46 @@ def test_oracle_against_reference_binaries(oracle):
                 assert a.shape == b.shape and np.array_equal(a, b)
 
 
+def test_oracle_sweep_against_reference_binaries(oracle):
+    """a wider sweep than the pins: odd geometries (incl. one dimension at the minimum of 8), gray and colour, photo / noise /
+    sparse / smooth content, every capacity class and PIXELS arguments -- restatement against the unmodified programs"""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    rng = np.random.default_rng(20261018)
+    shapes = [(8, 8), (9, 8), (8, 31), (17, 16), (33, 65), (64, 64), (129, 47), (200, 8), (96, 135), (255, 33)]
+    n = 0
+    for i, (w, h) in enumerate(shapes):
+        kind = i % 4
+        if kind == 0:
+            img = oracle.synth(w, h, "photo", 100 + i)
+        elif kind == 1:
+            img = oracle.synth(w, h, "noise", 100 + i)
+        elif kind == 2:   # sparse: long zero runs, high Rice orders
+            img = (rng.integers(0, 256, (h, w, 3)) * (rng.random((h, w, 3)) < 0.04)).astype(np.uint8)
+        else:             # smooth: mostly refinement bits
+            img = np.clip(np.cumsum(rng.integers(-2, 3, (h, w, 3)), axis=1) + 128, 0, 255).astype(np.uint8)
+        if i % 3 == 2:
+            img = np.ascontiguousarray(img[:, :, 1])  # 'W5' gray
+        full = oracle.ref_encode(img)
+        assert oracle.encode(img)[0] == full, (w, h, kind)
+        caps = sorted({1, 5, 6, 7, 8, 12, len(full) // 3, len(full) - 1, len(full), len(full) + 7})
+        for cap in caps:
+            if cap <= 0:
+                continue
+            s = oracle.ref_encode(img, cap)
+            assert oracle.encode(img, cap)[0] == s, (w, h, kind, cap)
+            for px in (None, 16, 64, w * h // 4, w * h):
+                if cap < 6 and px is not None:
+                    continue
+                a = oracle.decode(s) if px is None else oracle.decode(s, px)
+                b = oracle.ref_decode(s) if px is None else oracle.ref_decode(s, px)
+                assert (a is None) == (b is None), (w, h, kind, cap, px)
+                if a is not None:
+                    assert a.shape == b.shape and np.array_equal(a, b), (w, h, kind, cap, px)
+                n += 1
+    assert n > 300
+
+
 def test_smpte_pins(oracle):
     path = os.path.join(os.path.dirname(oracle.LIB_PATH), "_ref", "smpte.pnm")
     if not os.path.exists(path):
