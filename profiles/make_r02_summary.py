@@ -24,6 +24,7 @@ n2 = json.load(open(os.path.join(P, "r02_bench_n2.json")))
 ref = json.load(open(os.path.join(P, "r02_bench_reference_arm.json")))
 L = table("launches", "r02_launches_bench_steps2.csv.gz", "29")
 K = table("kernels", "r02_ncu_top_raw.csv.gz")
+KL = table("kernels", "r02_ncu_late_raw.csv.gz")
 KT = open(os.path.join(P, "r02_kernel_times.txt")).read()
 rows = []
 for k, name in [("lift_fwd", "forward lifting (colour fused)"), ("linearize", "linearise (Hilbert gather + bit-slicing)"),
@@ -55,7 +56,7 @@ config says otherwise.  Artefacts in this directory (gpurun calls `tools/gpu_rou
   put the forward lifting body back: `lift_fwd_kernel<0>` 134 -> 129 us);
 * `r02_ncu_top_raw.csv.gz` -- `ncu --set full --clock-control none`, raw page, every kernel of one encode + decode
   (`python tests/gpu_dec_once.py 7680 4320 1`, commit `58d9376`; later commits changed `dec_extend_walk_kernel`, `dec_resolve_kernel`
-  and `lift_fwd_kernel` only); `traffic.json` -- DRAM bytes per stage summed from it (`summarize.py traffic`);
+  and `lift_fwd_kernel` only: `r02_ncu_late_raw.csv.gz` holds the same page for those at the final commit); `traffic.json` -- DRAM bytes per stage summed from it (`summarize.py traffic`);
 * `r02_bench_n2.json` -- the bench under `torch.distributed.run` on 2 GPUs of one box at the final commit;
 * `r02_bench_n8.json` -- the bench under `torch.distributed.run` on the 8 GPUs of one box (session start commit `097101a`: what it
   shows is a host property, see below);
@@ -170,6 +171,9 @@ coefficient.
 """ + L + """
 ## per-kernel ncu page of one encode + decode (commit `58d9376`)
 
-""" + K
+""" + K + """
+## the same page for the kernels that changed after that capture (final commit, `r02_ncu_late_raw.csv.gz`)
+
+""" + KL
 open(os.path.join(P, "r02_summary.md"), "w").write(txt)
 print("written", len(txt))
